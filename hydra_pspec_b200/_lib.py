@@ -1,0 +1,98 @@
+"""ctypes binding of libhydra_pspec_b200.so (C ABI: include/hydra_pspec_b200.h)."""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "csrc" / "libhydra_pspec_b200.so"
+
+HP_RNG_INJECTED, HP_RNG_PHILOX = 0, 1
+HP_KEEP_CR, HP_KEEP_FG, HP_KEEP_CHISQ = 1, 2, 4
+(HP_BUF_PS, HP_BUF_LNPOST, HP_BUF_CR, HP_BUF_FG, HP_BUF_CHISQ, HP_BUF_LAST_CR, HP_BUF_LAST_FG,
+ HP_BUF_PS_CUR) = range(8)
+HP_NUM_KERNEL_CLASSES = 6
+
+
+class HPConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int), ("nchains", C.c_int), ("ntimes", C.c_int), ("nfreqs", C.c_int),
+        ("nmodes", C.c_int), ("rng_mode", C.c_int), ("cg_compat", C.c_int), ("refresh_omega", C.c_int),
+        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int),
+        ("seed", C.c_uint64), ("stream", C.c_void_p),
+    ]
+
+
+class HydraLibError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_SIGNATURES = {
+    "hp_engine_create": (C.c_int, [C.POINTER(HPConfig), C.POINTER(C.c_void_p)]),
+    "hp_engine_destroy": (C.c_int, [C.c_void_p]),
+    "hp_engine_load_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_engine_set_draws": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hp_engine_run": (C.c_int, [C.c_void_p, C.c_int]),
+    "hp_engine_gcr": (C.c_int, [C.c_void_p]),
+    "hp_engine_sync": (C.c_int, [C.c_void_p]),
+    "hp_engine_iterations_done": (C.c_int, [C.c_void_p]),
+    "hp_engine_rewind": (C.c_int, [C.c_void_p]),
+    "hp_engine_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "hp_engine_read_signal_S": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hp_engine_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hp_engine_kernel_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hp_engine_launch_count": (C.c_longlong, [C.c_void_p]),
+    "hp_kernel_class_name": (C.c_char_p, [C.c_int]),
+    "hp_sample_S": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_fourier_operator": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "hp_test_zgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_void_p]),
+    "hp_test_chol_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_last_error": (C.c_char_p, []),
+    "hp_version": (C.c_char_p, []),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded library.  Fails loudly when it has not been built (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise HydraLibError(
+                f"{LIB_PATH} not found: build it with hydra_pspec_b200/csrc/build.sh "
+                "(hydra_pspec_b200 has no CPU fallback)")
+        L = C.CDLL(os.fspath(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise HydraLibError(f"hydra_pspec_b200 error {rc}: {lib().hp_last_error().decode()}")
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,660 @@
+// hp_engine.cu -- chain engine and C ABI (include/hydra_pspec_b200.h).
+//
+// One engine holds `nchains` independent baselines of identical shape resident in HBM and
+// advances all of them one Gibbs iteration per step with a fixed sequence of batched kernels
+// (hp_kernels.cu).  The host only enqueues launches; nothing is read back between iterations.
+#include "../../include/hydra_pspec_b200.h"
+#include "hp_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(HP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+    return e;
+}
+
+// A[t][x] *= w[x]
+__global__ void k_mask_cols(double* A, const double* w, int rows, int n) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)rows * n) return;
+    int x = (int)(e % n);
+    A[2 * e] *= w[x];
+    A[2 * e + 1] *= w[x];
+}
+
+// Bmat[x][k] (k < n) = conj(U[k][x])   (Q = U^H: delay eigenbasis of a stationary S)
+__global__ void k_basis_fourier(double* Bmat, const double* U, int n, int Np) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    int x = (int)(e / n), k = (int)(e % n);
+    Bmat[2 * ((size_t)x * Np + k)] = U[2 * ((size_t)k * n + x)];
+    Bmat[2 * ((size_t)x * Np + k) + 1] = -U[2 * ((size_t)k * n + x) + 1];
+}
+// Bmat[x][k] = Q[x][k]
+__global__ void k_basis_general(double* Bmat, const double* Q, int n, int Np) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    int x = (int)(e / n), k = (int)(e % n);
+    Bmat[2 * ((size_t)x * Np + k)] = Q[2 * e];
+    Bmat[2 * ((size_t)x * Np + k) + 1] = Q[2 * e + 1];
+}
+// Bmat[x][n + j] = F[x][j];  Ft[j][x] = F[x][j]
+__global__ void k_basis_fg(double* Bmat, double* Ft, const double* F, int n, int m, int Np) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * m) return;
+    int x = (int)(e / m), j = (int)(e % m);
+    double fr = F[2 * e], fi = F[2 * e + 1];
+    Bmat[2 * ((size_t)x * Np + n + j)] = fr;
+    Bmat[2 * ((size_t)x * Np + n + j) + 1] = fi;
+    if (Ft) { Ft[2 * ((size_t)j * n + x)] = fr; Ft[2 * ((size_t)j * n + x) + 1] = fi; }
+}
+// per-channel noise vectors:  ni = w * ninv,  nu = sqrt(ni)
+__global__ void k_noise_vectors(const double* w, const double* ninv, double* ni, double* nu, int n) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    double v = w[x] * ninv[x];
+    ni[x] = v;
+    nu[x] = sqrt(v);
+}
+// lam[k] = sqrt(lamsq[k]) (k<n), 1 (fg rows), 0 (padding);  ps[k] = n * lamsq[k]
+__global__ void k_init_lam(double* lam, double* ps, const double* lamsq, int n, int N, int Np) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Np) return;
+    if (k < n) { lam[k] = sqrt(lamsq[k]); if (ps) ps[k] = (double)n * lamsq[k]; }
+    else lam[k] = k < N ? 1.0 : 0.0;
+}
+__global__ void k_scale_vec(double* out, const double* in, double s, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[k] * s;
+}
+
+inline unsigned nblocks(long long tot, int bs = 256) { return (unsigned)((tot + bs - 1) / bs); }
+
+struct Basis {
+    double* Bmat = nullptr;  // [C][n][Np]
+    double* Gp = nullptr;    // [C][tri][2048]
+    double* Rfix = nullptr;  // [C][Tp][Np]
+    double* wa = nullptr;    // [C][Tp][Np]   injected mode: Q^H omega_a
+    void release() {
+        cudaFree(Bmat); cudaFree(Gp); cudaFree(Rfix); cudaFree(wa);
+        Bmat = Gp = Rfix = wa = nullptr;
+    }
+};
+
+enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4, CLS_NOISE = 5 };
+
+}  // namespace
+
+struct hp_engine {
+    hp_config cfg;
+    int C, T, n, m, N, nblk, Np, Tp, ntiles;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    double *Fop = nullptr, *U = nullptr;
+    Basis bF, b0;
+    double *lam = nullptr, *ps = nullptr;
+    double *wd = nullptr, *w = nullptr, *ninvd = nullptr, *ni = nullptr, *nu = nullptr, *Ft = nullptr, *prior = nullptr;
+    double *Lp = nullptr, *Linvp = nullptr;
+    int* info = nullptr;
+    double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
+    double *Em = nullptr, *Eu = nullptr, *lnp1 = nullptr, *eta = nullptr, *z = nullptr;
+    double* sdraws = nullptr;
+    double *ps_out = nullptr, *lnpost_out = nullptr, *cr_out = nullptr, *fg_out = nullptr, *chisq_out = nullptr;
+    double *Gd = nullptr, *stage = nullptr, *vecn = nullptr;  // set-up scratch
+    std::vector<uint8_t> flagged;  // per chain: any channel flagged
+    std::vector<uint8_t> have_omega;
+    bool any_flagged = false;
+    bool eta_valid = false;
+    int iter = 0;     // Gibbs iterations since the chains were loaded (RNG counter, basis choice)
+    int out_pos = 0;  // cursor in the per-iteration output buffers
+    const double* last_sf = nullptr;  // where the last GCR solve's frequency-space signal lives
+    long long last_sf_bs = 0;         // its batch stride (complex elements)
+    long long launches = 0;
+    // profiling
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_cls;
+    double ms_acc[HP_NUM_KERNEL_CLASSES] = {0};
+    int launch_acc[HP_NUM_KERNEL_CLASSES] = {0};
+
+    void prof_begin(int cls) {
+        if (!cfg.profile || ev_cls.size() >= 8192) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        ev.push_back(a); ev.push_back(b); ev_cls.push_back(cls);
+    }
+    void prof_end(int cls, int nlaunch) {
+        launches += nlaunch;
+        launch_acc[cls] += nlaunch;
+        if (!cfg.profile || ev_cls.empty() || ev_cls.back() != cls) return;
+        cudaEventRecord(ev.back(), st);
+    }
+};
+
+extern "C" {
+
+const char* hp_last_error(void) { return g_err.c_str(); }
+const char* hp_version(void) { return "hydra_pspec_b200 0.1 (sm_100a)"; }
+const char* hp_kernel_class_name(int cls) {
+    static const char* names[HP_NUM_KERNEL_CLASSES] = {"chol", "solve", "transform", "post", "sample", "noise"};
+    return (cls >= 0 && cls < HP_NUM_KERNEL_CLASSES) ? names[cls] : "?";
+}
+
+int hp_engine_destroy(hp_engine* e) {
+    if (!e) return HP_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->st) cudaStreamSynchronize(e->st);
+    for (auto& x : e->ev) cudaEventDestroy(x);
+    e->bF.release(); e->b0.release();
+    double* ptrs[] = {e->Fop, e->U, e->lam, e->ps, e->wd, e->w, e->ninvd, e->ni, e->nu, e->Ft, e->prior, e->Lp, e->Linvp,
+                      e->X, e->Ssc, e->Ppart, e->Sf, e->Wm, e->Tmp, e->Em, e->Eu, e->lnp1, e->eta, e->z, e->sdraws,
+                      e->ps_out, e->lnpost_out, e->cr_out, e->fg_out, e->chisq_out, e->Gd, e->stage, e->vecn};
+    for (double* p : ptrs) cudaFree(p);
+    cudaFree(e->info);
+    if (e->own_stream) cudaStreamDestroy(e->st);
+    delete e;
+    return HP_OK;
+}
+
+static int alloc_basis(hp_engine* e, Basis& b) {
+    size_t C = e->C;
+    CU_TRY(dalloc(&b.Bmat, 2 * C * e->n * e->Np));
+    CU_TRY(dalloc(&b.Gp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles));
+    CU_TRY(dalloc(&b.Rfix, 2 * C * e->Tp * e->Np));
+    if (e->cfg.rng_mode == HP_RNG_INJECTED) CU_TRY(dalloc(&b.wa, 2 * C * e->Tp * e->Np));
+    return HP_OK;
+}
+
+int hp_engine_create(const hp_config* cfg, hp_engine** out) {
+    if (!cfg || !out) return fail(HP_ERR_ARG, "null argument");
+    if (cfg->nchains < 1 || cfg->ntimes < 2 || cfg->nfreqs < 2 || cfg->nmodes < 0 || cfg->max_iters < 1)
+        return fail(HP_ERR_ARG, "hp_engine_create: bad dimensions");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(HP_ERR_CUDA, "no CUDA device: hydra_pspec_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(cfg->device));
+    hp_engine* e = new hp_engine();
+    e->cfg = *cfg;
+    e->C = cfg->nchains; e->T = cfg->ntimes; e->n = cfg->nfreqs; e->m = cfg->nmodes;
+    e->N = e->n + e->m;
+    e->nblk = (e->N + hp::kNB - 1) / hp::kNB;
+    e->Np = e->nblk * hp::kNB;
+    e->ntiles = (e->T + hp::kTT - 1) / hp::kTT;
+    e->Tp = e->ntiles * hp::kTT;
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    if (hp::solve_smem_bytes(e->nblk) > (size_t)max_smem) {
+        delete e;
+        return fail(HP_ERR_SIZE, "Nfreqs + Nmodes = " + std::to_string(e->N) +
+                                     " is too large for the shared-memory resident solve tile on this device");
+    }
+    if (cfg->stream) e->st = (cudaStream_t)cfg->stream;
+    else { CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking)); e->own_stream = true; }
+    const size_t C = e->C, n = e->n, m = e->m, Np = e->Np, Tp = e->Tp, T = e->T, I = cfg->max_iters;
+    int rc;
+#define A_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { std::string msg = std::string(#x) + ": " + cudaGetErrorString(_e); hp_engine_destroy(e); return fail(HP_ERR_CUDA, msg); } } while (0)
+    A_TRY(dalloc(&e->Fop, 2 * n * n)); A_TRY(dalloc(&e->U, 2 * n * n));
+    if ((rc = alloc_basis(e, e->bF)) != HP_OK) { hp_engine_destroy(e); return rc; }
+    if (cfg->general_basis0 && (rc = alloc_basis(e, e->b0)) != HP_OK) { hp_engine_destroy(e); return rc; }
+    A_TRY(dalloc(&e->lam, C * Np)); A_TRY(dalloc(&e->ps, C * n));
+    A_TRY(dalloc(&e->wd, 2 * C * Tp * n)); A_TRY(dalloc(&e->w, C * n)); A_TRY(dalloc(&e->ninvd, C * n));
+    A_TRY(dalloc(&e->ni, C * n)); A_TRY(dalloc(&e->nu, C * n)); A_TRY(dalloc(&e->Ft, 2 * C * (m ? m : 1) * n));
+    A_TRY(dalloc(&e->prior, C * 2 * n));
+    A_TRY(dalloc(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles));
+    A_TRY(dalloc(&e->Linvp, C * e->nblk * hp::kBlkDoubles));
+    A_TRY(dalloc(&e->info, C));
+    A_TRY(dalloc(&e->X, 2 * C * Tp * Np)); A_TRY(dalloc(&e->Ssc, 2 * C * Tp * n));
+    A_TRY(dalloc(&e->Ppart, C * e->ntiles * n)); A_TRY(dalloc(&e->Sf, 2 * C * Tp * n));
+    A_TRY(dalloc(&e->Wm, 2 * C * Tp * n)); A_TRY(dalloc(&e->Tmp, 2 * C * Tp * n));
+    A_TRY(dalloc(&e->Em, C * n)); A_TRY(dalloc(&e->Eu, C * n)); A_TRY(dalloc(&e->lnp1, C * Tp));
+    if (cfg->rng_mode == HP_RNG_PHILOX) { A_TRY(dalloc(&e->eta, 2 * C * Tp * Np)); A_TRY(dalloc(&e->z, 2 * C * Tp * n)); }
+    else A_TRY(dalloc(&e->sdraws, C * I * n));
+    A_TRY(dalloc(&e->ps_out, C * I * n)); A_TRY(dalloc(&e->lnpost_out, C * I));
+    if (cfg->keep & HP_KEEP_CR) A_TRY(dalloc(&e->cr_out, 2 * C * I * T * n));
+    if (cfg->keep & HP_KEEP_FG) A_TRY(dalloc(&e->fg_out, 2 * C * I * T * (m ? m : 1)));
+    if (cfg->keep & HP_KEEP_CHISQ) A_TRY(dalloc(&e->chisq_out, C * I * T * n));
+    A_TRY(dalloc(&e->Gd, 2 * (size_t)e->N * e->N));
+    A_TRY(dalloc(&e->stage, 2 * (T * n > n * n ? T * n : n * n)));
+    A_TRY(dalloc(&e->vecn, 4 * n));
+#undef A_TRY
+    e->flagged.assign(C, 0);
+    e->have_omega.assign(C, 0);
+    hp::launch_fourier_operator(e->Fop, e->n, 1.0, e->st);
+    hp::launch_fourier_operator(e->U, e->n, 1.0 / std::sqrt((double)e->n), e->st);
+    if (cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        hp_engine_destroy(e);
+        return fail(HP_ERR_CUDA, "engine initialisation kernels failed");
+    }
+    *out = e;
+    return HP_OK;
+}
+
+// G = B^H diag(ni) B (packed), Rfix = B^H diag(ni) (w d)^T  for chain c in basis b
+static int build_basis_products(hp_engine* e, Basis& b, int c) {
+    const int n = e->n, N = e->N, Np = e->Np, T = e->T;
+    double* Bm = b.Bmat + 2 * (size_t)c * n * Np;
+    hp::ZgemmArgs g{};
+    g.A = Bm; g.sAi = 1; g.sAk = Np; g.bsA = 0; g.conjA = 1;
+    g.B = Bm; g.sBk = Np; g.sBj = 1; g.bsB = 0; g.conjB = 0;
+    g.C = e->Gd; g.sCi = N; g.sCj = 1; g.bsC = 0;
+    g.dk = e->ni + (size_t)c * n; g.bsD = 0;
+    g.M = N; g.N = N; g.K = n; g.accumulate = 0; g.alpha = 1.0; g.batch = 1;
+    hp::launch_zgemm(g, e->st);
+    hp::launch_pack_lower(e->Gd, N, 0, b.Gp + (size_t)c * hp::tri_blocks(e->nblk) * hp::kBlkDoubles, N, e->nblk, 1, e->st);
+    hp::ZgemmArgs r{};
+    r.A = e->wd + 2 * (size_t)c * e->Tp * n; r.sAi = n; r.sAk = 1; r.conjA = 0;
+    r.B = Bm; r.sBk = Np; r.sBj = 1; r.conjB = 1;
+    r.C = b.Rfix + 2 * (size_t)c * e->Tp * Np; r.sCi = Np; r.sCj = 1;
+    r.dk = e->ni + (size_t)c * n;
+    r.M = T; r.N = N; r.K = n; r.accumulate = 0; r.alpha = 1.0; r.batch = 1;
+    hp::launch_zgemm(r, e->st);
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* flags, const double* fgmodes,
+                         const double* ninv_diag, const double* basis0, const double* lam0sq, const double* ps_prior) {
+    if (!e || !vis || !flags || !ninv_diag || !lam0sq || (e->m > 0 && !fgmodes))
+        return fail(HP_ERR_ARG, "hp_engine_load_chain: null argument");
+    if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "hp_engine_load_chain: chain index out of range");
+    if (e->cfg.general_basis0 && !basis0) return fail(HP_ERR_ARG, "hp_engine_load_chain: general_basis0 set but basis0 is NULL");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const int n = e->n, m = e->m, N = e->N, Np = e->Np, T = e->T, Tp = e->Tp;
+    cudaStream_t st = e->st;
+    std::vector<double> wv(n);
+    bool anyf = false;
+    for (int x = 0; x < n; ++x) { wv[x] = flags[x] ? 1.0 : 0.0; anyf |= !flags[x]; }
+    e->flagged[c] = anyf;
+    e->any_flagged = false;
+    for (auto f : e->flagged) e->any_flagged |= (f != 0);
+    double* wd = e->wd + 2 * (size_t)c * Tp * n;
+    CU_TRY(cudaMemcpyAsync(e->w + (size_t)c * n, wv.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(e->ninvd + (size_t)c * n, ninv_diag, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(wd, vis, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));  // wv is a local
+    k_mask_cols<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->w + (size_t)c * n, T, n);
+    k_noise_vectors<<<nblocks(n), 256, 0, st>>>(e->w + (size_t)c * n, e->ninvd + (size_t)c * n, e->ni + (size_t)c * n,
+                                               e->nu + (size_t)c * n, n);
+    if (ps_prior) CU_TRY(cudaMemcpyAsync(e->prior + (size_t)c * 2 * n, ps_prior, 2 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    else CU_TRY(cudaMemsetAsync(e->prior + (size_t)c * 2 * n, 0, 2 * n * sizeof(double), st));
+    // bases
+    double* BF = e->bF.Bmat + 2 * (size_t)c * n * Np;
+    k_basis_fourier<<<nblocks((long long)n * n), 256, 0, st>>>(BF, e->U, n, Np);
+    if (m > 0) {
+        CU_TRY(cudaMemcpyAsync(e->stage, fgmodes, 2 * (size_t)n * m * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_basis_fg<<<nblocks((long long)n * m), 256, 0, st>>>(BF, e->Ft + 2 * (size_t)c * m * n, e->stage, n, m, Np);
+        if (e->cfg.general_basis0)
+            k_basis_fg<<<nblocks((long long)n * m), 256, 0, st>>>(e->b0.Bmat + 2 * (size_t)c * n * Np, nullptr, e->stage, n, m, Np);
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    if (e->cfg.general_basis0) {
+        CU_TRY(cudaMemcpyAsync(e->stage, basis0, 2 * (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_basis_general<<<nblocks((long long)n * n), 256, 0, st>>>(e->b0.Bmat + 2 * (size_t)c * n * Np, e->stage, n, Np);
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    int rc;
+    if ((rc = build_basis_products(e, e->bF, c)) != HP_OK) return rc;
+    if (e->cfg.general_basis0 && (rc = build_basis_products(e, e->b0, c)) != HP_OK) return rc;
+    // initial spectrum
+    CU_TRY(cudaMemcpyAsync(e->vecn, lam0sq, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_init_lam<<<nblocks(Np), 256, 0, st>>>(e->lam + (size_t)c * Np, e->ps + (size_t)c * n, e->vecn, n, N, Np);
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    e->iter = 0;
+    e->out_pos = 0;
+    e->eta_valid = false;
+    return HP_OK;
+}
+
+int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double* omega_b, const double* s_draws,
+                        int n_draw_iters) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (e->cfg.rng_mode != HP_RNG_INJECTED) return fail(HP_ERR_ARG, "hp_engine_set_draws: engine is not in injected-draw mode");
+    if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "chain index out of range");
+    if ((omega_a == nullptr) != (omega_b == nullptr)) return fail(HP_ERR_ARG, "omega_a and omega_b must both be given or both NULL");
+    if (n_draw_iters > e->cfg.max_iters) return fail(HP_ERR_ARG, "more draw iterations than max_iters");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const int n = e->n, Np = e->Np, T = e->T, Tp = e->Tp;
+    cudaStream_t st = e->st;
+    if (s_draws && n_draw_iters > 0)
+        CU_TRY(cudaMemcpyAsync(e->sdraws + (size_t)c * e->cfg.max_iters * n, s_draws, (size_t)n_draw_iters * n * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+    if (omega_a) {
+        for (int which = 0; which < (e->cfg.general_basis0 ? 2 : 1); ++which) {
+            Basis& b = which ? e->b0 : e->bF;
+            double* Bm = b.Bmat + 2 * (size_t)c * n * Np;
+            // Rfix += B^H nu omega_b
+            CU_TRY(cudaMemcpyAsync(e->stage, omega_b, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+            hp::ZgemmArgs r{};
+            r.A = e->stage; r.sAi = n; r.sAk = 1;
+            r.B = Bm; r.sBk = Np; r.sBj = 1; r.conjB = 1;
+            r.C = b.Rfix + 2 * (size_t)c * Tp * Np; r.sCi = Np; r.sCj = 1;
+            r.dk = e->nu + (size_t)c * n;
+            r.M = T; r.N = e->N; r.K = n; r.accumulate = 1; r.alpha = 1.0; r.batch = 1;
+            hp::launch_zgemm(r, st);
+            CU_TRY(cudaStreamSynchronize(st));
+            // wa = Q^H omega_a
+            CU_TRY(cudaMemcpyAsync(e->stage, omega_a, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+            hp::ZgemmArgs a{};
+            a.A = e->stage; a.sAi = n; a.sAk = 1;
+            a.B = Bm; a.sBk = Np; a.sBj = 1; a.conjB = 1;
+            a.C = b.wa + 2 * (size_t)c * Tp * Np; a.sCi = Np; a.sCj = 1;
+            a.M = T; a.N = n; a.K = n; a.accumulate = 0; a.alpha = 1.0; a.batch = 1;
+            hp::launch_zgemm(a, st);
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+        e->have_omega[c] = 1;
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+// noise term of this iteration (Philox):  eta = B^H (nu * omega_b)
+static void enqueue_noise(hp_engine* e, Basis& b, uint32_t iter) {
+    e->prof_begin(CLS_NOISE);
+    hp::launch_noise_draw(e->z, e->nu, e->T, e->Tp, e->n, e->C, (uint32_t)e->cfg.seed, (uint32_t)(e->cfg.seed >> 32), iter,
+                          nullptr, e->st);
+    hp::ZgemmArgs r{};
+    r.A = e->z; r.sAi = e->n; r.sAk = 1; r.bsA = (long long)e->Tp * e->n;
+    r.B = b.Bmat; r.sBk = e->Np; r.sBj = 1; r.conjB = 1; r.bsB = (long long)e->n * e->Np;
+    r.C = e->eta; r.sCi = e->Np; r.sCj = 1; r.bsC = (long long)e->Tp * e->Np;
+    r.M = e->Tp; r.N = e->N; r.K = e->n; r.accumulate = 0; r.alpha = 1.0; r.batch = e->C;
+    hp::launch_zgemm(r, e->st);
+    e->prof_end(CLS_NOISE, 2);
+}
+
+// GCR step: chol + solve + transform to frequency space.  `b` is the basis in use.
+static void enqueue_gcr(hp_engine* e, Basis& b, double* sf_dst, long long sf_bs) {
+    const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
+    const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : (uint32_t)e->iter;
+    if (philox && (e->cfg.refresh_omega || !e->eta_valid || &b == &e->b0 || e->iter == 1)) {
+        enqueue_noise(e, b, draw_iter);
+        e->eta_valid = true;
+    }
+    e->prof_begin(CLS_CHOL);
+    hp::CholArgs ca{};
+    ca.Gp = b.Gp; ca.lam = e->lam; ca.Lp = e->Lp; ca.Linvp = e->Linvp; ca.info = e->info;
+    ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = e->C;
+    hp::launch_chol(ca, e->st);
+    e->prof_end(CLS_CHOL, 1);
+
+    e->prof_begin(CLS_SOLVE);
+    hp::SolveArgs sa{};
+    sa.Lp = e->Lp; sa.Linvp = e->Linvp; sa.lam = e->lam;
+    sa.Rfix = b.Rfix; sa.eta = philox ? e->eta : nullptr;
+    bool any_omega = false;
+    for (auto h : e->have_omega) any_omega |= (h != 0);
+    sa.wa = (!philox && any_omega) ? b.wa : nullptr;
+    sa.X = e->X; sa.Ssc = e->Ssc; sa.Ppart = e->Ppart;
+    sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = e->C; sa.T = e->T;
+    sa.philox_wa = philox ? 1 : 0;
+    sa.cg_compat = e->cfg.cg_compat;
+    sa.key0 = (uint32_t)e->cfg.seed; sa.key1 = (uint32_t)(e->cfg.seed >> 32); sa.iter = draw_iter;
+    sa.chain_ids = nullptr;
+    hp::launch_solve(sa, e->st);
+    e->prof_end(CLS_SOLVE, 1);
+
+    // s = Q (lam * ytilde), written either to the scratch buffer or straight into the signal_cr slot
+    e->prof_begin(CLS_TRANSFORM);
+    hp::ZgemmArgs t{};
+    t.A = e->Ssc; t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
+    t.B = b.Bmat; t.sBk = 1; t.sBj = e->Np; t.bsB = (long long)e->n * e->Np;
+    t.C = sf_dst; t.sCi = e->n; t.sCj = 1; t.bsC = sf_bs;
+    t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
+    hp::launch_zgemm(t, e->st);
+    e->prof_end(CLS_TRANSFORM, 1);
+    e->last_sf = sf_dst;
+    e->last_sf_bs = sf_bs;
+}
+
+int hp_engine_gcr(hp_engine* e) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    Basis& b = (e->cfg.general_basis0 && e->iter == 0) ? e->b0 : e->bF;
+    enqueue_gcr(e, b, e->Sf, (long long)e->Tp * e->n);
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_engine_run(hp_engine* e, int niter) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (niter < 0 || e->out_pos + niter > e->cfg.max_iters)
+        return fail(HP_ERR_ARG, "hp_engine_run: would exceed max_iters (use hp_engine_rewind)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const size_t n = e->n, m = e->m, T = e->T, Tp = e->Tp, I = e->cfg.max_iters;
+    const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
+    for (int k = 0; k < niter; ++k) {
+        const int it = e->out_pos;
+        const bool general = e->cfg.general_basis0 && e->iter == 0;
+        Basis& b = general ? e->b0 : e->bF;
+        double* sf = e->cr_out ? e->cr_out + 2 * (size_t)it * T * n : e->Sf;
+        const long long sf_bs = e->cr_out ? (long long)(I * T * n) : (long long)(Tp * n);
+        enqueue_gcr(e, b, sf, sf_bs);
+
+        e->prof_begin(CLS_POST);
+        hp::PostArgs pa{};
+        pa.Sf = sf; pa.sf_bs = sf_bs; pa.X = e->X; pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
+        pa.fg_out = e->fg_out ? e->fg_out + 2 * (size_t)it * T * m : nullptr; pa.fg_bs = 2 * (long long)(I * T * m);
+        pa.chisq_out = e->chisq_out ? e->chisq_out + (size_t)it * T * n : nullptr; pa.chisq_bs = (long long)(I * T * n);
+        pa.Wm = e->any_flagged ? e->Wm : nullptr; pa.Rm = nullptr; pa.lnp1 = e->lnp1;
+        pa.n = e->n; pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C;
+        hp::launch_post(pa, e->st);
+        e->prof_end(CLS_POST, 1);
+
+        if (e->any_flagged || general) {
+            e->prof_begin(CLS_TRANSFORM);
+            int nl2 = 0;
+            hp::ZgemmArgs t{};
+            t.sAi = e->n; t.sAk = 1; t.bsA = (long long)Tp * n;
+            t.B = e->U; t.sBk = 1; t.sBj = e->n; t.bsB = 0;
+            t.C = e->Tmp; t.sCi = e->n; t.sCj = 1; t.bsC = (long long)Tp * n;
+            t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
+            if (e->any_flagged) {
+                t.A = e->Wm;
+                hp::launch_zgemm(t, e->st);
+                hp::launch_colsumsq(e->Tmp, e->Em, e->T, e->Tp, e->n, e->C, e->st);
+                nl2 += 2;
+            }
+            if (general) {
+                t.A = sf; t.bsA = sf_bs;
+                hp::launch_zgemm(t, e->st);
+                hp::launch_colsumsq(e->Tmp, e->Eu, e->T, e->Tp, e->n, e->C, e->st);
+                nl2 += 2;
+            }
+            e->prof_end(CLS_TRANSFORM, nl2);
+        }
+
+        e->prof_begin(CLS_SAMPLE);
+        hp::SampleArgs sp{};
+        sp.Ppart = e->Ppart; sp.Eu = e->Eu; sp.Em = e->any_flagged ? e->Em : nullptr;
+        sp.lnp1 = e->lnp1; sp.lnp1_dense = nullptr; sp.prior = e->prior;
+        sp.draws = philox ? nullptr : e->sdraws + (size_t)it * n; sp.draws_bs = (long long)(I * n);
+        sp.ps = e->ps; sp.lam = e->lam;
+        sp.ps_out = e->ps_out + (size_t)it * n; sp.ps_bs = (long long)(I * n);
+        sp.lnpost_out = e->lnpost_out + it; sp.lnpost_bs = (long long)I;
+        sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = e->C;
+        sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
+        sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = (uint32_t)e->iter;
+        sp.chain_ids = nullptr;
+        hp::launch_sample(sp, e->st);
+        e->prof_end(CLS_SAMPLE, 1);
+        e->iter++;
+        e->out_pos++;
+    }
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_engine_sync(hp_engine* e) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+int hp_engine_iterations_done(const hp_engine* e) { return e ? e->iter : -1; }
+int hp_engine_rewind(hp_engine* e) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    e->out_pos = 0;
+    return HP_OK;
+}
+long long hp_engine_launch_count(const hp_engine* e) { return e ? e->launches : -1; }
+
+int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* dst, size_t dst_bytes) {
+    if (!e || !dst) return fail(HP_ERR_ARG, "null argument");
+    if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "chain index out of range");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    const size_t n = e->n, m = e->m, T = e->T, Tp = e->Tp, Np = e->Np, I = e->cfg.max_iters;
+    const bool per_iter = buffer <= HP_BUF_CHISQ;
+    if (per_iter && (iter0 < 0 || niter < 0 || (size_t)(iter0 + niter) > I)) return fail(HP_ERR_ARG, "iteration range out of bounds");
+    const double* src = nullptr;
+    size_t bytes = 0;
+    switch (buffer) {
+        case HP_BUF_PS: src = e->ps_out + ((size_t)c * I + iter0) * n; bytes = (size_t)niter * n * 8; break;
+        case HP_BUF_LNPOST: src = e->lnpost_out + (size_t)c * I + iter0; bytes = (size_t)niter * 8; break;
+        case HP_BUF_CR:
+            if (!e->cr_out) return fail(HP_ERR_ARG, "signal_cr was not kept (cfg.keep)");
+            src = e->cr_out + 2 * ((size_t)c * I + iter0) * T * n; bytes = (size_t)niter * T * n * 16; break;
+        case HP_BUF_FG:
+            if (!e->fg_out) return fail(HP_ERR_ARG, "fg_amps was not kept (cfg.keep)");
+            src = e->fg_out + 2 * ((size_t)c * I + iter0) * T * m; bytes = (size_t)niter * T * m * 16; break;
+        case HP_BUF_CHISQ:
+            if (!e->chisq_out) return fail(HP_ERR_ARG, "chisq was not kept (cfg.keep)");
+            src = e->chisq_out + ((size_t)c * I + iter0) * T * n; bytes = (size_t)niter * T * n * 8; break;
+        case HP_BUF_LAST_CR:
+            if (!e->last_sf) return fail(HP_ERR_ARG, "no GCR solve has run yet");
+            src = e->last_sf + 2 * (size_t)c * e->last_sf_bs; bytes = T * n * 16; break;
+        case HP_BUF_PS_CUR: src = e->ps + (size_t)c * n; bytes = n * 8; break;
+        case HP_BUF_LAST_FG: {
+            bytes = T * m * 16;
+            if (dst_bytes < bytes) return fail(HP_ERR_ARG, "destination too small");
+            if (m == 0) return HP_OK;
+            CU_TRY(cudaMemcpy2D(dst, m * 16, e->X + 2 * ((size_t)c * Tp * Np + n), Np * 16, m * 16, T, cudaMemcpyDeviceToHost));
+            return HP_OK;
+        }
+        default: return fail(HP_ERR_ARG, "unknown buffer id");
+    }
+    if (dst_bytes < bytes) return fail(HP_ERR_ARG, "destination too small");
+    if (bytes) CU_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+int hp_engine_read_signal_S(hp_engine* e, int c, double* dst) {
+    if (!e || !dst) return fail(HP_ERR_ARG, "null argument");
+    if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "chain index out of range");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const int n = e->n;
+    // S = Fop^H diag(ps / n^2) Fop  (pspec.py:464, 313-322)
+    k_scale_vec<<<nblocks(n), 256, 0, e->st>>>(e->vecn + n, e->ps + (size_t)c * n, 1.0 / ((double)n * n), n);
+    hp::ZgemmArgs g{};
+    g.A = e->Fop; g.sAi = 1; g.sAk = n; g.conjA = 1;
+    g.B = e->Fop; g.sBk = n; g.sBj = 1;
+    g.C = e->stage; g.sCi = n; g.sCj = 1;
+    g.dk = e->vecn + n;
+    g.M = n; g.N = n; g.K = n; g.alpha = 1.0; g.batch = 1;
+    hp::launch_zgemm(g, e->st);
+    CU_TRY(cudaStreamSynchronize(e->st));
+    CU_TRY(cudaMemcpy(dst, e->stage, 2 * (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+int hp_engine_info(hp_engine* e, int* info_host) {
+    if (!e || !info_host) return fail(HP_ERR_ARG, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    CU_TRY(cudaMemcpy(info_host, e->info, e->C * sizeof(int), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+int hp_engine_kernel_ms(hp_engine* e, double* ms, int* launches, int reset) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->st));
+    for (size_t i = 0; i < e->ev_cls.size(); ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e->ev[2 * i], e->ev[2 * i + 1]) == cudaSuccess) e->ms_acc[e->ev_cls[i]] += t;
+        cudaEventDestroy(e->ev[2 * i]); cudaEventDestroy(e->ev[2 * i + 1]);
+    }
+    e->ev.clear(); e->ev_cls.clear();
+    for (int i = 0; i < HP_NUM_KERNEL_CLASSES; ++i) {
+        if (ms) ms[i] = e->ms_acc[i];
+        if (launches) launches[i] = e->launch_acc[i];
+        if (reset) { e->ms_acc[i] = 0; e->launch_acc[i] = 0; }
+    }
+    return HP_OK;
+}
+
+int hp_sample_S(int device, int T, int n, const double* s, const double* prior, const double* draws, double* out) {
+    if (!s || !draws || !out || T < 2 || n < 1) return fail(HP_ERR_ARG, "hp_sample_S: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(HP_ERR_CUDA, "no CUDA device: hydra_pspec_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    double *U, *S, *Sk, *Eu, *pr, *dr, *ps, *lam, *lnp1, *psout, *lnp;
+    CU_TRY(dalloc(&U, 2 * (size_t)n * n)); CU_TRY(dalloc(&S, 2 * (size_t)T * n)); CU_TRY(dalloc(&Sk, 2 * (size_t)T * n));
+    CU_TRY(dalloc(&Eu, n)); CU_TRY(dalloc(&pr, 2 * (size_t)n)); CU_TRY(dalloc(&dr, n)); CU_TRY(dalloc(&ps, n));
+    CU_TRY(dalloc(&lam, n + 64)); CU_TRY(dalloc(&lnp1, T)); CU_TRY(dalloc(&psout, n)); CU_TRY(dalloc(&lnp, 1));
+    hp::launch_fourier_operator(U, n, 1.0 / std::sqrt((double)n), 0);
+    CU_TRY(cudaMemcpy(S, s, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice));
+    if (prior) CU_TRY(cudaMemcpy(pr, prior, 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dr, draws, n * sizeof(double), cudaMemcpyHostToDevice));
+    hp::ZgemmArgs t{};
+    t.A = S; t.sAi = n; t.sAk = 1;
+    t.B = U; t.sBk = 1; t.sBj = n;
+    t.C = Sk; t.sCi = n; t.sCj = 1;
+    t.M = T; t.N = n; t.K = n; t.alpha = 1.0; t.batch = 1;
+    hp::launch_zgemm(t, 0);
+    hp::launch_colsumsq(Sk, Eu, T, T, n, 1, 0);
+    hp::SampleArgs sp{};
+    sp.Eu = Eu; sp.lnp1 = lnp1; sp.prior = pr; sp.draws = dr; sp.draws_bs = n;
+    sp.ps = ps; sp.lam = lam; sp.ps_out = psout; sp.ps_bs = n; sp.lnpost_out = lnp; sp.lnpost_bs = 1;
+    sp.n = n; sp.Np = n; sp.T = T; sp.Tp = T; sp.ntiles = 0; sp.nsys = 1; sp.beta_mode = 1; sp.philox = 0;
+    hp::launch_sample(sp, 0);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, psout, n * sizeof(double), cudaMemcpyDeviceToHost));
+    double* ptrs[] = {U, S, Sk, Eu, pr, dr, ps, lam, lnp1, psout, lnp};
+    for (double* p : ptrs) cudaFree(p);
+    return HP_OK;
+}
+
+int hp_fourier_operator(int device, int n, double* out) {
+    if (!out || n < 1) return fail(HP_ERR_ARG, "hp_fourier_operator: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(HP_ERR_CUDA, "no CUDA device: hydra_pspec_b200 has no CPU fallback");
+    CU_TRY(cudaSetDevice(device));
+    double* d;
+    CU_TRY(dalloc(&d, 2 * (size_t)n * n));
+    hp::launch_fourier_operator(d, n, 1.0, 0);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out, d, 2 * (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return HP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,804 @@
+// hp_kernels.cu -- sm_100a kernels of the per-baseline Gibbs hot path.
+//
+// Reference behaviour being reproduced: hydra_pspec/pspec.py (build_matrices :325-374,
+// gcr_fgmodes_1d :151-235, sample_S :67-127, gibbs_step_fgmodes :377-490).  The algebra is
+// re-derived for the GPU: the GCR system is whitened and written in the
+// eigenbasis Q of the current signal covariance S = Q diag(lam^2) Q^H,
+//
+//      M = J + D G D,   G = [Q|F]^H N^-1 [Q|F],   D = diag(lam, 1),   J = diag(1_n, 0_m)
+//
+// so that one iteration needs a Hermitian positive definite factorisation M = L L^H (k_chol)
+// and a two-sided triangular solve for all Ntimes right-hand sides (k_solve); every O(N^3) /
+// O(N^2 T) contraction runs on the FP64 tensor pipe (hp_mma.cuh).
+#include "hp_kernels.cuh"
+#include "hp_math.h"
+#include "hp_mma.cuh"
+
+namespace hp {
+
+// ==========================================================================================
+// small helpers
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kLdBlk = 36;  // leading dim (doubles) of a 32x32 plane in shared memory, == 4 mod 16
+
+// global packed block (2048 doubles: re plane, im plane, ld 32) -> shared planes (ld 36), async
+__device__ __forceinline__ void load_block_async(double* sr, double* si, const double* g) {
+    // 1024 16-byte chunks; 256 threads x 4
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int c = threadIdx.x + 256 * r;
+        int plane = c >> 9, cc = c & 511;
+        int row = cc >> 4, col = (cc & 15) * 2;
+        double* dst = (plane ? si : sr) + row * kLdBlk + col;
+        cp_async16(dst, g + plane * 1024 + row * 32 + col);
+    }
+}
+
+// ==========================================================================================
+// generic zgemm (set-up contractions and v1 basis transforms)
+constexpr int ZG_BM = 64, ZG_BN = 64, ZG_BK = 16;
+constexpr int ZG_LDA = 20;  // 16 + 4
+constexpr int ZG_LDB = 68;  // 64 + 4
+
+__global__ void __launch_bounds__(256) k_zgemm(ZgemmArgs a) {
+    __shared__ double Asr[ZG_BM * ZG_LDA], Asi[ZG_BM * ZG_LDA];
+    __shared__ double Bsr[ZG_BK * ZG_LDB], Bsi[ZG_BK * ZG_LDB];
+    const int b = blockIdx.z;
+    const double* A = a.A + 2 * a.bsA * b;
+    const double* B = a.B + 2 * a.bsB * b;
+    double* C = a.C + 2 * a.bsC * b;
+    const double* dk = a.dk ? a.dk + a.bsD * b : nullptr;
+    const int i0 = blockIdx.y * ZG_BM, j0 = blockIdx.x * ZG_BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = warp >> 2, wc = warp & 3;  // warp tile 32 x 16
+    double cr[4][2][2], ci[4][2][2];
+    warp_zero<4, 2>(cr, ci);
+    const bool a_kfast = a.sAk <= a.sAi;
+    const bool b_jfast = a.sBj <= a.sBk;
+    const double sgnA = a.conjA ? -1.0 : 1.0, sgnB = a.conjB ? -1.0 : 1.0;
+    for (int k0 = 0; k0 < a.K; k0 += ZG_BK) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int e = tid + 256 * r;
+            int i, k;
+            if (a_kfast) { i = e >> 4; k = e & 15; } else { i = e & 63; k = e >> 6; }
+            double xr = 0.0, xi = 0.0;
+            if (i0 + i < a.M && k0 + k < a.K) {
+                const double* p = A + 2 * ((long long)(i0 + i) * a.sAi + (long long)(k0 + k) * a.sAk);
+                xr = p[0]; xi = sgnA * p[1];
+                if (dk) { double d = dk[k0 + k]; xr *= d; xi *= d; }
+            }
+            Asr[i * ZG_LDA + k] = xr; Asi[i * ZG_LDA + k] = xi;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int e = tid + 256 * r;
+            int k, j;
+            if (b_jfast) { k = e >> 6; j = e & 63; } else { k = e & 15; j = e >> 4; }
+            double xr = 0.0, xi = 0.0;
+            if (k0 + k < a.K && j0 + j < a.N) {
+                const double* p = B + 2 * ((long long)(k0 + k) * a.sBk + (long long)(j0 + j) * a.sBj);
+                xr = p[0]; xi = sgnB * p[1];
+            }
+            Bsr[k * ZG_LDB + j] = xr; Bsi[k * ZG_LDB + j] = xi;
+        }
+        __syncthreads();
+        warp_zgemm<4, 2, false, false, false, false>(cr, ci, Asr + 32 * wr * ZG_LDA, Asi + 32 * wr * ZG_LDA, ZG_LDA,
+                                                     Bsr + 16 * wc, Bsi + 16 * wc, ZG_LDB, ZG_BK);
+        __syncthreads();
+    }
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int row = i0 + 32 * wr + 8 * i + g, col = j0 + 16 * wc + 8 * j + 2 * q + e;
+                if (row < a.M && col < a.N) {
+                    double* p = C + 2 * ((long long)row * a.sCi + (long long)col * a.sCj);
+                    double vr = a.alpha * cr[i][j][e], vi = a.alpha * ci[i][j][e];
+                    if (a.accumulate) { vr += p[0]; vi += p[1]; }
+                    p[0] = vr; p[1] = vi;
+                }
+            }
+}
+
+void launch_zgemm(const ZgemmArgs& a, cudaStream_t st) {
+    dim3 grid((a.N + ZG_BN - 1) / ZG_BN, (a.M + ZG_BM - 1) / ZG_BM, a.batch);
+    k_zgemm<<<grid, 256, 0, st>>>(a);
+}
+
+// ==========================================================================================
+__global__ void k_fourier_operator(double* out, int n, double scale) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    int k = (int)(e / n), x = (int)(e % n);
+    long long a = (long long)(k - n / 2) * (long long)(x - n / 2);
+    long long r = a % n;  // exact argument reduction: exp(-2 pi i a / n) depends on a mod n only
+    if (r < 0) r += n;
+    double s, c;
+    sincospi(-2.0 * (double)r / (double)n, &s, &c);
+    out[2 * e] = c * scale;
+    out[2 * e + 1] = s * scale;
+}
+void launch_fourier_operator(double* out, int n, double scale, cudaStream_t st) {
+    long long tot = (long long)n * n;
+    k_fourier_operator<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(out, n, scale);
+}
+
+__global__ void k_pack_lower(const double* dense, long long ld, long long bs, double* packed, int N, int nblk) {
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const double* D = dense + 2 * bs * blockIdx.z;
+    double* P = packed + ((size_t)blockIdx.z * tri_blocks(nblk) + blk_index(bi, bj)) * kBlkDoubles;
+    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
+        int r = e >> 5, c = e & 31;
+        int gi = bi * 32 + r, gj = bj * 32 + c;
+        double xr = 0.0, xi = 0.0;
+        if (gi < N && gj < N) { xr = D[2 * (gi * ld + gj)]; xi = D[2 * (gi * ld + gj) + 1]; }
+        P[e] = xr; P[1024 + e] = xi;
+    }
+}
+void launch_pack_lower(const double* dense, long long ld, long long bs, double* packed, int N, int nblk, int batch,
+                       cudaStream_t st) {
+    k_pack_lower<<<dim3(nblk, nblk, batch), 256, 0, st>>>(dense, ld, bs, packed, N, nblk);
+}
+
+__global__ void k_scale_rows(double* A, const double* d, int rows, int cols, long long ld) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)rows * cols) return;
+    int r = (int)(e / cols), c = (int)(e % cols);
+    A[2 * (r * ld + c)] *= d[r];
+    A[2 * (r * ld + c) + 1] *= d[r];
+}
+void launch_scale_rows(double* A, const double* d, int rows, int cols, long long ld, cudaStream_t st) {
+    long long tot = (long long)rows * cols;
+    k_scale_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, d, rows, cols, ld);
+}
+__global__ void k_fill(double* p, double v, size_t count) {
+    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e < count) p[e] = v;
+}
+void launch_fill(double* p, double v, size_t count, cudaStream_t st) {
+    if (count) k_fill<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(p, v, count);
+}
+
+// ==========================================================================================
+// k_chol: one CTA per system.  Left-looking blocked Cholesky of M = J + D G D with 32x32
+// blocks; M is never materialised (G blocks are scaled by lam on the fly).  Off-diagonal work
+// is DMMA; the 32x32 diagonal factorisation and its triangular inverse are done by all 256
+// threads in shared memory.
+struct CholSmem {
+    double Ar[32 * kLdBlk], Ai[32 * kLdBlk];
+    double Br[32 * kLdBlk], Bi[32 * kLdBlk];
+    double Vr[32 * kLdBlk], Vi[32 * kLdBlk];  // inverse of the current diagonal block
+    double redr[8 * 32], redi[8 * 32];
+};
+
+__global__ void __launch_bounds__(256) k_chol(CholArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CholSmem& s = *reinterpret_cast<CholSmem*>(smem_raw);
+    const int sys = blockIdx.x;
+    const int nblk = a.nblk, Np = nblk * 32;
+    const double* Gp = a.Gp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
+    double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
+    double* Linvp = a.Linvp + (size_t)sys * nblk * kBlkDoubles;
+    const double* lam = a.lam + (size_t)sys * Np;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int ti = warp >> 1, tj = warp & 1;  // warp tile: rows 8 ti .. +8, cols 16 tj .. +16
+    int bad = 0;
+
+    for (int k = 0; k < nblk; ++k) {
+        for (int i = k; i < nblk; ++i) {
+            double cr[1][2][2], ci[1][2][2];
+            warp_zero<1, 2>(cr, ci);
+            for (int j = 0; j < k; ++j) {
+                __syncthreads();
+                load_block_async(s.Ar, s.Ai, Lp + blk_index(i, j) * kBlkDoubles);
+                if (i != k) load_block_async(s.Br, s.Bi, Lp + blk_index(k, j) * kBlkDoubles);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                const double* br = (i != k) ? s.Br : s.Ar;
+                const double* bi = (i != k) ? s.Bi : s.Ai;
+                // acc += L_ij . L_kj^H
+                warp_zgemm<1, 2, false, false, true, true>(cr, ci, s.Ar + 8 * ti * kLdBlk, s.Ai + 8 * ti * kLdBlk, kLdBlk,
+                                                           br + 16 * tj * kLdBlk, bi + 16 * tj * kLdBlk, kLdBlk, 32);
+            }
+            // C = M_ik - acc, M_ik = J + lam_i G_ik lam_k
+            const double* Gb = Gp + blk_index(i, k) * kBlkDoubles;
+            __syncthreads();  // all warps done with the operand buffers
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int r = 8 * ti + g, c = 16 * tj + 8 * j + 2 * q + e;
+                    int gi = 32 * i + r, gj = 32 * k + c;
+                    double sc = lam[gi] * lam[gj];
+                    double vr = sc * Gb[r * 32 + c], vi = sc * Gb[1024 + r * 32 + c];
+                    if (gi == gj && (gi < a.n || gi >= a.N)) vr += 1.0;
+                    s.Ar[r * kLdBlk + c] = vr - cr[0][j][e];
+                    s.Ai[r * kLdBlk + c] = vi - ci[0][j][e];
+                }
+            __syncthreads();
+            if (i == k) {
+                // ---- unblocked Cholesky of the 32x32 diagonal block (lower), in place
+                for (int c = 0; c < 32; ++c) {
+                    if (tid < 32) {
+                        int r = tid;
+                        double piv = s.Ar[c * kLdBlk + c];
+                        if (!(piv > 0.0)) bad = k + 1;
+                        double d = sqrt(piv);
+                        if (r == c) { s.Ar[c * kLdBlk + c] = d; s.Ai[c * kLdBlk + c] = 0.0; }
+                        else if (r > c) { s.Ar[r * kLdBlk + c] /= d; s.Ai[r * kLdBlk + c] /= d; }
+                        else { s.Ar[r * kLdBlk + c] = 0.0; s.Ai[r * kLdBlk + c] = 0.0; }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        int e = tid + 256 * rr;
+                        int r = e >> 5, c2 = e & 31;
+                        if (c2 > c && r >= c2) {
+                            double xr = s.Ar[r * kLdBlk + c], xi = s.Ai[r * kLdBlk + c];
+                            double yr = s.Ar[c2 * kLdBlk + c], yi = s.Ai[c2 * kLdBlk + c];
+                            // A[r][c2] -= x * conj(y)
+                            s.Ar[r * kLdBlk + c2] -= xr * yr + xi * yi;
+                            s.Ai[r * kLdBlk + c2] -= xi * yr - xr * yi;
+                        }
+                    }
+                    __syncthreads();
+                }
+                // ---- V = L_kk^-1 by row recursion:  V[r][c] = -(sum_{p=c}^{r-1} L[r][p] V[p][c]) / L[r][r]
+                for (int e = tid; e < 32 * kLdBlk; e += 256) { s.Vr[e] = 0.0; s.Vi[e] = 0.0; }
+                __syncthreads();
+                for (int r = 0; r < 32; ++r) {
+                    int c = tid & 31, part = tid >> 5;
+                    double sr = 0.0, si = 0.0;
+                    for (int p = c + ((part - c) & 7); p < r; p += 8) {
+                        double lr = s.Ar[r * kLdBlk + p], li = s.Ai[r * kLdBlk + p];
+                        double vr = s.Vr[p * kLdBlk + c], vi = s.Vi[p * kLdBlk + c];
+                        sr += lr * vr - li * vi;
+                        si += lr * vi + li * vr;
+                    }
+                    s.redr[part * 32 + c] = sr; s.redi[part * 32 + c] = si;
+                    __syncthreads();
+                    if (tid < 32) {
+                        double d = s.Ar[r * kLdBlk + r];
+                        if (c < r) {
+                            double tr = 0.0, tim = 0.0;
+#pragma unroll
+                            for (int pp = 0; pp < 8; ++pp) { tr += s.redr[pp * 32 + c]; tim += s.redi[pp * 32 + c]; }
+                            s.Vr[r * kLdBlk + c] = -tr / d;
+                            s.Vi[r * kLdBlk + c] = -tim / d;
+                        } else if (c == r) {
+                            s.Vr[r * kLdBlk + r] = 1.0 / d;
+                        }
+                    }
+                    __syncthreads();
+                }
+                // write L_kk and V to global
+                double* Lb = Lp + blk_index(k, k) * kBlkDoubles;
+                double* Vb = Linvp + (size_t)k * kBlkDoubles;
+                for (int e = tid; e < 1024; e += 256) {
+                    int r = e >> 5, c = e & 31;
+                    Lb[e] = s.Ar[r * kLdBlk + c]; Lb[1024 + e] = s.Ai[r * kLdBlk + c];
+                    Vb[e] = s.Vr[r * kLdBlk + c]; Vb[1024 + e] = s.Vi[r * kLdBlk + c];
+                }
+            } else {
+                // L_ik = C . V^H
+                double dr[1][2][2], di[1][2][2];
+                warp_zero<1, 2>(dr, di);
+                warp_zgemm<1, 2, false, false, true, true>(dr, di, s.Ar + 8 * ti * kLdBlk, s.Ai + 8 * ti * kLdBlk, kLdBlk,
+                                                           s.Vr + 16 * tj * kLdBlk, s.Vi + 16 * tj * kLdBlk, kLdBlk, 32);
+                double* Lb = Lp + blk_index(i, k) * kBlkDoubles;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    int r = 8 * ti + g, c = 16 * tj + 8 * j + 2 * q;
+                    *reinterpret_cast<double2*>(Lb + r * 32 + c) = make_double2(dr[0][j][0], dr[0][j][1]);
+                    *reinterpret_cast<double2*>(Lb + 1024 + r * 32 + c) = make_double2(di[0][j][0], di[0][j][1]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && a.info) a.info[sys] = bad;
+}
+
+void launch_chol(const CholArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
+        attr_set = true;
+    }
+    k_chol<<<a.nsys, 256, sizeof(CholSmem), st>>>(a);
+}
+
+// ==========================================================================================
+// k_solve: CTA = (time tile of 16, system).  Builds its right-hand sides on the fly, runs the
+// forward (L) and backward (L^H) block substitutions with the 16-column solution tile resident
+// in shared memory, streams L blocks through a cp.async double buffer, and finishes with the
+// per-delay partial sums of |ytilde|^2 that sample_S needs.
+constexpr int kLdX = 20;  // 16 + 4, == 4 mod 16
+
+size_t solve_smem_bytes(int nblk) {
+    size_t Np = (size_t)nblk * 32;
+    size_t d = 2 * Np * kLdX            // X tile planes
+             + 2 * 2 * 32 * kLdBlk      // two block buffers (re, im)
+             + 2 * 32 * kLdX            // Z
+             + 16 * 16 * 3 + 64;        // reductions + theta
+    return d * sizeof(double);
+}
+
+struct RhsCtx {
+    const double* Rfix; const double* eta; const double* wa; const double* lam;
+    int Np, n, N, T, t0, philox_wa;
+    uint32_t key0, key1, iter, chain;
+};
+
+// right-hand side element (system row `row`, tile column `col`)
+__device__ __forceinline__ void rhs_elem(const RhsCtx& c, int row, int col, double& vr, double& vi) {
+    int t = c.t0 + col;
+    vr = 0.0; vi = 0.0;
+    if (t >= c.T || row >= c.N) return;
+    size_t off = 2 * ((size_t)t * c.Np + row);
+    double xr = c.Rfix[off], xi = c.Rfix[off + 1];
+    if (c.eta) { xr += c.eta[off]; xi += c.eta[off + 1]; }
+    double l = c.lam[row];
+    vr = l * xr; vi = l * xi;
+    if (row < c.n) {
+        if (c.wa) { vr += c.wa[off]; vi += c.wa[off + 1]; }
+        else if (c.philox_wa) {
+            u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)t; ctr.z = c.iter; ctr.w = c.chain;
+            double n0, n1;
+            normal_pair(philox4x32_10(ctr, c.key0, c.key1 ^ 0xA5A5A5A5u), n0, n1);
+            vr += n0 * 0.70710678118654752440; vi += n1 * 0.70710678118654752440;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nblk = a.nblk, Np = nblk * 32;
+    double* Xr = reinterpret_cast<double*>(smem_raw);
+    double* Xi = Xr + (size_t)Np * kLdX;
+    double* Lb = Xi + (size_t)Np * kLdX;              // [2 buffers][re, im][32*36]
+    double* Zr = Lb + 4 * 32 * kLdBlk;
+    double* Zi = Zr + 32 * kLdX;
+    double* red = Zi + 32 * kLdX;                     // 16*16*3
+    double* theta = red + 16 * 16 * 3;                // 16 * 2 (+pad)
+
+    const int sys = blockIdx.y, tile = blockIdx.x;
+    const double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
+    const double* Linvp = a.Linvp + (size_t)sys * nblk * kBlkDoubles;
+    const double* lam = a.lam + (size_t)sys * Np;
+    RhsCtx rc;
+    rc.Rfix = a.Rfix + 2 * (size_t)sys * a.Tp * Np;
+    rc.eta = a.eta ? a.eta + 2 * (size_t)sys * a.Tp * Np : nullptr;
+    rc.wa = a.wa ? a.wa + 2 * (size_t)sys * a.Tp * Np : nullptr;
+    rc.lam = lam; rc.Np = Np; rc.n = a.n; rc.N = a.N; rc.T = a.T; rc.t0 = tile * kTT;
+    rc.philox_wa = a.philox_wa; rc.key0 = a.key0; rc.key1 = a.key1; rc.iter = a.iter;
+    rc.chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)sys;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int ti = warp >> 1, tj = warp & 1;  // warp tile: rows 8 ti.., cols 8 tj..
+
+    auto bufr = [&](int b) { return Lb + (size_t)b * 2 * 32 * kLdBlk; };
+    auto bufi = [&](int b) { return Lb + (size_t)b * 2 * 32 * kLdBlk + 32 * kLdBlk; };
+
+    // ------------------------------------------------------------------ forward:  L Y = R
+    int buf = 0;
+    // stream of blocks: for i: (i,0) .. (i,i-1), Linv_i
+    load_block_async(bufr(0), bufi(0), Linvp);  // i = 0 has no off-diagonal blocks
+    cp_async_commit();
+    for (int i = 0; i < nblk; ++i) {
+        double cr[1][1][2], ci[1][1][2];
+        warp_zero<1, 1>(cr, ci);
+        for (int j = 0; j < i; ++j) {
+            // prefetch the next stream item into the other buffer
+            const double* nxt = (j + 1 < i) ? Lp + blk_index(i, j + 1) * kBlkDoubles : Linvp + (size_t)i * kBlkDoubles;
+            load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), nxt);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            warp_zgemm<1, 1, false, false, false, false>(cr, ci, bufr(buf) + 8 * ti * kLdBlk, bufi(buf) + 8 * ti * kLdBlk,
+                                                         kLdBlk, Xr + (size_t)32 * j * kLdX + 8 * tj,
+                                                         Xi + (size_t)32 * j * kLdX + 8 * tj, kLdX, 32);
+            __syncthreads();
+            buf ^= 1;
+        }
+        // current buffer holds Linv_i; prefetch first block of the next row
+        if (i + 1 < nblk) load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), Lp + blk_index(i + 1, 0) * kBlkDoubles);
+        cp_async_commit();
+        // Z = R_i - acc
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+            double vr, vi;
+            rhs_elem(rc, 32 * i + r, c, vr, vi);
+            Zr[r * kLdX + c] = vr - cr[0][0][e];
+            Zi[r * kLdX + c] = vi - ci[0][0][e];
+        }
+        cp_async_wait<1>();
+        __syncthreads();
+        double yr[1][1][2], yi[1][1][2];
+        warp_zero<1, 1>(yr, yi);
+        warp_zgemm<1, 1, false, false, false, false>(yr, yi, bufr(buf) + 8 * ti * kLdBlk, bufi(buf) + 8 * ti * kLdBlk, kLdBlk,
+                                                     Zr + 8 * tj, Zi + 8 * tj, kLdX, 32);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int r = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
+            Xr[(size_t)r * kLdX + c] = yr[0][0][e];
+            Xi[(size_t)r * kLdX + c] = yi[0][0][e];
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ------------------------------------------------------------------ backward:  L^H X = Y
+    // stream: for i = nblk-1 .. 0: (i+1,i) .. (nblk-1,i), Linv_i
+    buf = 0;
+    load_block_async(bufr(0), bufi(0), Linvp + (size_t)(nblk - 1) * kBlkDoubles);
+    cp_async_commit();
+    for (int i = nblk - 1; i >= 0; --i) {
+        double cr[1][1][2], ci[1][1][2];
+        warp_zero<1, 1>(cr, ci);
+        for (int j = i + 1; j < nblk; ++j) {
+            const double* nxt = (j + 1 < nblk) ? Lp + blk_index(j + 1, i) * kBlkDoubles : Linvp + (size_t)i * kBlkDoubles;
+            load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), nxt);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            // acc += L_ji^H . X_j :  A elem (r, k) = conj(L_ji[k][r])
+            warp_zgemm<1, 1, true, true, false, false>(cr, ci, bufr(buf) + 8 * ti, bufi(buf) + 8 * ti, kLdBlk,
+                                                       Xr + (size_t)32 * j * kLdX + 8 * tj, Xi + (size_t)32 * j * kLdX + 8 * tj,
+                                                       kLdX, 32);
+            __syncthreads();
+            buf ^= 1;
+        }
+        // current buffer holds Linv_i; the first item of row i-1 is block (i, i-1)
+        if (i > 0) load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), Lp + blk_index(i, i - 1) * kBlkDoubles);
+        cp_async_commit();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+            Zr[r * kLdX + c] = Xr[(size_t)(32 * i + r) * kLdX + c] - cr[0][0][e];
+            Zi[r * kLdX + c] = Xi[(size_t)(32 * i + r) * kLdX + c] - ci[0][0][e];
+        }
+        cp_async_wait<1>();
+        __syncthreads();
+        double yr[1][1][2], yi[1][1][2];
+        warp_zero<1, 1>(yr, yi);
+        // X_i = Linv_i^H . Z
+        warp_zgemm<1, 1, true, true, false, false>(yr, yi, bufr(buf) + 8 * ti, bufi(buf) + 8 * ti, kLdBlk, Zr + 8 * tj,
+                                                   Zi + 8 * tj, kLdX, 32);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int r = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
+            Xr[(size_t)r * kLdX + c] = yr[0][0][e];
+            Xi[(size_t)r * kLdX + c] = yi[0][0][e];
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ------------------------------------------------------------------ epilogue
+    if (a.cg_compat) {
+        // c = b^H x*, ||b||^2 in the reference's (unwhitened) variables:
+        //   weights lam^2 on the signal rows, 1 on the foreground rows ("CG model").
+        int col = tid & 15, rg = tid >> 4;
+        double sre = 0.0, sim = 0.0, sb = 0.0;
+        for (int row = rg; row < a.N; row += 16) {
+            double vr, vi;
+            rhs_elem(rc, row, col, vr, vi);
+            double w = row < a.n ? lam[row] * lam[row] : 1.0;
+            double xr = Xr[(size_t)row * kLdX + col], xi = Xi[(size_t)row * kLdX + col];
+            sre += w * (vr * xr + vi * xi);   // conj(R) X
+            sim += w * (vr * xi - vi * xr);
+            sb += w * (vr * vr + vi * vi);
+        }
+        red[(rg * 16 + col) * 3 + 0] = sre; red[(rg * 16 + col) * 3 + 1] = sim; red[(rg * 16 + col) * 3 + 2] = sb;
+        __syncthreads();
+        if (tid < 16) {
+            double cre = 0.0, cim = 0.0, b2 = 0.0;
+            for (int r2 = 0; r2 < 16; ++r2) {
+                cre += red[(r2 * 16 + tid) * 3 + 0]; cim += red[(r2 * 16 + tid) * 3 + 1]; b2 += red[(r2 * 16 + tid) * 3 + 2];
+            }
+            cplx c; c.re = cre; c.im = cim;
+            cplx th = cg_theta(c, sqrt(b2), 1e-8, 1e-6, 100000);
+            theta[2 * tid] = th.re; theta[2 * tid + 1] = th.im;
+        }
+        __syncthreads();
+        for (int e = tid; e < Np * 16; e += 256) {
+            int row = e >> 4, col2 = e & 15;
+            double xr = Xr[(size_t)row * kLdX + col2], xi = Xi[(size_t)row * kLdX + col2];
+            double tr = theta[2 * col2], tim = theta[2 * col2 + 1];
+            Xr[(size_t)row * kLdX + col2] = tr * xr - tim * xi;
+            Xi[(size_t)row * kLdX + col2] = tr * xi + tim * xr;
+        }
+        __syncthreads();
+    }
+    double* Xg = a.X + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * Np;
+    double* Sg = a.Ssc + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * a.n;
+    for (int t = 0; t < kTT; ++t) {
+        for (int row = tid; row < Np; row += 256) {
+            double xr = Xr[(size_t)row * kLdX + t], xi = Xi[(size_t)row * kLdX + t];
+            *reinterpret_cast<double2*>(Xg + 2 * ((size_t)t * Np + row)) = make_double2(xr, xi);
+            if (row < a.n) {
+                double l = lam[row];
+                *reinterpret_cast<double2*>(Sg + 2 * ((size_t)t * a.n + row)) = make_double2(l * xr, l * xi);
+            }
+        }
+    }
+    double* Pp = a.Ppart + ((size_t)sys * a.ntiles + tile) * a.n;
+    for (int row = tid; row < a.n; row += 256) {
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < kTT; ++t) {
+            double xr = Xr[(size_t)row * kLdX + t], xi = Xi[(size_t)row * kLdX + t];
+            acc += xr * xr + xi * xi;
+        }
+        Pp[row] = acc;
+    }
+}
+
+void launch_solve(const SolveArgs& a, cudaStream_t st) {
+    size_t smem = solve_smem_bytes(a.nblk);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_smem = smem;
+    }
+    k_solve<<<dim3(a.ntiles, a.nsys), 256, smem, st>>>(a);
+}
+
+// ==========================================================================================
+// k_post: one CTA per (time, system): model = s + F f, residual, chi^2, flagged copies.
+__global__ void __launch_bounds__(128) k_post(PostArgs a) {
+    extern __shared__ double fsh[];  // f_t: 2*m doubles
+    const int sys = blockIdx.y, t = blockIdx.x;
+    const double* X = a.X + 2 * ((size_t)sys * a.Tp + t) * a.Np;
+    for (int j = threadIdx.x; j < 2 * a.m; j += blockDim.x) fsh[j] = X[2 * a.n + j];
+    __syncthreads();
+    if (a.fg_out && t < a.T)
+        for (int j = threadIdx.x; j < 2 * a.m; j += blockDim.x) a.fg_out[(size_t)sys * a.fg_bs + (size_t)t * 2 * a.m + j] = fsh[j];
+    const double* Sf = a.Sf + 2 * ((size_t)sys * a.sf_bs + (size_t)t * a.n);
+    const double* wd = a.wd + 2 * ((size_t)sys * a.Tp + t) * a.n;
+    const double* Ft = a.Ft + 2 * (size_t)sys * a.m * a.n;
+    const double* w = a.w + (size_t)sys * a.n;
+    const double* nd = a.ninvd + (size_t)sys * a.n;
+    double part = 0.0;
+    for (int x = threadIdx.x; x < a.n; x += blockDim.x) {
+        double sr = 0.0, si = 0.0;
+        if (t < a.T) { sr = Sf[2 * x]; si = Sf[2 * x + 1]; }
+        double mr = sr, mi = si;
+        for (int j = 0; j < a.m; ++j) {
+            double fr = Ft[2 * ((size_t)j * a.n + x)], fi = Ft[2 * ((size_t)j * a.n + x) + 1];
+            double ar = fsh[2 * j], ai = fsh[2 * j + 1];
+            mr += ar * fr - ai * fi;
+            mi += ar * fi + ai * fr;
+        }
+        double rr = wd[2 * x] - mr, ri = wd[2 * x + 1] - mi;
+        double r2 = rr * rr + ri * ri;
+        if (t < a.T) {
+            if (a.chisq_out) a.chisq_out[(size_t)sys * a.chisq_bs + (size_t)t * a.n + x] = r2 * nd[x];
+            part += w[x] * nd[x] * r2;
+        }
+        if (a.Wm) {
+            double* p = a.Wm + 2 * (((size_t)sys * a.Tp + t) * a.n + x);
+            p[0] = w[x] * sr; p[1] = w[x] * si;
+        }
+    }
+    // block reduce
+    __shared__ double redp[4];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) redp[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += redp[i];
+        a.lnp1[(size_t)sys * a.Tp + t] = t < a.T ? s : 0.0;
+    }
+}
+void launch_post(const PostArgs& a, cudaStream_t st) {
+    k_post<<<dim3(a.Tp, a.nsys), 128, 2 * a.m * sizeof(double), st>>>(a);
+}
+
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_colsumsq(const double* A, double* out, int T, int Tp, int n) {
+    __shared__ double red[8][33];
+    const int sys = blockIdx.y;
+    const int k = blockIdx.x * 32 + (threadIdx.x & 31), tg = threadIdx.x >> 5;
+    double acc = 0.0;
+    if (k < n)
+        for (int t = tg; t < T; t += 8) {
+            const double* p = A + 2 * (((size_t)sys * Tp + t) * n + k);
+            acc += p[0] * p[0] + p[1] * p[1];
+        }
+    red[tg][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (tg == 0 && k < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
+        out[(size_t)sys * n + k] = s;
+    }
+}
+void launch_colsumsq(const double* A, double* out, int T, int Tp, int n, int nsys, cudaStream_t st) {
+    k_colsumsq<<<dim3((n + 31) / 32, nsys), 256, 0, st>>>(A, out, T, Tp, n);
+}
+
+// ==========================================================================================
+// k_sample: one CTA (1024 threads) per system.  beta -> new power spectrum sample
+// (pspec.py:67-127), lam for the next iteration, and ln_post (pspec.py:466-485).
+__device__ __forceinline__ double block_reduce(double v, double* sh, int op) {
+    // op 0 sum, 1 min, 2 max ; 1024 threads
+    for (int o = 16; o > 0; o >>= 1) {
+        double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = op == 0 ? v + w : (op == 1 ? fmin(v, w) : fmax(v, w));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double x = sh[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) {
+            double w = __shfl_xor_sync(0xffffffffu, x, o);
+            x = op == 0 ? x + w : (op == 1 ? fmin(x, w) : fmax(x, w));
+        }
+        if (threadIdx.x == 0) sh[32] = x;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+__global__ void __launch_bounds__(1024) k_sample(SampleArgs a) {
+    __shared__ double sh[40];
+    __shared__ double cdf[kInvGrid + 24];
+    __shared__ double pmx[kInvGrid + 24];
+    __shared__ double wmax[33];
+    __shared__ double beta_s;
+    const int sys = blockIdx.x, tid = threadIdx.x;
+    const int n = a.n;
+    double* ps = a.ps + (size_t)sys * n;
+    double* lam = a.lam + (size_t)sys * a.Np;
+    const double* prior = a.prior + (size_t)sys * 2 * n;
+    const double* draws = a.draws ? a.draws + (size_t)sys * a.draws_bs : nullptr;
+    const double alpha = (double)a.T - 1.0;  // pspec.py:108
+    const uint32_t chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)sys;
+
+    double lp2 = 0.0;  // sum_k E_k / Lambda'_k
+    for (int k0 = 0; k0 < n; k0 += 1024) {
+        int k = k0 + tid;
+        double beta = 0.0, newps = 0.0;
+        bool has_prior = false;
+        if (k < n) {
+            if (a.beta_mode == 0) {
+                double s = 0.0;
+                for (int tl = 0; tl < a.ntiles; ++tl) s += a.Ppart[((size_t)sys * a.ntiles + tl) * n + k];
+                beta = ps[k] * s;  // |sk|^2 = n lam^2 |ytilde|^2 = ps |ytilde|^2
+            } else {
+                beta = (double)n * a.Eu[(size_t)sys * n + k];
+            }
+            has_prior = prior[k] > 0.0 || prior[n + k] > 0.0;  // pspec.py:114
+            if (!has_prior) {
+                if (!a.philox) newps = draws[k] * beta;  // invgamma.rvs(a=alpha) * beta, pspec.py:125
+                else newps = beta / gamma_mt(alpha, (uint32_t)k, a.iter, chain, a.key0, a.key1 ^ 0x5A5A5A5Au);
+            }
+        }
+        // prior-bounded bins: inversion sampling, one bin at a time, grid evaluated by the CTA
+        for (int kk = k0; kk < min(k0 + 1024, n); ++kk) {
+            bool hp_ = prior[kk] > 0.0 || prior[n + kk] > 0.0;
+            if (!hp_) continue;
+            if (tid == kk - k0) beta_s = beta;
+            __syncthreads();
+            const double b = beta_s;
+            const double l0 = log10(prior[n + kk]), l1 = log10(prior[kk]);
+            double xj = 0.0, cj = 0.0;
+            if (tid < kInvGrid) {
+                xj = invsamp_grid_x(l0, l1, tid, kInvGrid);
+                cj = igamc(alpha + 1.0, b / xj);  // invgamma.cdf(x, a=alpha+1, scale=beta), pspec.py:51,121
+            }
+            double mn = block_reduce(tid < kInvGrid ? cj : INFINITY, sh, 1);
+            cj -= mn;
+            double mx = block_reduce(tid < kInvGrid ? cj : -INFINITY, sh, 2);
+            cj /= mx;
+            if (tid < kInvGrid) cdf[tid] = cj;
+            __syncthreads();
+            // exclusive prefix max -> first occurrences of a non-decreasing sequence (np.unique)
+            double run = tid < kInvGrid ? cj : -INFINITY;
+            for (int o = 1; o < 32; o <<= 1) {
+                double w = __shfl_up_sync(0xffffffffu, run, o);
+                if ((tid & 31) >= o) run = fmax(run, w);
+            }
+            if ((tid & 31) == 31) wmax[tid >> 5] = run;
+            __syncthreads();
+            if (tid < 32) {
+                double w = wmax[tid];
+                for (int o = 1; o < 32; o <<= 1) {
+                    double v = __shfl_up_sync(0xffffffffu, w, o);
+                    if (tid >= o) w = fmax(w, v);
+                }
+                wmax[tid] = w;
+            }
+            __syncthreads();
+            double incl = run;
+            if ((tid >> 5) > 0) incl = fmax(incl, wmax[(tid >> 5) - 1]);
+            if (tid < kInvGrid) pmx[tid] = incl;
+            __syncthreads();
+            bool keep = tid < kInvGrid && (tid == 0 || cj > pmx[tid - 1]);
+            double u;
+            if (!a.philox) u = draws[kk];
+            else {
+                u32x4 ctr; ctr.x = (uint32_t)kk; ctr.y = a.iter; ctr.z = 0xFFFFu; ctr.w = chain;
+                u32x4 r = philox4x32_10(ctr, a.key0, a.key1 ^ 0x5A5A5A5Au);
+                u = u53(r.x, r.y);
+            }
+            // bracket: lo = last kept with cdf <= u ; hi = first kept with cdf > u
+            double lo = block_reduce((keep && cj <= u) ? (double)tid : -1.0, sh, 2);
+            double hi = block_reduce((keep && cj > u) ? (double)tid : 1e9, sh, 1);
+            if (tid == kk - k0) {
+                if (lo < 0.0 || hi > 1e8) newps = NAN;
+                else {
+                    int il = (int)lo, ih = (int)hi;
+                    double xl = invsamp_grid_x(l0, l1, il, kInvGrid), xh = invsamp_grid_x(l0, l1, ih, kInvGrid);
+                    double slope = (xh - xl) / (cdf[ih] - cdf[il]);
+                    newps = slope * (u - cdf[il]) + xl;
+                }
+            }
+            __syncthreads();
+        }
+        if (k < n) {
+            ps[k] = newps;
+            lam[k] = sqrt(newps / (double)n);
+            a.ps_out[(size_t)sys * a.ps_bs + k] = newps;
+            double E = a.Em ? a.Em[(size_t)sys * n + k] : beta / (double)n;
+            lp2 += E / (newps / (double)n);
+        }
+    }
+    double s2 = block_reduce(lp2, sh, 0);
+    double l1 = 0.0;
+    const double* lnp1 = a.lnp1 + (size_t)sys * a.Tp;
+    for (int t = tid; t < a.T; t += 1024) l1 += lnp1[t];
+    double s1 = block_reduce(l1, sh, 0);
+    if (tid == 0) a.lnpost_out[(size_t)sys * a.lnpost_bs] = -s1 - s2;
+}
+void launch_sample(const SampleArgs& a, cudaStream_t st) { k_sample<<<a.nsys, 1024, 0, st>>>(a); }
+
+// ==========================================================================================
+__global__ void k_noise_draw(double* z, const double* nu, int T, int Tp, int n, uint32_t key0, uint32_t key1,
+                             uint32_t iter, const int* chain_ids) {
+    const int sys = blockIdx.z, t = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    double vr = 0.0, vi = 0.0;
+    if (t < T) {
+        u32x4 ctr; ctr.x = (uint32_t)x; ctr.y = (uint32_t)t; ctr.z = iter;
+        ctr.w = chain_ids ? (uint32_t)chain_ids[sys] : (uint32_t)sys;
+        double n0, n1;
+        normal_pair(philox4x32_10(ctr, key0, key1 ^ 0x3C3C3C3Cu), n0, n1);
+        double s = nu[(size_t)sys * n + x] * 0.70710678118654752440;
+        vr = s * n0; vi = s * n1;
+    }
+    double* p = z + 2 * (((size_t)sys * Tp + t) * n + x);
+    p[0] = vr; p[1] = vi;
+}
+void launch_noise_draw(double* z, const double* nu, int T, int Tp, int n, int nsys, uint32_t key0, uint32_t key1,
+                       uint32_t iter, const int* chain_ids, cudaStream_t st) {
+    k_noise_draw<<<dim3((n + 127) / 128, Tp, nsys), 128, 0, st>>>(z, nu, T, Tp, n, key0, key1, iter, chain_ids);
+}
+
+}  // namespace hp

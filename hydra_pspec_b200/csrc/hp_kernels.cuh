@@ -1,0 +1,121 @@
+// hp_kernels.cuh -- launch interfaces of the sm_100a kernels (definitions in hp_kernels.cu).
+//
+// Conventions
+//   * complex128 arrays in global memory are interleaved (re, im) doubles == numpy complex128.
+//   * "packed lower-block" matrices (G, L): 32x32 blocks, block (i, j), j <= i, at block index
+//     i (i+1)/2 + j; each block is 2048 doubles: a 32x32 row-major real plane followed by the
+//     imaginary plane.  Diagonal blocks of G hold both triangles.
+//   * system vectors are padded to Np = 32 * nblk rows; times are padded to Tp = 16 * ntiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hp {
+
+constexpr int kNB = 32;                 // block edge of the packed format
+constexpr int kBlkDoubles = 2 * 32 * 32;  // doubles per packed block (16 KiB)
+constexpr int kTT = 16;                 // right-hand sides (times) per solve CTA
+constexpr int kInvGrid = 1000;          // pspec.py:11 ngrid default
+
+__host__ __device__ inline size_t tri_blocks(int nblk) { return (size_t)nblk * (nblk + 1) / 2; }
+__host__ __device__ inline size_t blk_index(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
+
+// ---- generic strided batched complex GEMM:  C[b] (+)= alpha * opA(A[b]) * opB(B[b]) ----------
+struct ZgemmArgs {
+    const double* A; long long sAi, sAk, bsA;   // strides in complex elements
+    const double* B; long long sBk, sBj, bsB;
+    double* C;       long long sCi, sCj, bsC;
+    const double* dk; long long bsD;            // optional real scale of index k (A side), or null
+    int M, N, K;
+    int conjA, conjB, accumulate;
+    double alpha;
+    int batch;
+};
+void launch_zgemm(const ZgemmArgs& a, cudaStream_t st);
+
+// Fop[k][x] = exp(-2 pi i (k - n/2)(x - n/2) / n) * scale   (utils.py:14-40), n x n interleaved
+void launch_fourier_operator(double* out, int n, double scale, cudaStream_t st);
+
+// dense (N x N interleaved, leading dim ld, batch stride bs) -> packed lower blocks, zero padded
+void launch_pack_lower(const double* dense, long long ld, long long bs, double* packed, int N, int nblk,
+                       int batch, cudaStream_t st);
+
+// ---- per-iteration kernels ---------------------------------------------------------------
+struct CholArgs {
+    const double* Gp;      // [nsys][tri_blocks][2048]
+    const double* lam;     // [nsys][Np]   (lambda for rows < n, 1 for fg rows, 0 for padding)
+    double* Lp;            // [nsys][tri_blocks][2048]
+    double* Linvp;         // [nsys][nblk][2048]
+    int* info;             // [nsys]  0 ok, k+1 = non-positive pivot in block column k
+    int nblk, n, N, nsys;
+};
+void launch_chol(const CholArgs& a, cudaStream_t st);
+
+struct SolveArgs {
+    const double* Lp; const double* Linvp; const double* lam;   // as above
+    const double* Rfix;    // [nsys][Tp][Np] complex: B^H N^-1 (w d)   (+ frozen noise term in numpy mode)
+    const double* eta;     // [nsys][Tp][Np] complex or null: B^H N^-1/2 omega_b of this iteration
+    const double* wa;      // [nsys][Tp][Np] complex or null: Q^H omega_a (rows < n)
+    double* X;             // [nsys][Tp][Np] complex: solution [ytilde ; f]
+    double* Ssc;           // [nsys][Tp][n]  complex: lambda * ytilde (signal in the S eigenbasis)
+    double* Ppart;         // [nsys][ntiles][n] sum over the tile's times of |ytilde|^2
+    int nblk, n, N, Tp, ntiles, nsys;
+    int T;                 // valid times (t >= T are padding: zero RHS)
+    int philox_wa;         // 1: draw omega_a in-kernel (white in any unitary basis)
+    int cg_compat;         // 1: scale each column by the scalar CG model (hp_math.h:cg_theta)
+    uint32_t key0, key1, iter;
+    const int* chain_ids;  // [nsys] global chain id for the philox counter (or null -> sys index)
+};
+void launch_solve(const SolveArgs& a, cudaStream_t st);
+size_t solve_smem_bytes(int nblk);
+
+struct PostArgs {
+    const double* Sf;      // [nsys][>=T][n] complex: signal in frequency space (rows t < T are read)
+    long long sf_bs;       // batch stride of Sf in complex elements
+    const double* X;       // [nsys][Tp][Np]
+    const double* Ft;      // [nsys][m][n] complex: fgmodes transposed
+    const double* wd;      // [nsys][Tp][n] complex: flags * vis
+    const double* w;       // [nsys][n] 0/1
+    const double* ninvd;   // [nsys][n] diag(Ninv) (real part)
+    double* fg_out;        // [nsys][T][m] complex or null
+    double* chisq_out;     // [nsys][T][n] or null
+    double* Wm;            // [nsys][Tp][n] complex: w * s   (or null when no channel is flagged)
+    double* Rm;            // [nsys][Tp][n] complex: w * resid (dense-noise ln_post) or null
+    double* lnp1;          // [nsys][Tp]: sum_x w ninv |resid|^2  (diagonal noise)
+    int n, m, Np, T, Tp, nsys;
+    long long fg_bs, chisq_bs;  // batch strides (doubles) of the output slots
+};
+void launch_post(const PostArgs& a, cudaStream_t st);
+
+// out[sys][k] = sum_t |A[sys][t][k]|^2 over t < T
+void launch_colsumsq(const double* A, double* out, int T, int Tp, int n, int nsys, cudaStream_t st);
+
+struct SampleArgs {
+    const double* Ppart;   // [nsys][ntiles][n]  (beta_mode 0)
+    const double* Eu;      // [nsys][n]: sum_t |U s|^2 (beta_mode 1: general-basis iteration)
+    const double* Em;      // [nsys][n]: sum_t |U (w s)|^2, or null (no flags: = beta / n)
+    const double* lnp1;    // [nsys][Tp]
+    const double* lnp1_dense;  // [nsys][Tp] or null: dense-noise residual term (replaces lnp1)
+    const double* prior;   // [nsys][2][n]  (pspec.py:84: [0]=upper, [1]=lower)
+    const double* draws;   // [nsys][n] injected: uniform u for prior bins, 1/gammainccinv(alpha,u) otherwise
+    double* ps;            // [nsys][n] in: current spectrum (beta_mode 0), out: new sample
+    double* lam;           // [nsys][Np] out: sqrt(ps/n) for rows < n
+    double* ps_out;        // [nsys][n] output slot
+    double* lnpost_out;    // [nsys] output slot
+    int n, Np, T, Tp, ntiles, nsys;
+    int beta_mode, philox;
+    uint32_t key0, key1, iter;
+    const int* chain_ids;
+    long long ps_bs, lnpost_bs, draws_bs;
+};
+void launch_sample(const SampleArgs& a, cudaStream_t st);
+
+// z[sys][t][x] = nu[sys][x] * CN(0,1) (philox), zero for t >= T
+void launch_noise_draw(double* z, const double* nu, int T, int Tp, int n, int nsys, uint32_t key0,
+                       uint32_t key1, uint32_t iter, const int* chain_ids, cudaStream_t st);
+
+// small elementwise helpers used by the set-up
+void launch_scale_rows(double* A, const double* d, int rows, int cols, long long ld, cudaStream_t st);  // A[r][:] *= d[r]
+void launch_fill(double* p, double v, size_t count, cudaStream_t st);
+
+}  // namespace hp

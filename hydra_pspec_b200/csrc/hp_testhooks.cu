@@ -1,0 +1,83 @@
+// hp_testhooks.cu -- host-in / host-out wrappers around single kernels, for tests/ only.
+#include "../../include/hydra_pspec_b200.h"
+#include "hp_kernels.cuh"
+
+#include <string>
+#include <vector>
+
+extern "C" {
+
+// C (M x N) = opA(A) (M x K) . opB(B) (K x N), all row-major complex128 host arrays.
+//   transA: 0 = A is M x K, 1 = A is K x M (transposed storage);  conjA likewise; same for B.
+int hp_test_zgemm(int M, int N, int K, const double* A, int transA, int conjA, const double* B, int transB, int conjB,
+                  const double* dk, double* C) {
+    double *dA, *dB, *dC, *dD = nullptr;
+    if (cudaMalloc(&dA, 16ull * M * K) || cudaMalloc(&dB, 16ull * K * N) || cudaMalloc(&dC, 16ull * M * N)) return HP_ERR_CUDA;
+    cudaMemcpy(dA, A, 16ull * M * K, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B, 16ull * K * N, cudaMemcpyHostToDevice);
+    if (dk) { cudaMalloc(&dD, 8ull * K); cudaMemcpy(dD, dk, 8ull * K, cudaMemcpyHostToDevice); }
+    hp::ZgemmArgs g{};
+    g.A = dA; g.sAi = transA ? 1 : K; g.sAk = transA ? M : 1; g.conjA = conjA;
+    g.B = dB; g.sBk = transB ? 1 : N; g.sBj = transB ? K : 1; g.conjB = conjB;
+    g.C = dC; g.sCi = N; g.sCj = 1; g.dk = dD;
+    g.M = M; g.N = N; g.K = K; g.alpha = 1.0; g.batch = 1;
+    hp::launch_zgemm(g, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(C, dC, 16ull * M * N, cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dD);
+    return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
+}
+
+// Factor M = J + D G D (G dense N x N Hermitian, lam[N] with lam = 1 on the rows >= n) and solve
+// M X = R for T right-hand sides given as R[T][N] (already whitened: no lam scaling is applied
+// by the caller -- the kernel multiplies Rfix by lam, so pass Rfix and lam separately).
+//   Ldense [N][N] (lower triangle, optional), X [T][N].
+int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, const double* Rfix, const double* wa,
+                       int cg_compat, double* Ldense, double* X, int* info) {
+    const int N = n + m, nblk = (N + 31) / 32, Np = nblk * 32, ntiles = (T + 15) / 16, Tp = ntiles * 16;
+    double *dG, *dGp, *dlam, *dLp, *dLinv, *dR, *dW = nullptr, *dX, *dS, *dP;
+    int* dinfo;
+    size_t tri = hp::tri_blocks(nblk) * hp::kBlkDoubles;
+    cudaMalloc(&dG, 16ull * N * N); cudaMalloc(&dGp, 8 * tri); cudaMalloc(&dlam, 8ull * Np); cudaMalloc(&dLp, 8 * tri);
+    cudaMalloc(&dLinv, 8ull * nblk * hp::kBlkDoubles); cudaMalloc(&dR, 16ull * Tp * Np); cudaMalloc(&dX, 16ull * Tp * Np);
+    cudaMalloc(&dS, 16ull * Tp * n); cudaMalloc(&dP, 8ull * ntiles * n); cudaMalloc(&dinfo, 4);
+    cudaMemset(dR, 0, 16ull * Tp * Np); cudaMemset(dlam, 0, 8ull * Np);
+    cudaMemcpy(dG, G, 16ull * N * N, cudaMemcpyHostToDevice);
+    cudaMemcpy(dlam, lam, 8ull * N, cudaMemcpyHostToDevice);
+    cudaMemcpy2D(dR, 16ull * Np, Rfix, 16ull * N, 16ull * N, T, cudaMemcpyHostToDevice);
+    if (wa) {
+        cudaMalloc(&dW, 16ull * Tp * Np); cudaMemset(dW, 0, 16ull * Tp * Np);
+        cudaMemcpy2D(dW, 16ull * Np, wa, 16ull * n, 16ull * n, T, cudaMemcpyHostToDevice);
+    }
+    hp::launch_pack_lower(dG, N, 0, dGp, N, nblk, 1, 0);
+    hp::CholArgs ca{};
+    ca.Gp = dGp; ca.lam = dlam; ca.Lp = dLp; ca.Linvp = dLinv; ca.info = dinfo; ca.nblk = nblk; ca.n = n; ca.N = N; ca.nsys = 1;
+    hp::launch_chol(ca, 0);
+    hp::SolveArgs sa{};
+    sa.Lp = dLp; sa.Linvp = dLinv; sa.lam = dlam; sa.Rfix = dR; sa.wa = dW; sa.X = dX; sa.Ssc = dS; sa.Ppart = dP;
+    sa.nblk = nblk; sa.n = n; sa.N = N; sa.Tp = Tp; sa.ntiles = ntiles; sa.nsys = 1; sa.T = T; sa.cg_compat = cg_compat;
+    hp::launch_solve(sa, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) {
+        cudaMemcpy2D(X, 16ull * N, dX, 16ull * Np, 16ull * N, T, cudaMemcpyDeviceToHost);
+        cudaMemcpy(info, dinfo, 4, cudaMemcpyDeviceToHost);
+        if (Ldense) {
+            std::vector<double> lp(tri);
+            cudaMemcpy(lp.data(), dLp, 8 * tri, cudaMemcpyDeviceToHost);
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) {
+                    double re = 0, im = 0;
+                    if (j <= i) {
+                        const double* b = lp.data() + hp::blk_index(i / 32, j / 32) * hp::kBlkDoubles;
+                        re = b[(i % 32) * 32 + (j % 32)]; im = b[1024 + (i % 32) * 32 + (j % 32)];
+                    }
+                    Ldense[2 * ((size_t)i * N + j)] = re; Ldense[2 * ((size_t)i * N + j) + 1] = im;
+                }
+        }
+    }
+    cudaFree(dG); cudaFree(dGp); cudaFree(dlam); cudaFree(dLp); cudaFree(dLinv); cudaFree(dR); cudaFree(dW); cudaFree(dX);
+    cudaFree(dS); cudaFree(dP); cudaFree(dinfo);
+    return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
+}
+
+}  // extern "C"

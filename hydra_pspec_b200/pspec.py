@@ -1,0 +1,495 @@
+"""Drop-in for ``hydra_pspec.pspec`` (reference: hydra_pspec/pspec.py) on B200.
+
+Same function names, argument meaning, return values and error behaviour as the reference for
+the Gibbs hot path; the work is done by hand-written sm_100a kernels behind the C ABI in
+``include/hydra_pspec_b200.h``.  The host code in this module only validates and stages the
+inputs, reproduces the reference's numpy random streams when asked to (``rng="numpy"``), and
+copies the sample arrays back.
+
+Two fidelity modes
+------------------
+``rng="numpy"`` (default of the drop-in functions)
+    The draws are the reference's: ``np.random.seed(912983 + t)`` normals per time for the GCR
+    fluctuation terms (pspec.py:195-217, identical in every iteration) and one uniform per delay
+    bin per iteration from ``np.random.seed(seed)`` for ``sample_S`` (pspec.py:58, 125).  With
+    ``solver="reference-cg"`` (default in this mode) each solve is additionally scaled by the
+    scalar model of the reference's truncated CG, so a chain reproduces the reference's numbers
+    to ~1e-10.  ``solver="exact"`` returns the exact solution of the same linear system.
+``rng="philox"``
+    Device Philox4x32-10 draws, exact solves, new fluctuation terms every iteration
+    (``refresh_omega=True``) -- the production mode used by :class:`GibbsEngine` and ``bench.py``.
+"""
+import time
+
+import numpy as np
+import scipy.special
+from scipy.interpolate import interp1d
+from scipy.stats import invgamma
+
+from . import _lib, utils
+
+GCR_SEED_BASE = 912983  # pspec.py:153
+
+
+# --------------------------------------------------------------------------------------------
+# host-side helpers of the reference API (not on the hot path)
+def inversion_sample_invgamma(alpha, beta, prior_min, prior_max, ngrid=1000):
+    """pspec.py:11-64.  Host version (the chain uses the device implementation in k_sample)."""
+    if prior_min <= 0:
+        raise ValueError("prior_min must be greater than zero")
+    if prior_max <= 0:
+        raise ValueError("prior_max must be greater than zero")
+    if not np.isfinite(prior_max):
+        raise ValueError("prior_max must be finite")
+    if prior_max <= prior_min:
+        raise ValueError("prior_max must be greater than prior_min")
+    x = np.logspace(np.log10(prior_min), np.log10(prior_max), ngrid)
+    cdf = invgamma.cdf(x, a=alpha, loc=0, scale=beta)
+    cdf -= cdf.min()
+    cdf /= cdf.max()
+    cdf_unique, idxs_unique = np.unique(cdf, return_index=True)
+    u = np.random.uniform()
+    return interp1d(cdf_unique, x[idxs_unique], kind="linear")(u)
+
+
+def covariance_from_pspec(ps, fourier_op):
+    """pspec.py:313-322."""
+    ps = np.asarray(ps)
+    return fourier_op.T.conj() @ (ps.astype(complex)[:, None] * fourier_op)
+
+
+def sprior(signals, bins, factor):
+    """pspec.py:130-148."""
+    nobs, nfreq = signals.shape
+    sk_ = np.fft.fft(signals, axis=-1)
+    ds = np.sum(sk_ * sk_.conj(), axis=0).real
+    prior = np.zeros((2, nfreq))
+    prior[0] = ds * factor
+    prior[1] = ds / factor
+    prior[0, bins + 1:-bins] = 0
+    prior[1, bins + 1:-bins] = 0
+    return prior / (nobs / 2 - 1)
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's numpy draw streams
+def _reference_gcr_draws(ntimes, nfreqs):
+    """(omega_a, omega_b): pspec.py:195-217 -- reseeded per time index, four randn vectors."""
+    oma = np.empty((ntimes, nfreqs), dtype=np.complex128)
+    omb = np.empty((ntimes, nfreqs), dtype=np.complex128)
+    for idx in range(ntimes):
+        rs = np.random.RandomState(GCR_SEED_BASE + idx)
+        omi, omj = rs.randn(nfreqs), rs.randn(nfreqs)
+        omk, oml = rs.randn(nfreqs), rs.randn(nfreqs)
+        oma[idx] = (omi + 1.0j * omj) / 2 ** 0.5
+        omb[idx] = (omk + 1.0j * oml) / 2 ** 0.5
+    return oma, omb
+
+
+def _s_draws_from_uniforms(u, ps_prior, ntimes):
+    """Turn the per-bin uniforms of sample_S into what the device consumes: u itself for
+    prior-bounded bins (pspec.py:58), the invgamma(a = Ntimes - 1) variate for the others
+    (pspec.py:125; scipy evaluates rvs as ppf(u) = 1 / gammainccinv(a, u))."""
+    u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+    has_prior = np.any(np.asarray(ps_prior) > 0, axis=0)
+    y = 1.0 / scipy.special.gammainccinv(ntimes - 1.0, u)
+    return np.where(has_prior[None, :], u, y)
+
+
+def _check_prior(ps_prior, nfreqs):
+    """Raise the reference's errors (pspec.py:40-47) up front instead of mid-chain."""
+    if ps_prior is None:
+        return np.zeros((2, nfreqs))
+    ps_prior = np.asarray(ps_prior, dtype=np.float64)
+    if ps_prior.shape != (2, nfreqs):
+        raise ValueError(f"ps_prior must have shape (2, {nfreqs})")
+    for i in np.nonzero(np.any(ps_prior > 0, axis=0))[0]:
+        pmax, pmin = ps_prior[0, i], ps_prior[1, i]
+        if pmin <= 0:
+            raise ValueError("prior_min must be greater than zero")
+        if pmax <= 0:
+            raise ValueError("prior_max must be greater than zero")
+        if not np.isfinite(pmax):
+            raise ValueError("prior_max must be finite")
+        if pmax <= pmin:
+            raise ValueError("prior_max must be greater than prior_min")
+    return ps_prior
+
+
+_UNITARY_CACHE = {}
+
+
+def _unitary_dft(n):
+    if n not in _UNITARY_CACHE:
+        idx = np.arange(n) - n // 2
+        _UNITARY_CACHE[n] = np.exp(-2j * np.pi * (np.outer(idx, idx) % n) / n) / np.sqrt(n)
+    return _UNITARY_CACHE[n]
+
+
+def _analyse_signal_cov(S):
+    """Eigen-structure of the signal covariance handed to the device.
+
+    Returns (basis0 or None, lam0sq).  A delay-diagonal S (every covariance the chain itself
+    produces, the reference's test data, and the identity default) needs no decomposition:
+    its eigenvectors are the columns of U^H.  Anything else is decomposed once on the host
+    (numpy eigh); the first iteration then runs in that basis.
+    """
+    S = np.asarray(S)
+    n = S.shape[0]
+    U = _unitary_dft(n)
+    D = U @ S @ U.conj().T
+    d = np.real(np.diagonal(D)).copy()
+    off = D - np.diag(np.diagonal(D))
+    scale = max(np.max(np.abs(d)), 1e-300)
+    if np.max(np.abs(off)) <= 1e-13 * scale and np.max(np.abs(np.imag(np.diagonal(D)))) <= 1e-13 * scale:
+        return None, d
+    Sh = 0.5 * (S + S.conj().T)
+    w, V = np.linalg.eigh(Sh)
+    return np.ascontiguousarray(V, dtype=np.complex128), np.ascontiguousarray(w, dtype=np.float64)
+
+
+def _diag_noise(Ninv, nfreqs):
+    Ninv = np.asarray(Ninv)
+    if Ninv.ndim == 3:
+        raise NotImplementedError("per-time Ninv (Ntimes, Nfreqs, Nfreqs) is not supported by the reference's "
+                                  "build_matrices either (pspec.py:361)")
+    if Ninv.shape != (nfreqs, nfreqs):
+        raise ValueError("Ninv shape must be (Nfreqs, Nfreqs)")
+    d = np.diagonal(Ninv)
+    if np.any(Ninv - np.diag(d) != 0):
+        raise NotImplementedError("non-diagonal Ninv is not yet supported on the device path")
+    return np.ascontiguousarray(np.real(d), dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+class GibbsEngine:
+    """Batched Gibbs sampler: ``nchains`` baselines of identical shape resident on one GPU.
+
+    This is the production interface (one process per GPU, baselines sharded across ranks with
+    no collective on the hot path); the drop-in functions below are thin single-chain wrappers.
+    """
+
+    def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
+                 refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
+                 stream=None, profile=False):
+        self._h = None
+        L = _lib.lib()
+        cfg = _lib.HPConfig()
+        cfg.device = int(device)
+        cfg.nchains, cfg.ntimes, cfg.nfreqs, cfg.nmodes = int(nchains), int(ntimes), int(nfreqs), int(nmodes)
+        cfg.rng_mode = _lib.HP_RNG_PHILOX if rng == "philox" else _lib.HP_RNG_INJECTED
+        cfg.cg_compat = int(bool(cg_compat))
+        cfg.refresh_omega = int(bool(refresh_omega))
+        k = 0
+        for name, bit in (("cr", _lib.HP_KEEP_CR), ("fg", _lib.HP_KEEP_FG), ("chisq", _lib.HP_KEEP_CHISQ)):
+            if name in keep:
+                k |= bit
+        cfg.keep = k
+        cfg.max_iters = int(max_iters)
+        cfg.general_basis0 = int(bool(general_basis0))
+        cfg.profile = int(bool(profile))
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.stream = stream
+        h = _lib.C.c_void_p()
+        _lib.check(L.hp_engine_create(_lib.C.byref(cfg), _lib.C.byref(h)))
+        self._h = h
+        self.nchains, self.ntimes, self.nfreqs, self.nmodes = int(nchains), int(ntimes), int(nfreqs), int(nmodes)
+        self.max_iters = int(max_iters)
+        self.rng = rng
+        self.keep = tuple(keep)
+        self.general_basis0 = bool(general_basis0)
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().hp_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- loading
+    def load_chain(self, chain, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=None, basis0=None):
+        T, n, m = self.ntimes, self.nfreqs, self.nmodes
+        vis = _lib.c128(vis)
+        assert vis.shape == (T, n)
+        fl = np.ascontiguousarray(np.asarray(flags).astype(np.uint8))
+        assert fl.shape == (n,), "`flags` array must have shape (Nfreqs,)"
+        F = _lib.c128(fgmodes)
+        assert F.shape == (n, m), "fgmodes must have shape (Nfreqs, Nmodes)"
+        nd = _lib.f64(ninv_diag)
+        l0 = _lib.f64(lam0sq)
+        pr = None if ps_prior is None else _lib.f64(ps_prior)
+        b0 = None if basis0 is None else _lib.c128(basis0)
+        _lib.check(_lib.lib().hp_engine_load_chain(self._h, int(chain), _lib.ptr(vis), _lib.ptr(fl), _lib.ptr(F),
+                                                   _lib.ptr(nd), _lib.ptr(b0), _lib.ptr(l0), _lib.ptr(pr)))
+
+    def set_draws(self, chain, omega_a, omega_b, s_draws):
+        oa = None if omega_a is None else _lib.c128(omega_a)
+        ob = None if omega_b is None else _lib.c128(omega_b)
+        sd = None if s_draws is None else _lib.f64(s_draws)
+        nd = 0 if sd is None else sd.shape[0]
+        _lib.check(_lib.lib().hp_engine_set_draws(self._h, int(chain), _lib.ptr(oa), _lib.ptr(ob), _lib.ptr(sd), int(nd)))
+
+    # -- running
+    def run(self, niter):
+        _lib.check(_lib.lib().hp_engine_run(self._h, int(niter)))
+
+    def gcr(self):
+        _lib.check(_lib.lib().hp_engine_gcr(self._h))
+
+    def sync(self):
+        _lib.check(_lib.lib().hp_engine_sync(self._h))
+
+    def rewind(self):
+        _lib.check(_lib.lib().hp_engine_rewind(self._h))
+
+    @property
+    def iterations_done(self):
+        return _lib.lib().hp_engine_iterations_done(self._h)
+
+    @property
+    def launch_count(self):
+        return _lib.lib().hp_engine_launch_count(self._h)
+
+    def kernel_ms(self, reset=False):
+        ms = np.zeros(_lib.HP_NUM_KERNEL_CLASSES)
+        nl = np.zeros(_lib.HP_NUM_KERNEL_CLASSES, dtype=np.int32)
+        _lib.check(_lib.lib().hp_engine_kernel_ms(self._h, _lib.ptr(ms), _lib.ptr(nl), int(reset)))
+        names = [_lib.lib().hp_kernel_class_name(i).decode() for i in range(_lib.HP_NUM_KERNEL_CLASSES)]
+        return {k: (float(a), int(b)) for k, a, b in zip(names, ms, nl)}
+
+    def info(self):
+        out = np.zeros(self.nchains, dtype=np.int32)
+        _lib.check(_lib.lib().hp_engine_info(self._h, _lib.ptr(out)))
+        return out
+
+    # -- reading
+    def _read(self, chain, buf, shape, dtype, iter0=0, niter=0):
+        out = np.empty(shape, dtype=dtype)
+        _lib.check(_lib.lib().hp_engine_read(self._h, int(chain), int(buf), int(iter0), int(niter), _lib.ptr(out),
+                                             out.nbytes))
+        return out
+
+    def signal_ps(self, chain, iter0=0, niter=None):
+        niter = self.iterations_done - iter0 if niter is None else niter
+        return self._read(chain, _lib.HP_BUF_PS, (niter, self.nfreqs), np.float64, iter0, niter)
+
+    def ln_post(self, chain, iter0=0, niter=None):
+        niter = self.iterations_done - iter0 if niter is None else niter
+        return self._read(chain, _lib.HP_BUF_LNPOST, (niter,), np.float64, iter0, niter)
+
+    def signal_cr(self, chain, iter0=0, niter=None):
+        niter = self.iterations_done - iter0 if niter is None else niter
+        return self._read(chain, _lib.HP_BUF_CR, (niter, self.ntimes, self.nfreqs), np.complex128, iter0, niter)
+
+    def fg_amps(self, chain, iter0=0, niter=None):
+        niter = self.iterations_done - iter0 if niter is None else niter
+        return self._read(chain, _lib.HP_BUF_FG, (niter, self.ntimes, self.nmodes), np.complex128, iter0, niter)
+
+    def chisq(self, chain, iter0=0, niter=None):
+        niter = self.iterations_done - iter0 if niter is None else niter
+        return self._read(chain, _lib.HP_BUF_CHISQ, (niter, self.ntimes, self.nfreqs), np.float64, iter0, niter)
+
+    def last_gcr(self, chain):
+        """(Ntimes, Nfreqs + Nmodes) solution of the most recent GCR step (pspec.py:301)."""
+        s = self._read(chain, _lib.HP_BUF_LAST_CR, (self.ntimes, self.nfreqs), np.complex128)
+        f = self._read(chain, _lib.HP_BUF_LAST_FG, (self.ntimes, self.nmodes), np.complex128)
+        return np.concatenate([s, f], axis=1)
+
+    def current_ps(self, chain):
+        return self._read(chain, _lib.HP_BUF_PS_CUR, (self.nfreqs,), np.float64)
+
+    def signal_S(self, chain):
+        out = np.empty((self.nfreqs, self.nfreqs), dtype=np.complex128)
+        _lib.check(_lib.lib().hp_engine_read_signal_S(self._h, int(chain), _lib.ptr(out)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+class GCRMatrices:
+    """What :func:`build_matrices` returns on the device path.
+
+    The reference materialises sqrtm(S), sqrtm(N^-1), A and pinv(A) (pspec.py:355-372); the GPU
+    path never forms them (it factors the whitened Hermitian system instead), so this object just
+    carries the operands.  ``m[0][1]`` (S) and ``m[0][2]`` (N^-1 with the flags applied) index like
+    the reference's list so code that peeks at them keeps working.
+    """
+
+    def __init__(self, flags, signal_S, Ninv, fgmodes):
+        self.flags = np.asarray(flags, dtype=bool)
+        self.S = np.array(signal_S, dtype=complex)
+        fl = self.flags.astype(float)
+        self.Ni = (fl * np.asarray(Ninv) * fl).astype(complex)  # pspec.py:361
+        self.fgmodes = np.asarray(fgmodes)
+
+    def __getitem__(self, i):
+        if i == 0:
+            return {1: self.S, 2: self.Ni}
+        raise IndexError("the device path does not materialise A / pinv(A) (pspec.py:365-372)")
+
+
+def build_matrices(Nparams, flags, signal_S, Ninv, fgmodes):
+    """pspec.py:325-374."""
+    nfreqs = np.asarray(signal_S).shape[0]
+    assert Nparams == nfreqs + np.asarray(fgmodes).shape[1]
+    return GCRMatrices(flags, signal_S, Ninv, fgmodes)
+
+
+def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng, solver, map_estimate, keep,
+                         seed, device, s_uniforms=None):
+    """Engine with one chain loaded and (numpy mode) its draws injected."""
+    vis = np.asarray(vis)
+    ntimes, nfreqs = vis.shape
+    nmodes = np.asarray(fgmodes).shape[1]
+    ninv_diag = _diag_noise(Ninv, nfreqs)
+    basis0, lam0sq = _analyse_signal_cov(S)
+    if solver is None:
+        solver = "reference-cg" if rng == "numpy" else "exact"
+    if solver not in ("reference-cg", "exact"):
+        raise ValueError("solver must be 'reference-cg' or 'exact'")
+    eng = GibbsEngine(1, ntimes, nfreqs, nmodes, max_iters, rng=rng, cg_compat=(solver == "reference-cg"),
+                      refresh_omega=(rng == "philox"), keep=keep, general_basis0=basis0 is not None,
+                      seed=0 if seed is None else seed, device=device)
+    eng.load_chain(0, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=ps_prior, basis0=basis0)
+    if rng == "numpy":
+        if map_estimate:
+            oma = omb = None  # pspec.py:210-212
+        else:
+            oma, omb = _reference_gcr_draws(ntimes, nfreqs)
+        sd = None
+        if s_uniforms is not None:
+            sd = _s_draws_from_uniforms(s_uniforms, ps_prior if ps_prior is not None else np.zeros((2, nfreqs)), ntimes)
+        eng.set_draws(0, oma, omb, sd)
+    return eng
+
+
+def gcr_fgmodes(vis, w, matrices, fgmodes, f0=None, nproc=1, map_estimate=False, verbose=False,
+                rng="numpy", solver=None, device=0):
+    """GCR step for all times (pspec.py:238-310).  Returns ``(Ntimes, Nfreqs + Nmodes)`` samples.
+
+    ``f0`` / ``nproc`` are accepted for signature compatibility (the reference's CG ignores the
+    initial guess up to its tolerance; the device solve is direct and batched over times).
+    """
+    S = matrices[0][1]
+    Ni = matrices[0][2]
+    vis = np.asarray(vis)
+    # the reference multiplies the data by w again (pspec.py:221); Ni already carries the flags
+    eng = _single_chain_engine(vis, np.asarray(w), S, fgmodes, Ni, None, 1, rng, solver, map_estimate, (), None, device)
+    try:
+        eng.gcr()
+        out = eng.last_gcr(0)
+    finally:
+        eng.close()
+    return out
+
+
+def sample_S(s=None, sk=None, prior=None, device=0):
+    """pspec.py:67-127.  Draws one uniform per delay bin from numpy's global stream, like the
+    reference (explicitly for prior-bounded bins, inside ``invgamma.rvs`` for the others)."""
+    if s is None and sk is None:
+        raise ValueError("Must pass in s (real space) or sk (Fourier space) vector.")
+    if s is None:
+        sk = np.asarray(sk)
+        n = sk.shape[1]
+        U = _unitary_dft(n)
+        s = (sk / np.sqrt(n)) @ U.conj()  # sk = sqrt(n) U s  =>  s = U^H sk / sqrt(n)
+    s = _lib.c128(s)
+    nobs, nfreqs = s.shape
+    pr = _check_prior(prior, nfreqs)
+    u = np.array([np.random.uniform() for _ in range(nfreqs)])
+    draws = _lib.f64(_s_draws_from_uniforms(u, pr, nobs)[0])
+    out = np.empty(nfreqs)
+    pr = _lib.f64(pr)
+    _lib.check(_lib.lib().hp_sample_S(int(device), int(nobs), int(nfreqs), _lib.ptr(s), _lib.ptr(pr), _lib.ptr(draws),
+                                      _lib.ptr(out)))
+    return out
+
+
+def gibbs_step_fgmodes(vis, flags, signal_S, fgmodes, Ninv, ps_prior=None, f0=None, nproc=1, map_estimate=False,
+                       verbose=False, rng="numpy", solver=None, device=0):
+    """One Gibbs iteration (pspec.py:377-490).  ``vis`` is expected pre-multiplied by the flags,
+    as gibbs_sample_with_fg passes it (pspec.py:613)."""
+    vis = np.asarray(vis)
+    nfreqs = vis.shape[1]
+    flags = np.asarray(flags)
+    assert flags.shape == (nfreqs,), "`flags` array must have shape (Nfreqs,)"
+    pr = _check_prior(ps_prior, nfreqs)
+    u = np.array([np.random.uniform() for _ in range(nfreqs)])[None, :] if rng == "numpy" else None
+    eng = _single_chain_engine(vis, flags, signal_S, fgmodes, Ninv, pr, 1, rng, solver, map_estimate,
+                               ("cr", "fg", "chisq"), None, device, s_uniforms=u)
+    try:
+        eng.run(1)
+        out = (eng.signal_cr(0)[0], eng.signal_S(0), eng.signal_ps(0)[0], eng.fg_amps(0)[0], eng.chisq(0)[0],
+               float(eng.ln_post(0)[0]))
+    finally:
+        eng.close()
+    if verbose:
+        print(f"{out[5]:<12.1f}")
+    return out
+
+
+def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=100, seed=None, verbose=True,
+                         nproc=1, write_Niter=100, out_dir=None, map_estimate=False, rng="numpy", solver=None,
+                         device=0):
+    """Gibbs chain for one baseline (pspec.py:493-658); same arguments and return tuple:
+    ``signal_cr, signal_S, signal_ps, fg_amps, chisq, ln_post, write_time``.
+
+    Extra keyword arguments: ``rng`` / ``solver`` (see the module docstring) and ``device``.
+    ``nproc`` is accepted and ignored (all times are solved in one batched launch).
+    """
+    if map_estimate:
+        Niter = 1
+        write_Niter = 1
+    vis = np.asarray(vis)
+    ntimes, nfreqs = vis.shape
+    flags = np.asarray(flags)
+    fgmodes = np.asarray(fgmodes)
+    assert flags.shape == (nfreqs,), "`flags` array must have shape (Nfreqs,)"
+    assert fgmodes.shape[0] == nfreqs, "fgmodes must have shape (Nfreqs, Nmodes)"
+    Ninv = np.asarray(Ninv)
+    if len(Ninv.shape) == 3:
+        assert Ninv.shape[0] == ntimes, "Ninv shape must be (Ntimes, Nfreqs, Nfreqs) or (Nfreqs, Nfreqs)"
+    pr = _check_prior(ps_prior, nfreqs)
+    u = None
+    if rng == "numpy":
+        if map_estimate:
+            u = np.array([np.random.uniform() for _ in range(nfreqs)])[None, :]  # global stream, not reseeded
+        else:
+            u = np.random.RandomState(seed).uniform(size=(Niter, nfreqs))  # pspec.py:577
+    eng = _single_chain_engine(vis, flags, S_initial, fgmodes, Ninv, pr, Niter, rng, solver, map_estimate,
+                               ("cr", "fg", "chisq"), seed, device, s_uniforms=u)
+    write_time = 0.0
+    try:
+        if verbose:
+            print("Iter     ln Post")
+            print("-----    -------")
+        done = 0
+        while done < Niter:
+            chunk = min(write_Niter, Niter - done) if out_dir is not None else Niter - done
+            eng.run(chunk)
+            done += chunk
+            if out_dir is not None:
+                t0 = time.perf_counter()
+                utils.write_numpy_files(out_dir, eng.signal_cr(0), eng.signal_S(0), eng.signal_ps(0), eng.fg_amps(0),
+                                        eng.chisq(0), eng.ln_post(0))
+                write_time += time.perf_counter() - t0
+        bad = eng.info()
+        if np.any(bad != 0):
+            raise np.linalg.LinAlgError("GCR system not positive definite (Cholesky failed in block column "
+                                        f"{int(bad[0]) - 1})")
+        signal_cr = eng.signal_cr(0)
+        signal_S = eng.signal_S(0)
+        signal_ps = eng.signal_ps(0)
+        fg_amps = eng.fg_amps(0)
+        chisq = eng.chisq(0)
+        ln_post = eng.ln_post(0)
+    finally:
+        eng.close()
+    if verbose:
+        for i, lp in enumerate(ln_post):
+            print(f"{i + 1:<9d}{lp:<12.1f}")
+        print()
+    return signal_cr, signal_S, signal_ps, fg_amps, chisq, ln_post, write_time

@@ -1,0 +1,140 @@
+/* hydra_pspec_b200.h -- C ABI of the B200 Gibbs hot path (libhydra_pspec_b200.so).
+ *
+ * This is the boundary a maintainer of HydraRadio/hydra-pspec would bind (ctypes stub in
+ * INTEGRATION.md).  The reference is pure Python, so each entry point names the Python
+ * function(s) whose work it takes over (paths relative to the reference checkout).
+ *
+ * Conventions: plain pointers and sizes only.  complex128 arrays are interleaved (re, im)
+ * doubles in C order, i.e. exactly the memory of a numpy complex128 array.  All pointers are
+ * HOST pointers unless the name ends in _dev.  Every function returns 0 on success or a
+ * negative hp_status; hp_last_error() gives the message.  There is no CPU fallback: every
+ * compute entry point needs a CUDA device and fails with HP_ERR_CUDA otherwise.
+ */
+#ifndef HYDRA_PSPEC_B200_H
+#define HYDRA_PSPEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hp_engine hp_engine;
+
+enum hp_status { HP_OK = 0, HP_ERR_ARG = -1, HP_ERR_CUDA = -2, HP_ERR_SIZE = -3, HP_ERR_NUMERIC = -4 };
+
+enum hp_rng_mode {
+    HP_RNG_INJECTED = 0, /* draws supplied by the host: the reference's numpy streams */
+    HP_RNG_PHILOX = 1    /* device counter-based Philox4x32-10 */
+};
+
+/* outputs kept per iteration (ps and ln_post are always kept) */
+enum hp_keep { HP_KEEP_CR = 1, HP_KEEP_FG = 2, HP_KEEP_CHISQ = 4 };
+
+/* buffers readable with hp_engine_read */
+enum hp_buffer {
+    HP_BUF_PS = 0,      /* [iters][Nfreqs]            double     signal_ps   (pspec.py:592) */
+    HP_BUF_LNPOST = 1,  /* [iters]                    double     ln_post     (pspec.py:596) */
+    HP_BUF_CR = 2,      /* [iters][Ntimes][Nfreqs]    complex128 signal_cr   (pspec.py:590) */
+    HP_BUF_FG = 3,      /* [iters][Ntimes][Nmodes]    complex128 fg_amps     (pspec.py:593) */
+    HP_BUF_CHISQ = 4,   /* [iters][Ntimes][Nfreqs]    double     chisq       (pspec.py:595) */
+    HP_BUF_LAST_CR = 5, /* [Ntimes][Nfreqs]           complex128 signal part of the last GCR solve */
+    HP_BUF_LAST_FG = 6, /* [Ntimes][Nmodes]           complex128 fg amplitudes of the last GCR solve */
+    HP_BUF_PS_CUR = 7   /* [Nfreqs]                   double     current delay spectrum */
+};
+
+typedef struct hp_config {
+    int device;          /* CUDA device ordinal */
+    int nchains;         /* baselines resident in this engine (independent chains) */
+    int ntimes, nfreqs, nmodes;
+    int rng_mode;        /* hp_rng_mode */
+    int cg_compat;       /* 1: reproduce the reference's truncated CG (pspec.py:228) through the
+                            scalar model in csrc/hp_math.h; 0: exact solve */
+    int refresh_omega;   /* Philox only. 1: new GCR fluctuation draws every iteration; 0: the same
+                            draws in every iteration, as the reference does (pspec.py:195-197) */
+    int keep;            /* hp_keep bitmask */
+    int max_iters;       /* capacity of the per-iteration output buffers */
+    int general_basis0;  /* 1: S_initial is not delay-diagonal; hp_engine_load_chain gets its
+                            eigenvectors (first iteration runs in that basis) */
+    int profile;         /* 1: record per-kernel CUDA-event timings (hp_engine_kernel_ms) */
+    uint64_t seed;       /* Philox key */
+    void* stream;        /* cudaStream_t to launch on, or NULL for an engine-owned stream */
+} hp_config;
+
+/* Number of kernel classes reported by hp_engine_kernel_ms and their names. */
+#define HP_NUM_KERNEL_CLASSES 6
+const char* hp_kernel_class_name(int cls);
+
+int hp_engine_create(const hp_config* cfg, hp_engine** out);
+int hp_engine_destroy(hp_engine* e);
+
+/* Load one baseline (replaces the per-baseline set-up of gibbs_sample_with_fg, pspec.py:493-599,
+ * and the iteration-independent half of build_matrices, pspec.py:325-374).
+ *   vis        [Ntimes][Nfreqs] complex128  visibilities (NOT pre-multiplied by the flags)
+ *   flags      [Nfreqs] uint8, 1 = unflagged (pspec.py:520-522)
+ *   fgmodes    [Nfreqs][Nmodes] complex128
+ *   ninv_diag  [Nfreqs] diagonal of the inverse noise covariance
+ *   basis0     general_basis0 ? [Nfreqs][Nfreqs] complex128 eigenvectors (columns) of S_initial : NULL
+ *   lam0sq     [Nfreqs] eigenvalues of S_initial in that basis; for a delay-diagonal S_initial
+ *              these are diag(U S U^H) with U = fourier_operator(Nfreqs)/sqrt(Nfreqs)
+ *   ps_prior   [2][Nfreqs] (pspec.py:84-86; [0] upper, [1] lower; 0 = no prior)
+ */
+int hp_engine_load_chain(hp_engine* e, int chain, const double* vis, const uint8_t* flags, const double* fgmodes,
+                         const double* ninv_diag, const double* basis0, const double* lam0sq,
+                         const double* ps_prior);
+
+/* Injected draws (HP_RNG_INJECTED).
+ *   omega_a, omega_b [Ntimes][Nfreqs] complex128: the unit complex Gaussians of pspec.py:215-217
+ *                    (NULL, NULL = map_estimate, pspec.py:210-212)
+ *   s_draws [max_iters][Nfreqs]: per iteration and delay bin, the uniform u of pspec.py:58 for
+ *                    prior-bounded bins, or the invgamma(a = Ntimes-1) variate of pspec.py:125 otherwise
+ */
+int hp_engine_set_draws(hp_engine* e, int chain, const double* omega_a, const double* omega_b,
+                        const double* s_draws, int n_draw_iters);
+
+/* Run `niter` Gibbs iterations (gibbs_step_fgmodes, pspec.py:377-490) for all chains.
+ * Asynchronous on the engine's stream. */
+int hp_engine_run(hp_engine* e, int niter);
+/* Only the GCR step (gcr_fgmodes, pspec.py:238-310) with the current spectrum; results in
+ * HP_BUF_LAST_CR / HP_BUF_LAST_FG. */
+int hp_engine_gcr(hp_engine* e);
+int hp_engine_sync(hp_engine* e);
+int hp_engine_iterations_done(const hp_engine* e);
+/* Reset the iteration counter / output cursor (the spectrum state is kept). */
+int hp_engine_rewind(hp_engine* e);
+
+/* Copy results to the host.  iter0/niter select iterations for the per-iteration buffers. */
+int hp_engine_read(hp_engine* e, int chain, int buffer, int iter0, int niter, void* dst, size_t dst_bytes);
+/* signal_S of the reference's return value: F^H diag(ps / Nfreqs^2) F for the current spectrum
+ * (covariance_from_pspec, pspec.py:313-322).  dst [Nfreqs][Nfreqs] complex128. */
+int hp_engine_read_signal_S(hp_engine* e, int chain, double* dst);
+/* Cholesky status per chain of the last iteration (0 = ok). */
+int hp_engine_info(hp_engine* e, int* info_host);
+
+/* Accumulated device time per kernel class since creation or the last call with reset=1 (needs cfg.profile). */
+int hp_engine_kernel_ms(hp_engine* e, double* ms, int* launches, int reset);
+/* Total kernel launches issued by hp_engine_run / hp_engine_gcr so far. */
+long long hp_engine_launch_count(const hp_engine* e);
+
+/* sample_S (pspec.py:67-127) on its own: s [Ntimes][Nfreqs] complex128 signal realisations,
+ * prior [2][Nfreqs] or NULL, draws [Nfreqs] as in hp_engine_set_draws; out [Nfreqs]. */
+int hp_sample_S(int device, int ntimes, int nfreqs, const double* s, const double* prior, const double* draws,
+                double* out);
+
+/* utils.fourier_operator (utils.py:14-40), computed on the device; out [n][n] complex128. */
+int hp_fourier_operator(int device, int n, double* out);
+
+/* ---- test hooks (tests/ only): single kernels with host buffers ------------------------------- */
+int hp_test_zgemm(int M, int N, int K, const double* A, int transA, int conjA, const double* B, int transB, int conjB,
+                  const double* dk, double* C);
+int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, const double* Rfix, const double* wa,
+                       int cg_compat, double* Ldense, double* X, int* info);
+
+const char* hp_last_error(void);
+const char* hp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

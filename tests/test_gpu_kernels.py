@@ -1,0 +1,85 @@
+"""Single-kernel checks through the C ABI test hooks, against numpy.  GPU only."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from hydra_pspec_b200 import _lib
+    return _lib
+
+
+def crandn(rng, *shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (70, 45, 33), (7, 130, 5), (200, 136, 120)])
+@pytest.mark.parametrize("tA,cA,tB,cB", [(0, 0, 0, 0), (1, 1, 0, 0), (0, 0, 1, 1), (1, 0, 1, 1)])
+def test_zgemm(M, N, K, tA, cA, tB, cB):
+    L = _lib()
+    rng = np.random.default_rng(M * 1000 + N + K)
+    A = crandn(rng, M, K)
+    B = crandn(rng, K, N)
+    dk = rng.random(K) + 0.5
+    want = (A * dk[None, :]) @ B
+    As = A.T if tA else A
+    Bs = B.T if tB else B
+    As = np.ascontiguousarray(As.conj() if cA else As)
+    Bs = np.ascontiguousarray(Bs.conj() if cB else Bs)
+    C = np.empty((M, N), dtype=np.complex128)
+    L.check(L.lib().hp_test_zgemm(M, N, K, L.ptr(As), tA, cA, L.ptr(Bs), tB, cB, L.ptr(dk), L.ptr(C)))
+    assert rel(C, want) < 1e-14
+
+
+def test_fourier_operator_matches_reference_definition():
+    from hydra_pspec_b200 import utils
+    for n in (4, 5, 120, 384):
+        i = np.arange(n) - n // 2
+        want = np.exp(-2 * np.pi * 1j * (i.reshape(-1, 1) * i.reshape(1, -1) / n))  # utils.py:36-38
+        got = utils.fourier_operator(n)
+        assert np.max(np.abs(got - want)) < 5e-13  # the reference's own argument is only good to ~n*eps
+
+
+@pytest.mark.parametrize("n,m,T", [(32, 0, 16), (20, 4, 5), (64, 8, 33), (120, 12, 24), (384, 32, 48)])
+def test_chol_solve(n, m, T):
+    L = _lib()
+    rng = np.random.default_rng(n + m + T)
+    N = n + m
+    Bm = crandn(rng, n + 8, N)
+    G = Bm.conj().T @ Bm / (n + 8)
+    G = (G + G.conj().T) / 2
+    lam = np.concatenate([0.3 + rng.random(n), np.ones(m)])
+    J = np.concatenate([np.ones(n), np.zeros(m)])
+    Mmat = np.diag(J) + lam[:, None] * G * lam[None, :]
+    Rfix = crandn(rng, T, N)
+    wa = crandn(rng, T, n)
+    R = Rfix * lam[None, :]
+    R[:, :n] += wa
+    Xw = np.linalg.solve(Mmat, R.T).T
+    Lw = np.linalg.cholesky(Mmat)
+    Ld = np.empty((N, N), dtype=np.complex128)
+    X = np.empty((T, N), dtype=np.complex128)
+    info = np.zeros(1, dtype=np.int32)
+    G = np.ascontiguousarray(G)
+    L.check(L.lib().hp_test_chol_solve(n, m, T, L.ptr(G), L.ptr(lam), L.ptr(Rfix), L.ptr(wa), 0, L.ptr(Ld), L.ptr(X),
+                                       L.ptr(info)))
+    assert info[0] == 0
+    assert rel(Ld, Lw) < 1e-12
+    assert rel(X, Xw) < 1e-11
+
+
+def test_chol_reports_indefinite():
+    L = _lib()
+    n, m, T = 40, 0, 4
+    G = -2.0 * np.eye(n, dtype=np.complex128)  # M = I - 2 I is negative definite
+    lam = np.ones(n)
+    Rfix = np.zeros((T, n), dtype=np.complex128)
+    X = np.empty((T, n), dtype=np.complex128)
+    info = np.zeros(1, dtype=np.int32)
+    L.check(L.lib().hp_test_chol_solve(n, m, T, L.ptr(G), L.ptr(lam), L.ptr(Rfix), None, 0, None, L.ptr(X), L.ptr(info)))
+    assert info[0] != 0
