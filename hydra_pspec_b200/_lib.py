@@ -46,6 +46,7 @@ _SIGNATURES = {
     "hp_engine_read_signal_S": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hp_engine_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_engine_kernel_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hp_engine_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_engine_launch_count": (C.c_longlong, [C.c_void_p]),
     "hp_kernel_class_name": (C.c_char_p, [C.c_int]),
     "hp_sample_S": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -54,6 +55,9 @@ _SIGNATURES = {
                                 C.c_int, C.c_void_p, C.c_void_p]),
     "hp_test_chol_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_fp64_peak_tflops": (C.c_double, [C.c_int, C.c_double]),
+    "hp_pinned_alloc": (C.c_void_p, [C.c_size_t]),
+    "hp_pinned_free": (None, [C.c_void_p]),
     "hp_last_error": (C.c_char_p, []),
     "hp_version": (C.c_char_p, []),
 }
@@ -96,3 +100,17 @@ def c128(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (freed when the array is garbage collected)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = lib().hp_pinned_alloc(max(nbytes, 1))
+    if not p:
+        raise HydraLibError("cudaHostAlloc failed")
+    buf = (C.c_char * max(nbytes, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib().hp_pinned_free, p)
+    return arr

@@ -510,6 +510,12 @@ int hp_engine_run(hp_engine* e, int niter) {
     return HP_OK;
 }
 
+int hp_engine_set_profile(hp_engine* e, int on) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    e->cfg.profile = on ? 1 : 0;
+    return HP_OK;
+}
+
 int hp_engine_sync(hp_engine* e) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
     CU_TRY(cudaSetDevice(e->cfg.device));

@@ -80,4 +80,59 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
     return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
 }
 
+// ---- measurement helpers -----------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+}  // namespace
+
+// Measured FP64 tensor-pipe peak (DMMA.8x8x4 issue loop, all SMs), TFLOP/s.  Same loop as
+// profiles/microbench/fp64_peak.cu; used by bench.py as the roofline denominator.
+double hp_fp64_peak_tflops(int device, double seconds) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    int nsm = 0;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    double* out;
+    if (cudaMalloc(&out, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000, bps = 4;
+    k_fp64_peak<<<nsm * bps, 256>>>(out, iters / 10, 1.0000001, 1e-9);
+    cudaDeviceSynchronize();
+    double best = 0.0, spent = 0.0;
+    while (spent < seconds * 1e3) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<nsm * bps, 256>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 8 * 256 / 32.0 * iters * 256.0 * nsm * bps / ms * 1e-9;
+        if (tf > best) best = tf;
+        spent += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    return best;
+}
+
+void* hp_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void hp_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 }  // extern "C"

@@ -254,6 +254,9 @@ class GibbsEngine:
     def launch_count(self):
         return _lib.lib().hp_engine_launch_count(self._h)
 
+    def set_profile(self, on):
+        _lib.check(_lib.lib().hp_engine_set_profile(self._h, int(bool(on))))
+
     def kernel_ms(self, reset=False):
         ms = np.zeros(_lib.HP_NUM_KERNEL_CLASSES)
         nl = np.zeros(_lib.HP_NUM_KERNEL_CLASSES, dtype=np.int32)

@@ -114,6 +114,8 @@ int hp_engine_info(hp_engine* e, int* info_host);
 
 /* Accumulated device time per kernel class since creation or the last call with reset=1 (needs cfg.profile). */
 int hp_engine_kernel_ms(hp_engine* e, double* ms, int* launches, int reset);
+/* Switch the per-kernel event timing on or off at run time. */
+int hp_engine_set_profile(hp_engine* e, int on);
 /* Total kernel launches issued by hp_engine_run / hp_engine_gcr so far. */
 long long hp_engine_launch_count(const hp_engine* e);
 
@@ -130,6 +132,13 @@ int hp_test_zgemm(int M, int N, int K, const double* A, int transA, int conjA, c
                   const double* dk, double* C);
 int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, const double* Rfix, const double* wa,
                        int cg_compat, double* Ldense, double* X, int* info);
+
+/* ---- measurement helpers ---------------------------------------------------------------------- */
+/* FP64 tensor-pipe (DMMA.8x8x4) peak of the device measured with an issue loop for ~`seconds`; TFLOP/s. */
+double hp_fp64_peak_tflops(int device, double seconds);
+/* page-locked host memory for the host<->device copies of the end-to-end path */
+void* hp_pinned_alloc(size_t bytes);
+void hp_pinned_free(void* p);
 
 const char* hp_last_error(void);
 const char* hp_version(void);

@@ -1,0 +1,117 @@
+"""The C-ABI library loads and exports every symbol include/hydra_pspec_b200.h declares; host-side
+logic of the drop-in module (validation, draw streams, covariance analysis).  CPU only -- no
+compute entry point is called."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_symbols():
+    txt = (ROOT / "include" / "hydra_pspec_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hp_[a-z0-9_A-Z]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hydra_pspec_b200 import _lib
+    L = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in the header but not exported"
+    for s in _lib.EXPORTED_SYMBOLS:
+        assert s in syms, f"{s} bound by _lib.py but not declared in the header"
+    assert L.hp_version().startswith(b"hydra_pspec_b200")
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hydra_pspec_b200 import _lib, pspec, utils
+    with pytest.raises(_lib.HydraLibError, match="no CPU fallback"):
+        utils.fourier_operator(8)
+    with pytest.raises(_lib.HydraLibError, match="no CPU fallback"):
+        pspec.gibbs_sample_with_fg(np.ones((4, 8), complex), np.ones(8, bool), np.eye(8), np.ones((8, 2)), np.eye(8),
+                                   np.zeros((2, 8)), Niter=1, verbose=False)
+
+
+def test_product_does_not_import_oracle():
+    for f in (ROOT / "hydra_pspec_b200").rglob("*.py"):
+        assert "oracle" not in f.read_text(), f
+    for f in (ROOT / "hydra_pspec_b200" / "csrc").glob("*.cu*"):
+        assert "oracle/" not in f.read_text().replace("oracle/hydra_oracle.py:cg_theta for the derivation", ""), f
+
+
+def test_reference_draw_streams(golden_dir):
+    from hydra_pspec_b200 import pspec
+    fn = np.load(golden_dir / "functions.npz")
+    oma, omb = pspec._reference_gcr_draws(6, 6)
+    for idx in (0, 5):
+        assert np.array_equal(oma[idx], fn[f"gcrdraw_a_{idx}"])
+        assert np.array_equal(omb[idx], fn[f"gcrdraw_b_{idx}"])
+
+
+def test_s_draw_transformation():
+    import scipy.stats
+    from hydra_pspec_b200 import pspec
+    u = np.random.default_rng(0).uniform(size=(3, 10))
+    prior = np.zeros((2, 10))
+    prior[:, 4] = [2.0, 0.1]
+    d = pspec._s_draws_from_uniforms(u, prior, 25)
+    assert np.array_equal(d[:, 4], u[:, 4])
+    want = scipy.stats.invgamma.ppf(u, a=24.0)  # what invgamma.rvs(a) evaluates for the same uniform
+    mask = np.ones(10, bool)
+    mask[4] = False
+    assert np.allclose(d[:, mask], want[:, mask], rtol=1e-13)
+
+
+def test_prior_validation_errors():
+    from hydra_pspec_b200 import pspec
+    for bad, msg in [([[1.0], [0.0]], "prior_min must be greater than zero"),
+                     ([[np.inf], [1.0]], "prior_max must be finite"),
+                     ([[1.0], [2.0]], "prior_max must be greater than prior_min")]:
+        with pytest.raises(ValueError, match=msg):
+            pspec._check_prior(np.array(bad), 1)
+    assert pspec._check_prior(None, 5).shape == (2, 5)
+
+
+def test_signal_cov_analysis():
+    from hydra_pspec_b200 import pspec
+    n = 12
+    idx = np.arange(n) - n // 2
+    fop = np.exp(-2j * np.pi * np.outer(idx, idx) / n)
+    p = np.random.default_rng(1).random(n) + 0.2
+    S = fop.conj().T @ np.diag(p / n ** 2) @ fop
+    b0, lam = pspec._analyse_signal_cov(S)
+    assert b0 is None and np.allclose(lam, p / n)      # Lambda = n q = ps / n
+    b0, lam = pspec._analyse_signal_cov(np.eye(n))
+    assert b0 is None and np.allclose(lam, 1.0)
+    X = np.random.default_rng(2).standard_normal((n, n))
+    b0, lam = pspec._analyse_signal_cov(X @ X.T + np.eye(n))
+    assert b0 is not None and np.allclose((b0 * lam) @ b0.conj().T, X @ X.T + np.eye(n))
+
+
+def test_host_helpers_match_reference(golden_dir):
+    from hydra_pspec_b200 import pspec
+    fn = np.load(golden_dir / "functions.npz")
+    idx = np.arange(12) - 6
+    fop = np.exp(-2j * np.pi * np.outer(idx, idx) / 12)
+    assert np.allclose(pspec.covariance_from_pspec(fn["cov_ps"], fop), fn["cov_out"], rtol=1e-13, atol=1e-15)
+    assert np.allclose(pspec.sprior(fn["sprior_in"], 2, 10.0), fn["sprior_out"], rtol=1e-13)
+    for k, ((alpha, beta, lo, hi), want) in enumerate(zip(fn["invsamp_cases"], fn["invsamp_out"])):
+        np.random.seed(1000 + 10 * (k // 4) + k % 4)
+        assert abs(pspec.inversion_sample_invgamma(alpha, beta, lo, hi) - want) < 1e-13 * want
+
+
+def test_dense_noise_is_refused_loudly():
+    from hydra_pspec_b200 import pspec
+    N = np.eye(4) + 0.1
+    with pytest.raises(NotImplementedError):
+        pspec._diag_noise(N, 4)
