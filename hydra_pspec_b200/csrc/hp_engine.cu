@@ -131,6 +131,7 @@ struct hp_engine {
     bool eta_valid = false;
     int iter = 0;     // Gibbs iterations since the chains were loaded (RNG counter, basis choice)
     int out_pos = 0;  // cursor in the per-iteration output buffers
+    uint32_t draw_counter = 0;  // Philox counter of the GCR fluctuation draws (advances per GCR step)
     const double* last_sf = nullptr;  // where the last GCR solve's frequency-space signal lives
     long long last_sf_bs = 0;         // its batch stride (complex elements)
     long long launches = 0;
@@ -326,6 +327,7 @@ int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* 
     CU_TRY(cudaGetLastError());
     e->iter = 0;
     e->out_pos = 0;
+    e->draw_counter = 0;
     e->eta_valid = false;
     return HP_OK;
 }
@@ -391,7 +393,7 @@ static void enqueue_noise(hp_engine* e, Basis& b, uint32_t iter) {
 // GCR step: chol + solve + transform to frequency space.  `b` is the basis in use.
 static void enqueue_gcr(hp_engine* e, Basis& b, double* sf_dst, long long sf_bs) {
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
-    const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : (uint32_t)e->iter;
+    const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
     if (philox && (e->cfg.refresh_omega || !e->eta_valid || &b == &e->b0 || e->iter == 1)) {
         enqueue_noise(e, b, draw_iter);
         e->eta_valid = true;
