@@ -12,14 +12,14 @@ HP_RNG_INJECTED, HP_RNG_PHILOX = 0, 1
 HP_KEEP_CR, HP_KEEP_FG, HP_KEEP_CHISQ = 1, 2, 4
 (HP_BUF_PS, HP_BUF_LNPOST, HP_BUF_CR, HP_BUF_FG, HP_BUF_CHISQ, HP_BUF_LAST_CR, HP_BUF_LAST_FG,
  HP_BUF_PS_CUR) = range(8)
-HP_NUM_KERNEL_CLASSES = 6
+HP_NUM_KERNEL_CLASSES = 5
 
 
 class HPConfig(C.Structure):
     _fields_ = [
         ("device", C.c_int), ("nchains", C.c_int), ("ntimes", C.c_int), ("nfreqs", C.c_int),
         ("nmodes", C.c_int), ("rng_mode", C.c_int), ("cg_compat", C.c_int), ("refresh_omega", C.c_int),
-        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int),
+        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("force_dense_transforms", C.c_int),
         ("seed", C.c_uint64), ("stream", C.c_void_p),
     ]
 

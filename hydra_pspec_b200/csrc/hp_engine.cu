@@ -105,7 +105,7 @@ struct Basis {
     }
 };
 
-enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4, CLS_NOISE = 5 };
+enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4 };
 
 }  // namespace
 
@@ -121,14 +121,17 @@ struct hp_engine {
     double *Lp = nullptr, *Linvp = nullptr;
     int* info = nullptr;
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
-    double *Em = nullptr, *Eu = nullptr, *lnp1 = nullptr, *eta = nullptr, *z = nullptr;
+    double *Em = nullptr, *Eu = nullptr, *lnp1 = nullptr;
     double* sdraws = nullptr;
     double *ps_out = nullptr, *lnpost_out = nullptr, *cr_out = nullptr, *fg_out = nullptr, *chisq_out = nullptr;
     double *Gd = nullptr, *stage = nullptr, *vecn = nullptr;  // set-up scratch
+    hp::FftPlan plan{};
+    bool fft_ok = false;
+    int ntilesE = 0;
+    double *tw = nullptr, *Empart = nullptr, *Eupart = nullptr;
     std::vector<uint8_t> flagged;  // per chain: any channel flagged
     std::vector<uint8_t> have_omega;
     bool any_flagged = false;
-    bool eta_valid = false;
     int iter = 0;     // Gibbs iterations since the chains were loaded (RNG counter, basis choice)
     int out_pos = 0;  // cursor in the per-iteration output buffers
     uint32_t draw_counter = 0;  // Philox counter of the GCR fluctuation draws (advances per GCR step)
@@ -161,7 +164,7 @@ extern "C" {
 const char* hp_last_error(void) { return g_err.c_str(); }
 const char* hp_version(void) { return "hydra_pspec_b200 0.1 (sm_100a)"; }
 const char* hp_kernel_class_name(int cls) {
-    static const char* names[HP_NUM_KERNEL_CLASSES] = {"chol", "solve", "transform", "post", "sample", "noise"};
+    static const char* names[HP_NUM_KERNEL_CLASSES] = {"chol", "solve", "transform", "post", "sample"};
     return (cls >= 0 && cls < HP_NUM_KERNEL_CLASSES) ? names[cls] : "?";
 }
 
@@ -172,8 +175,9 @@ int hp_engine_destroy(hp_engine* e) {
     for (auto& x : e->ev) cudaEventDestroy(x);
     e->bF.release(); e->b0.release();
     double* ptrs[] = {e->Fop, e->U, e->lam, e->ps, e->wd, e->w, e->ninvd, e->ni, e->nu, e->Ft, e->prior, e->Lp, e->Linvp,
-                      e->X, e->Ssc, e->Ppart, e->Sf, e->Wm, e->Tmp, e->Em, e->Eu, e->lnp1, e->eta, e->z, e->sdraws,
-                      e->ps_out, e->lnpost_out, e->cr_out, e->fg_out, e->chisq_out, e->Gd, e->stage, e->vecn};
+                      e->X, e->Ssc, e->Ppart, e->Sf, e->Wm, e->Tmp, e->Em, e->Eu, e->lnp1, e->sdraws,
+                      e->ps_out, e->lnpost_out, e->cr_out, e->fg_out, e->chisq_out, e->Gd, e->stage, e->vecn,
+                      e->tw, e->Empart, e->Eupart};
     for (double* p : ptrs) cudaFree(p);
     cudaFree(e->info);
     if (e->own_stream) cudaStreamDestroy(e->st);
@@ -225,15 +229,14 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     A_TRY(dalloc(&e->wd, 2 * C * Tp * n)); A_TRY(dalloc(&e->w, C * n)); A_TRY(dalloc(&e->ninvd, C * n));
     A_TRY(dalloc(&e->ni, C * n)); A_TRY(dalloc(&e->nu, C * n)); A_TRY(dalloc(&e->Ft, 2 * C * (m ? m : 1) * n));
     A_TRY(dalloc(&e->prior, C * 2 * n));
-    A_TRY(dalloc(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles));
-    A_TRY(dalloc(&e->Linvp, C * e->nblk * hp::kBlkDoubles));
+    A_TRY(dalloc(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles));
+    A_TRY(dalloc(&e->Linvp, C * e->nblk * hp::kLBlkDoubles));
     A_TRY(dalloc(&e->info, C));
     A_TRY(dalloc(&e->X, 2 * C * Tp * Np)); A_TRY(dalloc(&e->Ssc, 2 * C * Tp * n));
     A_TRY(dalloc(&e->Ppart, C * e->ntiles * n)); A_TRY(dalloc(&e->Sf, 2 * C * Tp * n));
     A_TRY(dalloc(&e->Wm, 2 * C * Tp * n)); A_TRY(dalloc(&e->Tmp, 2 * C * Tp * n));
     A_TRY(dalloc(&e->Em, C * n)); A_TRY(dalloc(&e->Eu, C * n)); A_TRY(dalloc(&e->lnp1, C * Tp));
-    if (cfg->rng_mode == HP_RNG_PHILOX) { A_TRY(dalloc(&e->eta, 2 * C * Tp * Np)); A_TRY(dalloc(&e->z, 2 * C * Tp * n)); }
-    else A_TRY(dalloc(&e->sdraws, C * I * n));
+    if (cfg->rng_mode != HP_RNG_PHILOX) A_TRY(dalloc(&e->sdraws, C * I * n));
     A_TRY(dalloc(&e->ps_out, C * I * n)); A_TRY(dalloc(&e->lnpost_out, C * I));
     if (cfg->keep & HP_KEEP_CR) A_TRY(dalloc(&e->cr_out, 2 * C * I * T * n));
     if (cfg->keep & HP_KEEP_FG) A_TRY(dalloc(&e->fg_out, 2 * C * I * T * (m ? m : 1)));
@@ -241,11 +244,17 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     A_TRY(dalloc(&e->Gd, 2 * (size_t)e->N * e->N));
     A_TRY(dalloc(&e->stage, 2 * (T * n > n * n ? T * n : n * n)));
     A_TRY(dalloc(&e->vecn, 4 * n));
+    e->fft_ok = hp::make_fft_plan(e->n, &e->plan) && hp::postfft_smem_bytes(e->n, e->m) <= (size_t)max_smem &&
+                !cfg->force_dense_transforms;
+    e->ntilesE = hp::postfft_tiles(e->T);
+    A_TRY(dalloc(&e->tw, 2 * n));
+    A_TRY(dalloc(&e->Empart, C * e->ntilesE * n)); A_TRY(dalloc(&e->Eupart, C * e->ntilesE * n));
 #undef A_TRY
     e->flagged.assign(C, 0);
     e->have_omega.assign(C, 0);
     hp::launch_fourier_operator(e->Fop, e->n, 1.0, e->st);
     hp::launch_fourier_operator(e->U, e->n, 1.0 / std::sqrt((double)e->n), e->st);
+    hp::launch_twiddles(e->tw, e->n, e->st);
     if (cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         hp_engine_destroy(e);
         return fail(HP_ERR_CUDA, "engine initialisation kernels failed");
@@ -328,7 +337,6 @@ int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* 
     e->iter = 0;
     e->out_pos = 0;
     e->draw_counter = 0;
-    e->eta_valid = false;
     return HP_OK;
 }
 
@@ -376,28 +384,21 @@ int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double
     return HP_OK;
 }
 
-// noise term of this iteration (Philox):  eta = B^H (nu * omega_b)
-static void enqueue_noise(hp_engine* e, Basis& b, uint32_t iter) {
-    e->prof_begin(CLS_NOISE);
-    hp::launch_noise_draw(e->z, e->nu, e->T, e->Tp, e->n, e->C, (uint32_t)e->cfg.seed, (uint32_t)(e->cfg.seed >> 32), iter,
-                          nullptr, e->st);
-    hp::ZgemmArgs r{};
-    r.A = e->z; r.sAi = e->n; r.sAk = 1; r.bsA = (long long)e->Tp * e->n;
-    r.B = b.Bmat; r.sBk = e->Np; r.sBj = 1; r.conjB = 1; r.bsB = (long long)e->n * e->Np;
-    r.C = e->eta; r.sCi = e->Np; r.sCj = 1; r.bsC = (long long)e->Tp * e->Np;
-    r.M = e->Tp; r.N = e->N; r.K = e->n; r.accumulate = 0; r.alpha = 1.0; r.batch = e->C;
-    hp::launch_zgemm(r, e->st);
-    e->prof_end(CLS_NOISE, 2);
-}
+// Output slots of one Gibbs iteration (null = not kept).
+struct IterOut {
+    double* sf; long long sf_bs;            // frequency-space signal (scratch or signal_cr slot)
+    double* fg; long long fg_bs;
+    double* chisq; long long chisq_bs;
+};
 
-// GCR step: chol + solve + transform to frequency space.  `b` is the basis in use.
-static void enqueue_gcr(hp_engine* e, Basis& b, double* sf_dst, long long sf_bs) {
+// GCR step (gcr_fgmodes) and everything of gibbs_step_fgmodes up to the power-spectrum draw:
+// chol + solve + back-transform + residual statistics.  `b` is the basis in use.
+static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o) {
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
+    const bool general = &b == &e->b0;
+    // Philox: the fluctuation term is xi ~ CN(0, I) added between the two triangular solves
+    // (hp_solve.cu); refresh_omega = 0 re-uses the same xi in every iteration.
     const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
-    if (philox && (e->cfg.refresh_omega || !e->eta_valid || &b == &e->b0 || e->iter == 1)) {
-        enqueue_noise(e, b, draw_iter);
-        e->eta_valid = true;
-    }
     e->prof_begin(CLS_CHOL);
     hp::CholArgs ca{};
     ca.Gp = b.Gp; ca.lam = e->lam; ca.Lp = e->Lp; ca.Linvp = e->Linvp; ca.info = e->info;
@@ -405,14 +406,15 @@ static void enqueue_gcr(hp_engine* e, Basis& b, double* sf_dst, long long sf_bs)
     hp::launch_chol(ca, e->st);
     e->prof_end(CLS_CHOL, 1);
 
+    const bool fused_inverse = e->fft_ok && !general;  // s = U^H (lam ytilde) inside k_post_fft
     e->prof_begin(CLS_SOLVE);
     hp::SolveArgs sa{};
     sa.Lp = e->Lp; sa.Linvp = e->Linvp; sa.lam = e->lam;
-    sa.Rfix = b.Rfix; sa.eta = philox ? e->eta : nullptr;
+    sa.Rfix = b.Rfix; sa.eta = nullptr;
     bool any_omega = false;
     for (auto h : e->have_omega) any_omega |= (h != 0);
     sa.wa = (!philox && any_omega) ? b.wa : nullptr;
-    sa.X = e->X; sa.Ssc = e->Ssc; sa.Ppart = e->Ppart;
+    sa.X = e->X; sa.Ssc = fused_inverse ? nullptr : e->Ssc; sa.Ppart = e->Ppart;
     sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = e->C; sa.T = e->T;
     sa.philox_wa = philox ? 1 : 0;
     sa.cg_compat = e->cfg.cg_compat;
@@ -421,24 +423,73 @@ static void enqueue_gcr(hp_engine* e, Basis& b, double* sf_dst, long long sf_bs)
     hp::launch_solve(sa, e->st);
     e->prof_end(CLS_SOLVE, 1);
 
-    // s = Q (lam * ytilde), written either to the scratch buffer or straight into the signal_cr slot
-    e->prof_begin(CLS_TRANSFORM);
-    hp::ZgemmArgs t{};
-    t.A = e->Ssc; t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
-    t.B = b.Bmat; t.sBk = 1; t.sBj = e->Np; t.bsB = (long long)e->n * e->Np;
-    t.C = sf_dst; t.sCi = e->n; t.sCj = 1; t.bsC = sf_bs;
-    t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
-    hp::launch_zgemm(t, e->st);
-    e->prof_end(CLS_TRANSFORM, 1);
-    e->last_sf = sf_dst;
-    e->last_sf_bs = sf_bs;
+    if (!fused_inverse) {
+        // s = Q (lam * ytilde) as a dense product (general eigenbasis, or Nfreqs without an FFT plan)
+        e->prof_begin(CLS_TRANSFORM);
+        hp::ZgemmArgs t{};
+        t.A = e->Ssc; t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
+        t.B = b.Bmat; t.sBk = 1; t.sBj = e->Np; t.bsB = (long long)e->n * e->Np;
+        t.C = o.sf; t.sCi = e->n; t.sCj = 1; t.bsC = o.sf_bs;
+        t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
+        hp::launch_zgemm(t, e->st);
+        e->prof_end(CLS_TRANSFORM, 1);
+    }
+    e->last_sf = o.sf;
+    e->last_sf_bs = o.sf_bs;
+
+    if (e->fft_ok) {
+        e->prof_begin(CLS_POST);
+        hp::PostFftArgs pa{};
+        pa.plan = e->plan; pa.tw = e->tw; pa.X = e->X; pa.lam = e->lam; pa.Sf = o.sf; pa.sf_bs = o.sf_bs;
+        pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
+        pa.fg_out = o.fg; pa.fg_bs = o.fg_bs; pa.chisq_out = o.chisq; pa.chisq_bs = o.chisq_bs;
+        pa.lnp1 = e->lnp1;
+        pa.Empart = e->any_flagged ? e->Empart : nullptr;
+        pa.Eupart = general ? e->Eupart : nullptr;
+        pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C; pa.do_inverse = fused_inverse ? 1 : 0;
+        hp::launch_post_fft(pa, e->st);
+        e->prof_end(CLS_POST, 1);
+        return;
+    }
+    // dense fallback for Nfreqs with a large prime factor
+    e->prof_begin(CLS_POST);
+    hp::PostArgs pa{};
+    pa.Sf = o.sf; pa.sf_bs = o.sf_bs; pa.X = e->X; pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
+    pa.fg_out = o.fg; pa.fg_bs = o.fg_bs; pa.chisq_out = o.chisq; pa.chisq_bs = o.chisq_bs;
+    pa.Wm = e->any_flagged ? e->Wm : nullptr; pa.Rm = nullptr; pa.lnp1 = e->lnp1;
+    pa.n = e->n; pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C;
+    hp::launch_post(pa, e->st);
+    e->prof_end(CLS_POST, 1);
+    if (e->any_flagged || general) {
+        e->prof_begin(CLS_TRANSFORM);
+        int nl2 = 0;
+        hp::ZgemmArgs t{};
+        t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
+        t.B = e->U; t.sBk = 1; t.sBj = e->n; t.bsB = 0;
+        t.C = e->Tmp; t.sCi = e->n; t.sCj = 1; t.bsC = (long long)e->Tp * e->n;
+        t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
+        if (e->any_flagged) {
+            t.A = e->Wm;
+            hp::launch_zgemm(t, e->st);
+            hp::launch_colsumsq(e->Tmp, e->Em, e->T, e->Tp, e->n, e->C, e->st);
+            nl2 += 2;
+        }
+        if (general) {
+            t.A = o.sf; t.bsA = o.sf_bs;
+            hp::launch_zgemm(t, e->st);
+            hp::launch_colsumsq(e->Tmp, e->Eu, e->T, e->Tp, e->n, e->C, e->st);
+            nl2 += 2;
+        }
+        e->prof_end(CLS_TRANSFORM, nl2);
+    }
 }
 
 int hp_engine_gcr(hp_engine* e) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
     CU_TRY(cudaSetDevice(e->cfg.device));
     Basis& b = (e->cfg.general_basis0 && e->iter == 0) ? e->b0 : e->bF;
-    enqueue_gcr(e, b, e->Sf, (long long)e->Tp * e->n);
+    IterOut o{e->Sf, (long long)e->Tp * e->n, nullptr, 0, nullptr, 0};
+    enqueue_gcr(e, b, o);
     CU_TRY(cudaGetLastError());
     return HP_OK;
 }
@@ -454,46 +505,19 @@ int hp_engine_run(hp_engine* e, int niter) {
         const int it = e->out_pos;
         const bool general = e->cfg.general_basis0 && e->iter == 0;
         Basis& b = general ? e->b0 : e->bF;
-        double* sf = e->cr_out ? e->cr_out + 2 * (size_t)it * T * n : e->Sf;
-        const long long sf_bs = e->cr_out ? (long long)(I * T * n) : (long long)(Tp * n);
-        enqueue_gcr(e, b, sf, sf_bs);
-
-        e->prof_begin(CLS_POST);
-        hp::PostArgs pa{};
-        pa.Sf = sf; pa.sf_bs = sf_bs; pa.X = e->X; pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
-        pa.fg_out = e->fg_out ? e->fg_out + 2 * (size_t)it * T * m : nullptr; pa.fg_bs = 2 * (long long)(I * T * m);
-        pa.chisq_out = e->chisq_out ? e->chisq_out + (size_t)it * T * n : nullptr; pa.chisq_bs = (long long)(I * T * n);
-        pa.Wm = e->any_flagged ? e->Wm : nullptr; pa.Rm = nullptr; pa.lnp1 = e->lnp1;
-        pa.n = e->n; pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C;
-        hp::launch_post(pa, e->st);
-        e->prof_end(CLS_POST, 1);
-
-        if (e->any_flagged || general) {
-            e->prof_begin(CLS_TRANSFORM);
-            int nl2 = 0;
-            hp::ZgemmArgs t{};
-            t.sAi = e->n; t.sAk = 1; t.bsA = (long long)Tp * n;
-            t.B = e->U; t.sBk = 1; t.sBj = e->n; t.bsB = 0;
-            t.C = e->Tmp; t.sCi = e->n; t.sCj = 1; t.bsC = (long long)Tp * n;
-            t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
-            if (e->any_flagged) {
-                t.A = e->Wm;
-                hp::launch_zgemm(t, e->st);
-                hp::launch_colsumsq(e->Tmp, e->Em, e->T, e->Tp, e->n, e->C, e->st);
-                nl2 += 2;
-            }
-            if (general) {
-                t.A = sf; t.bsA = sf_bs;
-                hp::launch_zgemm(t, e->st);
-                hp::launch_colsumsq(e->Tmp, e->Eu, e->T, e->Tp, e->n, e->C, e->st);
-                nl2 += 2;
-            }
-            e->prof_end(CLS_TRANSFORM, nl2);
-        }
+        IterOut o{};
+        o.sf = e->cr_out ? e->cr_out + 2 * (size_t)it * T * n : e->Sf;
+        o.sf_bs = e->cr_out ? (long long)(I * T * n) : (long long)(Tp * n);
+        o.fg = e->fg_out ? e->fg_out + 2 * (size_t)it * T * m : nullptr; o.fg_bs = 2 * (long long)(I * T * m);
+        o.chisq = e->chisq_out ? e->chisq_out + (size_t)it * T * n : nullptr; o.chisq_bs = (long long)(I * T * n);
+        enqueue_gcr(e, b, o);
 
         e->prof_begin(CLS_SAMPLE);
         hp::SampleArgs sp{};
-        sp.Ppart = e->Ppart; sp.Eu = e->Eu; sp.Em = e->any_flagged ? e->Em : nullptr;
+        sp.Ppart = e->Ppart;
+        sp.ntilesE = e->fft_ok ? e->ntilesE : 0;
+        sp.Eu = e->fft_ok ? e->Eupart : e->Eu;
+        sp.Em = e->any_flagged ? (e->fft_ok ? e->Empart : e->Em) : nullptr;
         sp.lnp1 = e->lnp1; sp.lnp1_dense = nullptr; sp.prior = e->prior;
         sp.draws = philox ? nullptr : e->sdraws + (size_t)it * n; sp.draws_bs = (long long)(I * n);
         sp.ps = e->ps; sp.lam = e->lam;

@@ -1,0 +1,302 @@
+// hp_fft.cu -- fused delay-transform kernel (shared-memory Stockham FFT + DMMA foreground products).
+//
+// The reference applies its shifted Fourier operator (utils.py:14-40) as dense matrices
+// (pspec.py:91-95, 313-322).  On the device the operator is only ever applied to vectors, so it
+// becomes an in-shared-memory mixed-radix FFT with pre/post twiddles for the two half-band shifts:
+//
+//     (U v)[k] = post[k] * sum_x exp(-2 pi i k x / n) (pre[x] v[x]),      h = n // 2
+//     pre[x]  = exp(+2 pi i h x / n),   post[k] = exp(+2 pi i h k / n) exp(-2 pi i h^2 / n) / sqrt(n)
+//
+// and U^H v = conj(U conj(v)) because U is symmetric.
+//
+//   k_post_fft  : per (baseline, 8 times): s = U^H (lam * ytilde), model = s + F f (DMMA),
+//                 residual, chi^2, ln-posterior partial sums, and |U (w s)|^2 partial sums
+//                 (gibbs_step_fgmodes, pspec.py:442-485)
+#include "hp_kernels.cuh"
+#include "hp_math.h"
+#include "hp_mma.cuh"
+
+namespace hp {
+
+namespace {
+
+__device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// multiply by -i / +i
+__device__ __forceinline__ double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }
+
+// Forward DFT (kernel exp(-2 pi i k x / n)) of nvec vectors of length n, Stockham autosort,
+// ping-pong between src and dst; returns the buffer that holds the result.  tw[j] = exp(-2 pi i j / n).
+// All threads of the CTA must call it; it starts and ends with a barrier.
+__device__ double2* fft_forward(double2* src, double2* dst, int nvec, const FftPlan& p, const double2* tw) {
+    const int n = p.n;
+    int Ns = 1;
+    __syncthreads();
+    for (int pass = 0; pass < p.nf; ++pass) {
+        const int R = p.radix[pass];
+        const int nb = n / R;
+        const int tstep = n / (Ns * R);
+        for (int b = threadIdx.x; b < nvec * nb; b += blockDim.x) {
+            const int v = b / nb, j = b - v * nb;
+            const int k = j % Ns;
+            const double2* s = src + (size_t)v * n + j;
+            double2* d = dst + (size_t)v * n + (j / Ns) * Ns * R + k;
+            const int tk = k * tstep;  // twiddle index step: exp(-2 pi i r k / (Ns R)) = tw[r * tk]
+            if (R == 4) {
+                double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb], a3 = s[3 * nb];
+                if (k) { a1 = cmul2(a1, tw[tk]); a2 = cmul2(a2, tw[2 * tk]); a3 = cmul2(a3, tw[3 * tk]); }
+                double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = cmul_mi(csub(a1, a3));
+                d[0] = cadd(b0, b2); d[Ns] = cadd(b1, b3); d[2 * Ns] = csub(b0, b2); d[3 * Ns] = csub(b1, b3);
+            } else if (R == 2) {
+                double2 a0 = s[0], a1 = s[nb];
+                if (k) a1 = cmul2(a1, tw[tk]);
+                d[0] = cadd(a0, a1); d[Ns] = csub(a0, a1);
+            } else if (R == 3) {
+                double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb];
+                if (k) { a1 = cmul2(a1, tw[tk]); a2 = cmul2(a2, tw[2 * tk]); }
+                const double S3 = 0.86602540378443864676;
+                double2 t1 = cadd(a1, a2), t2 = make_double2(a0.x - 0.5 * t1.x, a0.y - 0.5 * t1.y);
+                double2 t3 = make_double2(S3 * (a1.y - a2.y), -S3 * (a1.x - a2.x));  // -i sqrt(3)/2 (a1 - a2)
+                d[0] = cadd(a0, t1); d[Ns] = cadd(t2, t3); d[2 * Ns] = csub(t2, t3);
+            } else {
+                // generic radix (5, 7, 11, ...): O(R^2) with table twiddles
+                const int wstep = n / R;  // exp(-2 pi i q r / R) = tw[((q r) % R) * wstep]
+                for (int q = 0; q < R; ++q) {
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int r = 0; r < R; ++r) {
+                        double2 a = s[r * nb];
+                        int idx = r * tk + ((q * r) % R) * wstep;
+                        idx %= n;
+                        acc = cadd(acc, cmul2(a, tw[idx]));
+                    }
+                    d[q * Ns] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        double2* t = src; src = dst; dst = t;
+        Ns *= R;
+    }
+    return src;
+}
+
+__device__ __forceinline__ double2 shift_pre(const double2* tw, int n, int x) {  // exp(+2 pi i h x / n)
+    return cconj(tw[(int)(((long long)(n / 2) * x) % n)]);
+}
+
+// one warp: C (8 x 8 complex) += A (8 x K, shared, interleaved, ld in complex) . B (K x 8, global interleaved)
+//   B element (k, col) at Bg[k * sBk + col * sBj] (complex strides), conjugated if BC; rows k >= K zero.
+template <bool BC>
+__device__ __forceinline__ void warp_fg_product(double (&cr)[2], double (&ci)[2], const double2* As, int lda,
+                                                const double* Bg, long long sBk, long long sBj, int col0, int ncols,
+                                                int k0, int k1) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const bool colok = col0 + g < ncols;
+    for (int kk = k0; kk < k1; kk += 4) {
+        const int k = kk + q;
+        double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+        if (k < k1) {
+            a = As[(size_t)g * lda + k];
+            if (colok) b = *reinterpret_cast<const double2*>(Bg + 2 * ((long long)k * sBk + (long long)(col0 + g) * sBj));
+        }
+        if (BC) b.y = -b.y;
+        dmma884(cr[0], cr[1], a.x, b.x);
+        dmma884(ci[0], ci[1], a.x, b.y);
+        dmma884(cr[0], cr[1], -a.y, b.y);
+        dmma884(ci[0], ci[1], a.y, b.x);
+    }
+}
+
+}  // namespace
+
+bool make_fft_plan(int n, FftPlan* plan) {
+    plan->n = n;
+    plan->nf = 0;
+    int rem = n;
+    while (rem % 4 == 0 && plan->nf < 16) { plan->radix[plan->nf++] = 4; rem /= 4; }
+    for (int p = 2; p <= 31 && rem > 1; ++p)
+        while (rem % p == 0) {
+            if (plan->nf >= 16) return false;
+            plan->radix[plan->nf++] = p;
+            rem /= p;
+        }
+    return rem == 1 && n >= 2;
+}
+
+__global__ void k_twiddles(double* tw, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)n, &s, &c);
+    tw[2 * j] = c;
+    tw[2 * j + 1] = s;
+}
+void launch_twiddles(double* tw, int n, cudaStream_t st) { k_twiddles<<<(n + 255) / 256, 256, 0, st>>>(tw, n); }
+
+// ==========================================================================================
+constexpr int kTP = 8;  // times per CTA of the fused transform kernels
+
+size_t postfft_smem_bytes(int n, int m) {
+    int mk = ((m + 3) / 4) * 4;
+    return sizeof(double2) * ((size_t)2 * kTP * n + n + (size_t)kTP * (mk + 1)) + 64 * sizeof(double);
+}
+
+__global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.plan.n, m = a.m, mk = ((m + 3) / 4) * 4, ldf = mk + 1;
+    double2* buf0 = reinterpret_cast<double2*>(smem_raw);
+    double2* buf1 = buf0 + (size_t)kTP * n;
+    double2* tw = buf1 + (size_t)kTP * n;
+    double2* fs = tw + n;
+    double* red = reinterpret_cast<double*>(fs + (size_t)kTP * ldf);
+    const int sys = blockIdx.y, tile = blockIdx.x, t0 = tile * kTP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* X = a.X + 2 * ((size_t)sys * a.Tp + t0) * a.Np;
+    const double* lam = a.lam + (size_t)sys * a.Np;
+    const double* w = a.w + (size_t)sys * n;
+    const double* nd = a.ninvd + (size_t)sys * n;
+    double* Sf = a.Sf + 2 * ((size_t)sys * a.sf_bs + (size_t)t0 * n);
+    const double2* twg = reinterpret_cast<const double2*>(a.tw);
+    const double rsn = rsqrt((double)n);
+    const double2 c0 = twg[(int)(((long long)(n / 2) * (n / 2)) % n)];  // exp(-2 pi i h^2 / n)
+
+    for (int j = tid; j < n; j += 256) tw[j] = twg[j];
+    for (int e = tid; e < kTP * ldf; e += 256) {
+        int t = e / ldf, j = e - t * ldf;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < m && t0 + t < a.T) v = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + n + j));
+        fs[e] = v;
+        if (j < m && t0 + t < a.T && a.fg_out)
+            *reinterpret_cast<double2*>(a.fg_out + (size_t)sys * a.fg_bs + 2 * ((size_t)(t0 + t) * m + j)) = v;
+    }
+    __syncthreads();
+    double2* sbuf;
+    if (a.do_inverse) {
+        // s = U^H a = conj(U conj(a)),  a = lam * ytilde
+        for (int e = tid; e < kTP * n; e += 256) {
+            int t = e / n, k = e - t * n;
+            double2 v = make_double2(0.0, 0.0);
+            if (t0 + t < a.T) {
+                v = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + k));
+                double l = lam[k];
+                v = cmul2(make_double2(l * v.x, -l * v.y), shift_pre(tw, n, k));
+            }
+            buf0[e] = v;
+        }
+        double2* res = fft_forward(buf0, buf1, kTP, a.plan, tw);
+        for (int e = tid; e < kTP * n; e += 256) {
+            int t = e / n, x = e - t * n;
+            double2 post = cmul2(shift_pre(tw, n, x), c0);
+            double2 v = cconj(cmul2(res[e], post));
+            v.x *= rsn; v.y *= rsn;
+            res[e] = v;
+            if (t0 + t < a.T) *reinterpret_cast<double2*>(Sf + 2 * ((size_t)t * n + x)) = v;
+        }
+        sbuf = res;
+    } else {
+        for (int e = tid; e < kTP * n; e += 256) {
+            int t = e / n, x = e - t * n;
+            buf0[e] = t0 + t < a.T ? *reinterpret_cast<const double2*>(Sf + 2 * ((size_t)t * n + x)) : make_double2(0.0, 0.0);
+        }
+        sbuf = buf0;
+    }
+    double2* obuf = sbuf == buf0 ? buf1 : buf0;
+    __syncthreads();
+    // foreground model F f on the tensor pipe:  obuf[t][x] = sum_j f[t][j] Ft[j][x]
+    {
+        const double* Ft = a.Ft + 2 * (size_t)sys * m * n;
+        const int nct = (n + 7) / 8;
+        const int g = lane >> 2, q = lane & 3;
+        for (int ct = warp; ct < nct; ct += 8) {
+            double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
+            if (m > 0) warp_fg_product<false>(cr, ci, fs, ldf, Ft, n, 1, 8 * ct, n, 0, m);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int x = 8 * ct + 2 * q + e;
+                if (x < n) obuf[(size_t)g * n + x] = make_double2(cr[e], ci[e]);
+            }
+        }
+    }
+    __syncthreads();
+    // residual, chi^2, ln-posterior partial, masked signal
+    {
+        const double* wd = a.wd + 2 * ((size_t)sys * a.Tp + t0) * n;
+        double part[kTP];
+#pragma unroll
+        for (int t = 0; t < kTP; ++t) part[t] = 0.0;
+        for (int x = tid; x < n; x += 256) {
+            const double wx = w[x], ndx = nd[x];
+            const double2 pre = shift_pre(tw, n, x);
+#pragma unroll
+            for (int t = 0; t < kTP; ++t) {
+                double2 s = sbuf[(size_t)t * n + x];
+                double2 mf = obuf[(size_t)t * n + x];
+                double2 d = make_double2(0.0, 0.0);
+                if (t0 + t < a.T) d = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)t * n + x));
+                double rr = d.x - s.x - mf.x, ri = d.y - s.y - mf.y;
+                double r2 = rr * rr + ri * ri;
+                if (t0 + t < a.T) {
+                    if (a.chisq_out) a.chisq_out[(size_t)sys * a.chisq_bs + (size_t)(t0 + t) * n + x] = r2 * ndx;
+                    part[t] += wx * ndx * r2;
+                }
+                obuf[(size_t)t * n + x] = cmul2(make_double2(wx * s.x, wx * s.y), pre);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kTP; ++t) {
+            double v = part[t];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp * kTP + t] = v;
+        }
+        __syncthreads();
+        if (tid < kTP) {
+            double s = 0.0;
+            for (int wv = 0; wv < 8; ++wv) s += red[wv * kTP + tid];
+            if (t0 + tid < a.Tp) a.lnp1[(size_t)sys * a.Tp + t0 + tid] = t0 + tid < a.T ? s : 0.0;
+        }
+    }
+    // |U (w s)|^2 summed over the tile's times (second term of ln_post, pspec.py:479-483)
+    if (a.Empart) {
+        double2* res = fft_forward(obuf, sbuf, kTP, a.plan, tw);
+        double* Ep = a.Empart + ((size_t)sys * gridDim.x + tile) * n;
+        for (int k = tid; k < n; k += 256) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < kTP; ++t) { double2 v = res[(size_t)t * n + k]; acc += v.x * v.x + v.y * v.y; }
+            Ep[k] = acc / (double)n;
+        }
+    }
+    // |U s|^2 (unmasked) for the general-basis iteration: reload s from global
+    if (a.Eupart) {
+        __syncthreads();
+        for (int e = tid; e < kTP * n; e += 256) {
+            int t = e / n, x = e - t * n;
+            double2 v = make_double2(0.0, 0.0);
+            if (t0 + t < a.T) v = cmul2(*reinterpret_cast<const double2*>(Sf + 2 * ((size_t)t * n + x)), shift_pre(tw, n, x));
+            buf0[e] = v;
+        }
+        double2* res = fft_forward(buf0, buf1, kTP, a.plan, tw);
+        double* Ep = a.Eupart + ((size_t)sys * gridDim.x + tile) * n;
+        for (int k = tid; k < n; k += 256) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < kTP; ++t) { double2 v = res[(size_t)t * n + k]; acc += v.x * v.x + v.y * v.y; }
+            Ep[k] = acc / (double)n;
+        }
+    }
+}
+
+int postfft_tiles(int T) { return (T + kTP - 1) / kTP; }
+
+void launch_post_fft(const PostFftArgs& a, cudaStream_t st) {
+    size_t smem = postfft_smem_bytes(a.plan.n, a.m);
+    static size_t attr = 0;
+    if (smem > attr) { cudaFuncSetAttribute(k_post_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+    k_post_fft<<<dim3(postfft_tiles(a.T), a.nsys), 256, smem, st>>>(a);
+}
+
+}  // namespace hp

@@ -26,19 +26,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kLdBlk = 36;  // leading dim (doubles) of a 32x32 plane in shared memory, == 4 mod 16
 
-// global packed block (2048 doubles: re plane, im plane, ld 32) -> shared planes (ld 36), async
-__device__ __forceinline__ void load_block_async(double* sr, double* si, const double* g) {
-    // 1024 16-byte chunks; 256 threads x 4
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int c = threadIdx.x + 256 * r;
-        int plane = c >> 9, cc = c & 511;
-        int row = cc >> 4, col = (cc & 15) * 2;
-        double* dst = (plane ? si : sr) + row * kLdBlk + col;
-        cp_async16(dst, g + plane * 1024 + row * 32 + col);
-    }
+// global L block (padded layout: re plane [32][36], im plane [32][36]) -> the same layout in shared
+// memory (s: 2304 contiguous doubles), async
+__device__ __forceinline__ void load_block_async(double* s, const double* g) {
+    for (int c = threadIdx.x; c < kLBlkDoubles / 2; c += 256) cp_async16(s + 2 * c, g + 2 * c);
 }
 
 // ==========================================================================================
@@ -177,7 +169,7 @@ void launch_fill(double* p, double v, size_t count, cudaStream_t st) {
 // is DMMA; the 32x32 diagonal factorisation and its triangular inverse are done by all 256
 // threads in shared memory.
 struct CholSmem {
-    double Ar[32 * kLdBlk], Ai[32 * kLdBlk];
+    double Ar[32 * kLdBlk], Ai[32 * kLdBlk];  // contiguous (Ar, Ai) == one padded L block
     double Br[32 * kLdBlk], Bi[32 * kLdBlk];
     double Vr[32 * kLdBlk], Vi[32 * kLdBlk];  // inverse of the current diagonal block
     double redr[8 * 32], redi[8 * 32];
@@ -189,8 +181,8 @@ __global__ void __launch_bounds__(256) k_chol(CholArgs a) {
     const int sys = blockIdx.x;
     const int nblk = a.nblk, Np = nblk * 32;
     const double* Gp = a.Gp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
-    double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
-    double* Linvp = a.Linvp + (size_t)sys * nblk * kBlkDoubles;
+    double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    double* Linvp = a.Linvp + (size_t)sys * nblk * kLBlkDoubles;
     const double* lam = a.lam + (size_t)sys * Np;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
@@ -203,8 +195,8 @@ __global__ void __launch_bounds__(256) k_chol(CholArgs a) {
             warp_zero<1, 2>(cr, ci);
             for (int j = 0; j < k; ++j) {
                 __syncthreads();
-                load_block_async(s.Ar, s.Ai, Lp + blk_index(i, j) * kBlkDoubles);
-                if (i != k) load_block_async(s.Br, s.Bi, Lp + blk_index(k, j) * kBlkDoubles);
+                load_block_async(s.Ar, Lp + blk_index(i, j) * kLBlkDoubles);
+                if (i != k) load_block_async(s.Br, Lp + blk_index(k, j) * kLBlkDoubles);
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncthreads();
@@ -286,12 +278,11 @@ __global__ void __launch_bounds__(256) k_chol(CholArgs a) {
                     __syncthreads();
                 }
                 // write L_kk and V to global
-                double* Lb = Lp + blk_index(k, k) * kBlkDoubles;
-                double* Vb = Linvp + (size_t)k * kBlkDoubles;
-                for (int e = tid; e < 1024; e += 256) {
-                    int r = e >> 5, c = e & 31;
-                    Lb[e] = s.Ar[r * kLdBlk + c]; Lb[1024 + e] = s.Ai[r * kLdBlk + c];
-                    Vb[e] = s.Vr[r * kLdBlk + c]; Vb[1024 + e] = s.Vi[r * kLdBlk + c];
+                double* Lb = Lp + blk_index(k, k) * kLBlkDoubles;
+                double* Vb = Linvp + (size_t)k * kLBlkDoubles;
+                for (int e = tid; e < kLBlkDoubles; e += 256) {  // (Ar, Ai) and (Vr, Vi) are contiguous padded blocks
+                    Lb[e] = s.Ar[e];
+                    Vb[e] = s.Vr[e];
                 }
             } else {
                 // L_ik = C . V^H
@@ -299,12 +290,12 @@ __global__ void __launch_bounds__(256) k_chol(CholArgs a) {
                 warp_zero<1, 2>(dr, di);
                 warp_zgemm<1, 2, false, false, true, true>(dr, di, s.Ar + 8 * ti * kLdBlk, s.Ai + 8 * ti * kLdBlk, kLdBlk,
                                                            s.Vr + 16 * tj * kLdBlk, s.Vi + 16 * tj * kLdBlk, kLdBlk, 32);
-                double* Lb = Lp + blk_index(i, k) * kBlkDoubles;
+                double* Lb = Lp + blk_index(i, k) * kLBlkDoubles;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     int r = 8 * ti + g, c = 16 * tj + 8 * j + 2 * q;
-                    *reinterpret_cast<double2*>(Lb + r * 32 + c) = make_double2(dr[0][j][0], dr[0][j][1]);
-                    *reinterpret_cast<double2*>(Lb + 1024 + r * 32 + c) = make_double2(di[0][j][0], di[0][j][1]);
+                    *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][j][0], dr[0][j][1]);
+                    *reinterpret_cast<double2*>(Lb + kLPlane + r * kLdBlk + c) = make_double2(di[0][j][0], di[0][j][1]);
                 }
             }
         }
@@ -320,249 +311,6 @@ void launch_chol(const CholArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     k_chol<<<a.nsys, 256, sizeof(CholSmem), st>>>(a);
-}
-
-// ==========================================================================================
-// k_solve: CTA = (time tile of 16, system).  Builds its right-hand sides on the fly, runs the
-// forward (L) and backward (L^H) block substitutions with the 16-column solution tile resident
-// in shared memory, streams L blocks through a cp.async double buffer, and finishes with the
-// per-delay partial sums of |ytilde|^2 that sample_S needs.
-constexpr int kLdX = 20;  // 16 + 4, == 4 mod 16
-
-size_t solve_smem_bytes(int nblk) {
-    size_t Np = (size_t)nblk * 32;
-    size_t d = 2 * Np * kLdX            // X tile planes
-             + 2 * 2 * 32 * kLdBlk      // two block buffers (re, im)
-             + 2 * 32 * kLdX            // Z
-             + 16 * 16 * 3 + 64;        // reductions + theta
-    return d * sizeof(double);
-}
-
-struct RhsCtx {
-    const double* Rfix; const double* eta; const double* wa; const double* lam;
-    int Np, n, N, T, t0, philox_wa;
-    uint32_t key0, key1, iter, chain;
-};
-
-// right-hand side element (system row `row`, tile column `col`)
-__device__ __forceinline__ void rhs_elem(const RhsCtx& c, int row, int col, double& vr, double& vi) {
-    int t = c.t0 + col;
-    vr = 0.0; vi = 0.0;
-    if (t >= c.T || row >= c.N) return;
-    size_t off = 2 * ((size_t)t * c.Np + row);
-    double xr = c.Rfix[off], xi = c.Rfix[off + 1];
-    if (c.eta) { xr += c.eta[off]; xi += c.eta[off + 1]; }
-    double l = c.lam[row];
-    vr = l * xr; vi = l * xi;
-    if (row < c.n) {
-        if (c.wa) { vr += c.wa[off]; vi += c.wa[off + 1]; }
-        else if (c.philox_wa) {
-            u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)t; ctr.z = c.iter; ctr.w = c.chain;
-            double n0, n1;
-            normal_pair(philox4x32_10(ctr, c.key0, c.key1 ^ 0xA5A5A5A5u), n0, n1);
-            vr += n0 * 0.70710678118654752440; vi += n1 * 0.70710678118654752440;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nblk = a.nblk, Np = nblk * 32;
-    double* Xr = reinterpret_cast<double*>(smem_raw);
-    double* Xi = Xr + (size_t)Np * kLdX;
-    double* Lb = Xi + (size_t)Np * kLdX;              // [2 buffers][re, im][32*36]
-    double* Zr = Lb + 4 * 32 * kLdBlk;
-    double* Zi = Zr + 32 * kLdX;
-    double* red = Zi + 32 * kLdX;                     // 16*16*3
-    double* theta = red + 16 * 16 * 3;                // 16 * 2 (+pad)
-
-    const int sys = blockIdx.y, tile = blockIdx.x;
-    const double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
-    const double* Linvp = a.Linvp + (size_t)sys * nblk * kBlkDoubles;
-    const double* lam = a.lam + (size_t)sys * Np;
-    RhsCtx rc;
-    rc.Rfix = a.Rfix + 2 * (size_t)sys * a.Tp * Np;
-    rc.eta = a.eta ? a.eta + 2 * (size_t)sys * a.Tp * Np : nullptr;
-    rc.wa = a.wa ? a.wa + 2 * (size_t)sys * a.Tp * Np : nullptr;
-    rc.lam = lam; rc.Np = Np; rc.n = a.n; rc.N = a.N; rc.T = a.T; rc.t0 = tile * kTT;
-    rc.philox_wa = a.philox_wa; rc.key0 = a.key0; rc.key1 = a.key1; rc.iter = a.iter;
-    rc.chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)sys;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, q = lane & 3;
-    const int ti = warp >> 1, tj = warp & 1;  // warp tile: rows 8 ti.., cols 8 tj..
-
-    auto bufr = [&](int b) { return Lb + (size_t)b * 2 * 32 * kLdBlk; };
-    auto bufi = [&](int b) { return Lb + (size_t)b * 2 * 32 * kLdBlk + 32 * kLdBlk; };
-
-    // ------------------------------------------------------------------ forward:  L Y = R
-    int buf = 0;
-    // stream of blocks: for i: (i,0) .. (i,i-1), Linv_i
-    load_block_async(bufr(0), bufi(0), Linvp);  // i = 0 has no off-diagonal blocks
-    cp_async_commit();
-    for (int i = 0; i < nblk; ++i) {
-        double cr[1][1][2], ci[1][1][2];
-        warp_zero<1, 1>(cr, ci);
-        for (int j = 0; j < i; ++j) {
-            // prefetch the next stream item into the other buffer
-            const double* nxt = (j + 1 < i) ? Lp + blk_index(i, j + 1) * kBlkDoubles : Linvp + (size_t)i * kBlkDoubles;
-            load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), nxt);
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncthreads();
-            warp_zgemm<1, 1, false, false, false, false>(cr, ci, bufr(buf) + 8 * ti * kLdBlk, bufi(buf) + 8 * ti * kLdBlk,
-                                                         kLdBlk, Xr + (size_t)32 * j * kLdX + 8 * tj,
-                                                         Xi + (size_t)32 * j * kLdX + 8 * tj, kLdX, 32);
-            __syncthreads();
-            buf ^= 1;
-        }
-        // current buffer holds Linv_i; prefetch first block of the next row
-        if (i + 1 < nblk) load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), Lp + blk_index(i + 1, 0) * kBlkDoubles);
-        cp_async_commit();
-        // Z = R_i - acc
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
-            double vr, vi;
-            rhs_elem(rc, 32 * i + r, c, vr, vi);
-            Zr[r * kLdX + c] = vr - cr[0][0][e];
-            Zi[r * kLdX + c] = vi - ci[0][0][e];
-        }
-        cp_async_wait<1>();
-        __syncthreads();
-        double yr[1][1][2], yi[1][1][2];
-        warp_zero<1, 1>(yr, yi);
-        warp_zgemm<1, 1, false, false, false, false>(yr, yi, bufr(buf) + 8 * ti * kLdBlk, bufi(buf) + 8 * ti * kLdBlk, kLdBlk,
-                                                     Zr + 8 * tj, Zi + 8 * tj, kLdX, 32);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int r = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
-            Xr[(size_t)r * kLdX + c] = yr[0][0][e];
-            Xi[(size_t)r * kLdX + c] = yi[0][0][e];
-        }
-        __syncthreads();
-        buf ^= 1;
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // ------------------------------------------------------------------ backward:  L^H X = Y
-    // stream: for i = nblk-1 .. 0: (i+1,i) .. (nblk-1,i), Linv_i
-    buf = 0;
-    load_block_async(bufr(0), bufi(0), Linvp + (size_t)(nblk - 1) * kBlkDoubles);
-    cp_async_commit();
-    for (int i = nblk - 1; i >= 0; --i) {
-        double cr[1][1][2], ci[1][1][2];
-        warp_zero<1, 1>(cr, ci);
-        for (int j = i + 1; j < nblk; ++j) {
-            const double* nxt = (j + 1 < nblk) ? Lp + blk_index(j + 1, i) * kBlkDoubles : Linvp + (size_t)i * kBlkDoubles;
-            load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), nxt);
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncthreads();
-            // acc += L_ji^H . X_j :  A elem (r, k) = conj(L_ji[k][r])
-            warp_zgemm<1, 1, true, true, false, false>(cr, ci, bufr(buf) + 8 * ti, bufi(buf) + 8 * ti, kLdBlk,
-                                                       Xr + (size_t)32 * j * kLdX + 8 * tj, Xi + (size_t)32 * j * kLdX + 8 * tj,
-                                                       kLdX, 32);
-            __syncthreads();
-            buf ^= 1;
-        }
-        // current buffer holds Linv_i; the first item of row i-1 is block (i, i-1)
-        if (i > 0) load_block_async(bufr(buf ^ 1), bufi(buf ^ 1), Lp + blk_index(i, i - 1) * kBlkDoubles);
-        cp_async_commit();
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
-            Zr[r * kLdX + c] = Xr[(size_t)(32 * i + r) * kLdX + c] - cr[0][0][e];
-            Zi[r * kLdX + c] = Xi[(size_t)(32 * i + r) * kLdX + c] - ci[0][0][e];
-        }
-        cp_async_wait<1>();
-        __syncthreads();
-        double yr[1][1][2], yi[1][1][2];
-        warp_zero<1, 1>(yr, yi);
-        // X_i = Linv_i^H . Z
-        warp_zgemm<1, 1, true, true, false, false>(yr, yi, bufr(buf) + 8 * ti, bufi(buf) + 8 * ti, kLdBlk, Zr + 8 * tj,
-                                                   Zi + 8 * tj, kLdX, 32);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int r = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
-            Xr[(size_t)r * kLdX + c] = yr[0][0][e];
-            Xi[(size_t)r * kLdX + c] = yi[0][0][e];
-        }
-        __syncthreads();
-        buf ^= 1;
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // ------------------------------------------------------------------ epilogue
-    if (a.cg_compat) {
-        // c = b^H x*, ||b||^2 in the reference's (unwhitened) variables:
-        //   weights lam^2 on the signal rows, 1 on the foreground rows ("CG model").
-        int col = tid & 15, rg = tid >> 4;
-        double sre = 0.0, sim = 0.0, sb = 0.0;
-        for (int row = rg; row < a.N; row += 16) {
-            double vr, vi;
-            rhs_elem(rc, row, col, vr, vi);
-            double w = row < a.n ? lam[row] * lam[row] : 1.0;
-            double xr = Xr[(size_t)row * kLdX + col], xi = Xi[(size_t)row * kLdX + col];
-            sre += w * (vr * xr + vi * xi);   // conj(R) X
-            sim += w * (vr * xi - vi * xr);
-            sb += w * (vr * vr + vi * vi);
-        }
-        red[(rg * 16 + col) * 3 + 0] = sre; red[(rg * 16 + col) * 3 + 1] = sim; red[(rg * 16 + col) * 3 + 2] = sb;
-        __syncthreads();
-        if (tid < 16) {
-            double cre = 0.0, cim = 0.0, b2 = 0.0;
-            for (int r2 = 0; r2 < 16; ++r2) {
-                cre += red[(r2 * 16 + tid) * 3 + 0]; cim += red[(r2 * 16 + tid) * 3 + 1]; b2 += red[(r2 * 16 + tid) * 3 + 2];
-            }
-            cplx c; c.re = cre; c.im = cim;
-            cplx th = cg_theta(c, sqrt(b2), 1e-8, 1e-6, 100000);
-            theta[2 * tid] = th.re; theta[2 * tid + 1] = th.im;
-        }
-        __syncthreads();
-        for (int e = tid; e < Np * 16; e += 256) {
-            int row = e >> 4, col2 = e & 15;
-            double xr = Xr[(size_t)row * kLdX + col2], xi = Xi[(size_t)row * kLdX + col2];
-            double tr = theta[2 * col2], tim = theta[2 * col2 + 1];
-            Xr[(size_t)row * kLdX + col2] = tr * xr - tim * xi;
-            Xi[(size_t)row * kLdX + col2] = tr * xi + tim * xr;
-        }
-        __syncthreads();
-    }
-    double* Xg = a.X + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * Np;
-    double* Sg = a.Ssc + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * a.n;
-    for (int t = 0; t < kTT; ++t) {
-        for (int row = tid; row < Np; row += 256) {
-            double xr = Xr[(size_t)row * kLdX + t], xi = Xi[(size_t)row * kLdX + t];
-            *reinterpret_cast<double2*>(Xg + 2 * ((size_t)t * Np + row)) = make_double2(xr, xi);
-            if (row < a.n) {
-                double l = lam[row];
-                *reinterpret_cast<double2*>(Sg + 2 * ((size_t)t * a.n + row)) = make_double2(l * xr, l * xi);
-            }
-        }
-    }
-    double* Pp = a.Ppart + ((size_t)sys * a.ntiles + tile) * a.n;
-    for (int row = tid; row < a.n; row += 256) {
-        double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t < kTT; ++t) {
-            double xr = Xr[(size_t)row * kLdX + t], xi = Xi[(size_t)row * kLdX + t];
-            acc += xr * xr + xi * xi;
-        }
-        Pp[row] = acc;
-    }
-}
-
-void launch_solve(const SolveArgs& a, cudaStream_t st) {
-    size_t smem = solve_smem_bytes(a.nblk);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
-    }
-    k_solve<<<dim3(a.ntiles, a.nsys), 256, smem, st>>>(a);
 }
 
 // ==========================================================================================
@@ -690,6 +438,10 @@ __global__ void __launch_bounds__(1024) k_sample(SampleArgs a) {
                 double s = 0.0;
                 for (int tl = 0; tl < a.ntiles; ++tl) s += a.Ppart[((size_t)sys * a.ntiles + tl) * n + k];
                 beta = ps[k] * s;  // |sk|^2 = n lam^2 |ytilde|^2 = ps |ytilde|^2
+            } else if (a.ntilesE > 0) {
+                double s = 0.0;
+                for (int tl = 0; tl < a.ntilesE; ++tl) s += a.Eu[((size_t)sys * a.ntilesE + tl) * n + k];
+                beta = (double)n * s;
             } else {
                 beta = (double)n * a.Eu[(size_t)sys * n + k];
             }
@@ -765,7 +517,15 @@ __global__ void __launch_bounds__(1024) k_sample(SampleArgs a) {
             ps[k] = newps;
             lam[k] = sqrt(newps / (double)n);
             a.ps_out[(size_t)sys * a.ps_bs + k] = newps;
-            double E = a.Em ? a.Em[(size_t)sys * n + k] : beta / (double)n;
+            double E = beta / (double)n;
+            if (a.Em) {
+                if (a.ntilesE > 0) {
+                    E = 0.0;
+                    for (int tl = 0; tl < a.ntilesE; ++tl) E += a.Em[((size_t)sys * a.ntilesE + tl) * n + k];
+                } else {
+                    E = a.Em[(size_t)sys * n + k];
+                }
+            }
             lp2 += E / (newps / (double)n);
         }
     }
@@ -777,28 +537,5 @@ __global__ void __launch_bounds__(1024) k_sample(SampleArgs a) {
     if (tid == 0) a.lnpost_out[(size_t)sys * a.lnpost_bs] = -s1 - s2;
 }
 void launch_sample(const SampleArgs& a, cudaStream_t st) { k_sample<<<a.nsys, 1024, 0, st>>>(a); }
-
-// ==========================================================================================
-__global__ void k_noise_draw(double* z, const double* nu, int T, int Tp, int n, uint32_t key0, uint32_t key1,
-                             uint32_t iter, const int* chain_ids) {
-    const int sys = blockIdx.z, t = blockIdx.y;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
-    double vr = 0.0, vi = 0.0;
-    if (t < T) {
-        u32x4 ctr; ctr.x = (uint32_t)x; ctr.y = (uint32_t)t; ctr.z = iter;
-        ctr.w = chain_ids ? (uint32_t)chain_ids[sys] : (uint32_t)sys;
-        double n0, n1;
-        normal_pair(philox4x32_10(ctr, key0, key1 ^ 0x3C3C3C3Cu), n0, n1);
-        double s = nu[(size_t)sys * n + x] * 0.70710678118654752440;
-        vr = s * n0; vi = s * n1;
-    }
-    double* p = z + 2 * (((size_t)sys * Tp + t) * n + x);
-    p[0] = vr; p[1] = vi;
-}
-void launch_noise_draw(double* z, const double* nu, int T, int Tp, int n, int nsys, uint32_t key0, uint32_t key1,
-                       uint32_t iter, const int* chain_ids, cudaStream_t st) {
-    k_noise_draw<<<dim3((n + 127) / 128, Tp, nsys), 128, 0, st>>>(z, nu, T, Tp, n, key0, key1, iter, chain_ids);
-}
 
 }  // namespace hp

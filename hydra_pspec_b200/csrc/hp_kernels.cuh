@@ -4,7 +4,9 @@
 //   * complex128 arrays in global memory are interleaved (re, im) doubles == numpy complex128.
 //   * "packed lower-block" matrices (G, L): 32x32 blocks, block (i, j), j <= i, at block index
 //     i (i+1)/2 + j; each block is 2048 doubles: a 32x32 row-major real plane followed by the
-//     imaginary plane.  Diagonal blocks of G hold both triangles.
+//     imaginary plane.  Diagonal blocks of G hold both triangles.  The factor L and the inverses of its
+//     diagonal blocks use the same block order with rows padded to 36 doubles, so that one block is
+//     one TMA bulk copy into its bank-conflict-free shared-memory layout.
 //   * system vectors are padded to Np = 32 * nblk rows; times are padded to Tp = 16 * ntiles.
 #pragma once
 #include <cuda_runtime.h>
@@ -13,7 +15,10 @@
 namespace hp {
 
 constexpr int kNB = 32;                 // block edge of the packed format
-constexpr int kBlkDoubles = 2 * 32 * 32;  // doubles per packed block (16 KiB)
+constexpr int kBlkDoubles = 2 * 32 * 32;  // doubles per packed block of G (16 KiB)
+constexpr int kLdBlk = 36;               // row stride (doubles) of a 32x32 plane of an L block, == 4 mod 16
+constexpr int kLPlane = 32 * kLdBlk;     // doubles per plane of an L block
+constexpr int kLBlkDoubles = 2 * kLPlane;  // L / L^-1 blocks are stored in the padded shared-memory layout (18 KiB)
 constexpr int kTT = 16;                 // right-hand sides (times) per solve CTA
 constexpr int kInvGrid = 1000;          // pspec.py:11 ngrid default
 
@@ -44,8 +49,8 @@ void launch_pack_lower(const double* dense, long long ld, long long bs, double* 
 struct CholArgs {
     const double* Gp;      // [nsys][tri_blocks][2048]
     const double* lam;     // [nsys][Np]   (lambda for rows < n, 1 for fg rows, 0 for padding)
-    double* Lp;            // [nsys][tri_blocks][2048]
-    double* Linvp;         // [nsys][nblk][2048]
+    double* Lp;            // [nsys][tri_blocks][2304]
+    double* Linvp;         // [nsys][nblk][2304]
     int* info;             // [nsys]  0 ok, k+1 = non-positive pivot in block column k
     int nblk, n, N, nsys;
 };
@@ -54,14 +59,14 @@ void launch_chol(const CholArgs& a, cudaStream_t st);
 struct SolveArgs {
     const double* Lp; const double* Linvp; const double* lam;   // as above
     const double* Rfix;    // [nsys][Tp][Np] complex: B^H N^-1 (w d)   (+ frozen noise term in numpy mode)
-    const double* eta;     // [nsys][Tp][Np] complex or null: B^H N^-1/2 omega_b of this iteration
+    const double* eta;     // [nsys][Tp][Np] complex or null: extra right-hand-side term added to Rfix
     const double* wa;      // [nsys][Tp][Np] complex or null: Q^H omega_a (rows < n)
     double* X;             // [nsys][Tp][Np] complex: solution [ytilde ; f]
     double* Ssc;           // [nsys][Tp][n]  complex: lambda * ytilde (signal in the S eigenbasis)
     double* Ppart;         // [nsys][ntiles][n] sum over the tile's times of |ytilde|^2
     int nblk, n, N, Tp, ntiles, nsys;
     int T;                 // valid times (t >= T are padding: zero RHS)
-    int philox_wa;         // 1: draw omega_a in-kernel (white in any unitary basis)
+    int philox_wa;         // 1: add xi ~ CN(0, I) (Philox) to y = L^-1 r before the backward pass
     int cg_compat;         // 1: scale each column by the scalar CG model (hp_math.h:cg_theta)
     uint32_t key0, key1, iter;
     const int* chain_ids;  // [nsys] global chain id for the philox counter (or null -> sys index)
@@ -104,15 +109,37 @@ struct SampleArgs {
     double* lnpost_out;    // [nsys] output slot
     int n, Np, T, Tp, ntiles, nsys;
     int beta_mode, philox;
+    int ntilesE;           // > 0: Em / Eu are per-tile partial sums [nsys][ntilesE][n]
     uint32_t key0, key1, iter;
     const int* chain_ids;
     long long ps_bs, lnpost_bs, draws_bs;
 };
 void launch_sample(const SampleArgs& a, cudaStream_t st);
 
-// z[sys][t][x] = nu[sys][x] * CN(0,1) (philox), zero for t >= T
-void launch_noise_draw(double* z, const double* nu, int T, int Tp, int n, int nsys, uint32_t key0,
-                       uint32_t key1, uint32_t iter, const int* chain_ids, cudaStream_t st);
+// ---- fused FFT kernels (hp_fft.cu) ----------------------------------------------------------
+struct FftPlan { int n, nf; int radix[16]; };
+bool make_fft_plan(int n, FftPlan* plan);          // false: n has a prime factor > 31 (dense fallback)
+void launch_twiddles(double* tw, int n, cudaStream_t st);  // tw[j] = exp(-2 pi i j / n), interleaved
+int postfft_tiles(int T);
+size_t postfft_smem_bytes(int n, int m);
+
+struct PostFftArgs {
+    FftPlan plan;
+    const double* tw;
+    const double* X;       // [nsys][Tp][Np]
+    const double* lam;     // [nsys][Np]
+    double* Sf;            // [nsys][..][n] frequency-space signal: written (do_inverse) or read
+    long long sf_bs;
+    const double* Ft;      // [nsys][m][n]
+    const double* wd; const double* w; const double* ninvd;
+    double* fg_out; double* chisq_out; long long fg_bs, chisq_bs;
+    double* lnp1;          // [nsys][Tp]
+    double* Empart;        // [nsys][tiles][n] or null
+    double* Eupart;        // [nsys][tiles][n] or null
+    int m, Np, T, Tp, nsys, do_inverse;
+};
+void launch_post_fft(const PostFftArgs& a, cudaStream_t st);
+
 
 // small elementwise helpers used by the set-up
 void launch_scale_rows(double* A, const double* d, int rows, int cols, long long ld, cudaStream_t st);  // A[r][:] *= d[r]

@@ -37,9 +37,9 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
     const int N = n + m, nblk = (N + 31) / 32, Np = nblk * 32, ntiles = (T + 15) / 16, Tp = ntiles * 16;
     double *dG, *dGp, *dlam, *dLp, *dLinv, *dR, *dW = nullptr, *dX, *dS, *dP;
     int* dinfo;
-    size_t tri = hp::tri_blocks(nblk) * hp::kBlkDoubles;
-    cudaMalloc(&dG, 16ull * N * N); cudaMalloc(&dGp, 8 * tri); cudaMalloc(&dlam, 8ull * Np); cudaMalloc(&dLp, 8 * tri);
-    cudaMalloc(&dLinv, 8ull * nblk * hp::kBlkDoubles); cudaMalloc(&dR, 16ull * Tp * Np); cudaMalloc(&dX, 16ull * Tp * Np);
+    size_t tri = hp::tri_blocks(nblk) * hp::kLBlkDoubles, trig = hp::tri_blocks(nblk) * hp::kBlkDoubles;
+    cudaMalloc(&dG, 16ull * N * N); cudaMalloc(&dGp, 8 * trig); cudaMalloc(&dlam, 8ull * Np); cudaMalloc(&dLp, 8 * tri);
+    cudaMalloc(&dLinv, 8ull * nblk * hp::kLBlkDoubles); cudaMalloc(&dR, 16ull * Tp * Np); cudaMalloc(&dX, 16ull * Tp * Np);
     cudaMalloc(&dS, 16ull * Tp * n); cudaMalloc(&dP, 8ull * ntiles * n); cudaMalloc(&dinfo, 4);
     cudaMemset(dR, 0, 16ull * Tp * Np); cudaMemset(dlam, 0, 8ull * Np);
     cudaMemcpy(dG, G, 16ull * N * N, cudaMemcpyHostToDevice);
@@ -68,8 +68,8 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
                 for (int j = 0; j < N; ++j) {
                     double re = 0, im = 0;
                     if (j <= i) {
-                        const double* b = lp.data() + hp::blk_index(i / 32, j / 32) * hp::kBlkDoubles;
-                        re = b[(i % 32) * 32 + (j % 32)]; im = b[1024 + (i % 32) * 32 + (j % 32)];
+                        const double* b = lp.data() + hp::blk_index(i / 32, j / 32) * hp::kLBlkDoubles;
+                        re = b[(i % 32) * hp::kLdBlk + (j % 32)]; im = b[hp::kLPlane + (i % 32) * hp::kLdBlk + (j % 32)];
                     }
                     Ldense[2 * ((size_t)i * N + j)] = re; Ldense[2 * ((size_t)i * N + j) + 1] = im;
                 }

@@ -30,6 +30,10 @@ from . import _lib, utils
 
 GCR_SEED_BASE = 912983  # pspec.py:153
 
+# Test switch: apply the Fourier operator as dense products instead of the fused FFT kernels (the
+# path Nfreqs with a prime factor > 31 takes anyway).
+_FORCE_DENSE_TRANSFORMS = False
+
 
 # --------------------------------------------------------------------------------------------
 # host-side helpers of the reference API (not on the hot path)
@@ -171,7 +175,7 @@ class GibbsEngine:
 
     def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
                  refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
-                 stream=None, profile=False):
+                 stream=None, profile=False, force_dense_transforms=False):
         self._h = None
         L = _lib.lib()
         cfg = _lib.HPConfig()
@@ -188,6 +192,7 @@ class GibbsEngine:
         cfg.max_iters = int(max_iters)
         cfg.general_basis0 = int(bool(general_basis0))
         cfg.profile = int(bool(profile))
+        cfg.force_dense_transforms = int(bool(force_dense_transforms))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.stream = stream
         h = _lib.C.c_void_p()
@@ -355,7 +360,8 @@ def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng,
         raise ValueError("solver must be 'reference-cg' or 'exact'")
     eng = GibbsEngine(1, ntimes, nfreqs, nmodes, max_iters, rng=rng, cg_compat=(solver == "reference-cg"),
                       refresh_omega=(rng == "philox"), keep=keep, general_basis0=basis0 is not None,
-                      seed=0 if seed is None else seed, device=device)
+                      seed=0 if seed is None else seed, device=device,
+                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS)
     eng.load_chain(0, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=ps_prior, basis0=basis0)
     if rng == "numpy":
         if map_estimate:

@@ -52,18 +52,21 @@ typedef struct hp_config {
     int cg_compat;       /* 1: reproduce the reference's truncated CG (pspec.py:228) through the
                             scalar model in csrc/hp_math.h; 0: exact solve */
     int refresh_omega;   /* Philox only. 1: new GCR fluctuation draws every iteration; 0: the same
-                            draws in every iteration, as the reference does (pspec.py:195-197) */
+                            white draws in every iteration (the reference re-uses its draws,
+                            pspec.py:195-197) */
     int keep;            /* hp_keep bitmask */
     int max_iters;       /* capacity of the per-iteration output buffers */
     int general_basis0;  /* 1: S_initial is not delay-diagonal; hp_engine_load_chain gets its
                             eigenvectors (first iteration runs in that basis) */
     int profile;         /* 1: record per-kernel CUDA-event timings (hp_engine_kernel_ms) */
+    int force_dense_transforms; /* 1: apply the Fourier operator as dense products even when Nfreqs has
+                            an FFT plan (the path used for Nfreqs with a prime factor > 31); tests */
     uint64_t seed;       /* Philox key */
     void* stream;        /* cudaStream_t to launch on, or NULL for an engine-owned stream */
 } hp_config;
 
 /* Number of kernel classes reported by hp_engine_kernel_ms and their names. */
-#define HP_NUM_KERNEL_CLASSES 6
+#define HP_NUM_KERNEL_CLASSES 5
 const char* hp_kernel_class_name(int cls);
 
 int hp_engine_create(const hp_config* cfg, hp_engine** out);

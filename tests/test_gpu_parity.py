@@ -50,11 +50,14 @@ def test_map_estimate_matches_reference_golden(golden_dir):
         assert rel(o, g[k]) < TOL, k
 
 
+@pytest.mark.parametrize("dense", [False, True])
 @pytest.mark.parametrize("nt,nf,nm,nflag,seed", [(16, 32, 4, 0, 1), (21, 45, 5, 3, 2), (40, 120, 12, 5, 3),
-                                                 (33, 96, 0, 2, 4)])
-def test_chain_matches_oracle_exact(nt, nf, nm, nflag, seed):
-    """Fresh inputs, numpy draw streams, exact solver on both sides."""
+                                                 (33, 96, 0, 2, 4), (9, 37, 3, 1, 5), (5, 77, 2, 0, 6)])
+def test_chain_matches_oracle_exact(nt, nf, nm, nflag, seed, dense, monkeypatch):
+    """Fresh inputs, numpy draw streams, exact solver on both sides.  Runs through the fused FFT
+    kernels and through the dense-transform path (which Nfreqs = 37 takes in any case)."""
     from hydra_pspec_b200 import pspec
+    monkeypatch.setattr(pspec, "_FORCE_DENSE_TRANSFORMS", dense)
     rng = np.random.default_rng(seed)
     F = np.linalg.qr(crandn(rng, nf, max(nm, 1)))[0][:, :nm]
     fop = ho.fourier_operator(nf)
