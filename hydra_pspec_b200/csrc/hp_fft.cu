@@ -207,19 +207,55 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     double2* obuf = sbuf == buf0 ? buf1 : buf0;
     __syncthreads();
     // foreground model F f on the tensor pipe:  obuf[t][x] = sum_j f[t][j] Ft[j][x]
+    // A = f tile (8 x m) stays in registers for all column tiles; the B fragments of a tile come
+    // straight from global (L2-resident Ft) as one 16-byte load per k-step, issued as a batch and
+    // prefetched one tile ahead.
     {
         const double* Ft = a.Ft + 2 * (size_t)sys * m * n;
         const int nct = (n + 7) / 8;
         const int g = lane >> 2, q = lane & 3;
-        for (int ct = warp; ct < nct; ct += 8) {
-            double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
-            if (m > 0) warp_fg_product<false>(cr, ci, fs, ldf, Ft, n, 1, 8 * ct, n, 0, m);
+        for (int kc = 0; kc < mk; kc += 32) {  // chunks of 8 k-steps
+            double2 af[8], bcur[8], bnxt[8];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int x = 8 * ct + 2 * q + e;
-                if (x < n) obuf[(size_t)g * n + x] = make_double2(cr[e], ci[e]);
+            for (int s8 = 0; s8 < 8; ++s8) {
+                int k = kc + 4 * s8 + q;
+                af[s8] = k < mk ? fs[(size_t)g * ldf + k] : make_double2(0.0, 0.0);
+            }
+            auto load_b = [&](int ct, double2 (&b)[8]) {
+                const int x = 8 * ct + g;
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    int k = kc + 4 * s8 + q;
+                    b[s8] = (k < m && x < n && ct < nct) ? *reinterpret_cast<const double2*>(Ft + 2 * ((size_t)k * n + x))
+                                                         : make_double2(0.0, 0.0);
+                }
+            };
+            load_b(warp, bcur);
+            for (int ct = warp; ct < nct; ct += 8) {
+                load_b(ct + 8, bnxt);
+                double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0}, dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0};
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    dmma884(cr[0], cr[1], af[s8].x, bcur[s8].x);
+                    dmma884(ci[0], ci[1], af[s8].x, bcur[s8].y);
+                    dmma884(dr[0], dr[1], af[s8].y, bcur[s8].y);
+                    dmma884(di[0], di[1], af[s8].y, bcur[s8].x);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int x = 8 * ct + 2 * q + e;
+                    if (x < n) {
+                        double2 v = make_double2(cr[e] - dr[e], ci[e] + di[e]);
+                        if (kc) { double2 o = obuf[(size_t)g * n + x]; v.x += o.x; v.y += o.y; }
+                        obuf[(size_t)g * n + x] = v;
+                    }
+                }
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) bcur[s8] = bnxt[s8];
             }
         }
+        if (mk == 0)
+            for (int e = tid; e < kTP * n; e += 256) obuf[e] = make_double2(0.0, 0.0);
     }
     __syncthreads();
     // residual, chi^2, ln-posterior partial, masked signal

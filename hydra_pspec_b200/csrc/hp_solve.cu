@@ -143,6 +143,16 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     if (warp == 8) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
+            // pull this tile's right-hand-side rows into L2 ahead of the consumers' row-by-row loads
+            for (int t = 0; t < kTT; ++t) {
+                if (tile * kTT + t >= a.T) break;
+                const double* rrow = a.Rfix + 2 * (((size_t)sys * a.Tp + (size_t)tile * kTT + t) * Np);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rrow), "r"((uint32_t)(Np * 16)) : "memory");
+                if (a.wa) {
+                    const double* wrow = a.wa + 2 * (((size_t)sys * a.Tp + (size_t)tile * kTT + t) * Np);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wrow), "r"((uint32_t)(Np * 16)) : "memory");
+                }
+            }
             uint32_t item = 0;
             auto push = [&](const double* src) {
                 const uint32_t s = item % kStages, k = item / kStages;
@@ -186,10 +196,15 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     };
 
     // ------------------------------------------------------------------ forward:  L Y = R
-    for (int i = 0; i < nblk; ++i) {
-        double rr[2], ri[2];
+    double rn[2], in_[2];  // right-hand side of the next block row (prefetched one row ahead)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) rhs_elem(rc, 32 * i + 8 * ti + g, 8 * tj + 2 * q + e, rr[e], ri[e]);
+    for (int e = 0; e < 2; ++e) rhs_elem(rc, 8 * ti + g, 8 * tj + 2 * q + e, rn[e], in_[e]);
+    for (int i = 0; i < nblk; ++i) {
+        double rr[2] = {rn[0], rn[1]}, ri[2] = {in_[0], in_[1]};
+        if (i + 1 < nblk) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) rhs_elem(rc, 32 * (i + 1) + 8 * ti + g, 8 * tj + 2 * q + e, rn[e], in_[e]);
+        }
         double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         for (int j = 0; j < i; ++j) {
             const double* blk = acquire();
