@@ -118,7 +118,7 @@ struct hp_engine {
     Basis bF, b0;
     double *lam = nullptr, *ps = nullptr;
     double *wd = nullptr, *w = nullptr, *ninvd = nullptr, *ni = nullptr, *nu = nullptr, *Ft = nullptr, *prior = nullptr;
-    double *Lp = nullptr, *Linvp = nullptr;
+    double *Lp = nullptr, *Linvp = nullptr, *Wp = nullptr;
     int* info = nullptr;
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
     double *Em = nullptr, *Eu = nullptr, *lnp1 = nullptr;
@@ -174,7 +174,7 @@ int hp_engine_destroy(hp_engine* e) {
     if (e->st) cudaStreamSynchronize(e->st);
     for (auto& x : e->ev) cudaEventDestroy(x);
     e->bF.release(); e->b0.release();
-    double* ptrs[] = {e->Fop, e->U, e->lam, e->ps, e->wd, e->w, e->ninvd, e->ni, e->nu, e->Ft, e->prior, e->Lp, e->Linvp,
+    double* ptrs[] = {e->Fop, e->U, e->lam, e->ps, e->wd, e->w, e->ninvd, e->ni, e->nu, e->Ft, e->prior, e->Lp, e->Linvp, e->Wp,
                       e->X, e->Ssc, e->Ppart, e->Sf, e->Wm, e->Tmp, e->Em, e->Eu, e->lnp1, e->sdraws,
                       e->ps_out, e->lnpost_out, e->cr_out, e->fg_out, e->chisq_out, e->Gd, e->stage, e->vecn,
                       e->tw, e->Empart, e->Eupart};
@@ -231,6 +231,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     A_TRY(dalloc(&e->prior, C * 2 * n));
     A_TRY(dalloc(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles));
     A_TRY(dalloc(&e->Linvp, C * e->nblk * hp::kLBlkDoubles));
+    A_TRY(dalloc(&e->Wp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles));
     A_TRY(dalloc(&e->info, C));
     A_TRY(dalloc(&e->X, 2 * C * Tp * Np)); A_TRY(dalloc(&e->Ssc, 2 * C * Tp * n));
     A_TRY(dalloc(&e->Ppart, C * e->ntiles * n)); A_TRY(dalloc(&e->Sf, 2 * C * Tp * n));
@@ -404,13 +405,14 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o) {
     ca.Gp = b.Gp; ca.lam = e->lam; ca.Lp = e->Lp; ca.Linvp = e->Linvp; ca.info = e->info;
     ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = e->C;
     hp::launch_chol(ca, e->st);
-    e->prof_end(CLS_CHOL, 1);
+    hp::launch_trinv(e->Lp, e->Linvp, e->Wp, e->nblk, e->C, e->st);
+    e->prof_end(CLS_CHOL, 2);
 
     const bool fused_inverse = e->fft_ok && !general;  // s = U^H (lam ytilde) inside k_post_fft
     e->prof_begin(CLS_SOLVE);
     hp::SolveArgs sa{};
-    sa.Lp = e->Lp; sa.Linvp = e->Linvp; sa.lam = e->lam;
-    sa.Rfix = b.Rfix; sa.eta = nullptr;
+    sa.Wp = e->Wp; sa.lam = e->lam;
+    sa.Rfix = b.Rfix;
     bool any_omega = false;
     for (auto h : e->have_omega) any_omega |= (h != 0);
     sa.wa = (!philox && any_omega) ? b.wa : nullptr;

@@ -314,6 +314,81 @@ void launch_chol(const CholArgs& a, cudaStream_t st) {
 }
 
 // ==========================================================================================
+// k_trinv: W = L^-1 (block lower triangular), one CTA per (block column, system).
+//   W_jj = V_jj (inverse of the diagonal block, from k_chol)
+//   W_ij = -V_ii sum_{k=j}^{i-1} L_ik W_kj            (i > j)
+// With W explicit, both triangular solves of k_solve become plain block products without any
+// dependency between block rows.
+struct TrinvSmem {
+    double A[kLBlkDoubles];   // L_ik, later the accumulated sum (as B operand)
+    double B[kLBlkDoubles];   // W_kj
+    double V[kLBlkDoubles];   // V_ii
+};
+
+__global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lp_all, const double* __restrict__ Linvp_all,
+                                               double* Wp_all, int nblk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TrinvSmem& s = *reinterpret_cast<TrinvSmem*>(smem_raw);
+    const int j = blockIdx.x, sys = blockIdx.y;
+    const double* Lp = Lp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    const double* Vp = Linvp_all + (size_t)sys * nblk * kLBlkDoubles;
+    double* Wp = Wp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int ti = warp >> 1, tj = warp & 1;
+    // W_jj = V_jj
+    for (int e = tid; e < kLBlkDoubles; e += 256) Wp[blk_index(j, j) * kLBlkDoubles + e] = Vp[(size_t)j * kLBlkDoubles + e];
+    for (int i = j + 1; i < nblk; ++i) {
+        double cr[1][2][2], ci[1][2][2];
+        warp_zero<1, 2>(cr, ci);
+        for (int k = j; k < i; ++k) {
+            __syncthreads();  // previous operands consumed; W_kj written by this CTA is visible
+            load_block_async(s.A, Lp + blk_index(i, k) * kLBlkDoubles);
+            load_block_async(s.B, Wp + blk_index(k, j) * kLBlkDoubles);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            warp_zgemm<1, 2, false, false, false, false>(cr, ci, s.A + 8 * ti * kLdBlk, s.A + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                         s.B + 16 * tj, s.B + kLPlane + 16 * tj, kLdBlk, 32);
+        }
+        __syncthreads();
+        load_block_async(s.V, Vp + (size_t)i * kLBlkDoubles);
+        cp_async_commit();
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int r = 8 * ti + g, c = 16 * tj + 8 * jj + 2 * q + e;
+                s.A[r * kLdBlk + c] = -cr[0][jj][e];
+                s.A[kLPlane + r * kLdBlk + c] = -ci[0][jj][e];
+            }
+        cp_async_wait<0>();
+        __syncthreads();
+        double dr[1][2][2], di[1][2][2];
+        warp_zero<1, 2>(dr, di);
+        // V_ii is lower triangular: rows 8 ti.. only need k < 8 (ti + 1)
+        warp_zgemm<1, 2, false, false, false, false>(dr, di, s.V + 8 * ti * kLdBlk, s.V + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                     s.A + 16 * tj, s.A + kLPlane + 16 * tj, kLdBlk, 8 * (ti + 1));
+        double* Wb = Wp + blk_index(i, j) * kLBlkDoubles;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            int r = 8 * ti + g, c = 16 * tj + 8 * jj + 2 * q;
+            *reinterpret_cast<double2*>(Wb + r * kLdBlk + c) = make_double2(dr[0][jj][0], dr[0][jj][1]);
+            *reinterpret_cast<double2*>(Wb + kLPlane + r * kLdBlk + c) = make_double2(di[0][jj][0], di[0][jj][1]);
+        }
+    }
+}
+
+void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, int nsys, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrinvSmem));
+        attr_set = true;
+    }
+    k_trinv<<<dim3(nblk, nsys), 256, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, nblk);
+}
+
+// ==========================================================================================
 // k_post: one CTA per (time, system): model = s + F f, residual, chi^2, flagged copies.
 __global__ void __launch_bounds__(128) k_post(PostArgs a) {
     extern __shared__ double fsh[];  // f_t: 2*m doubles

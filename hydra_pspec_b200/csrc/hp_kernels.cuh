@@ -55,11 +55,13 @@ struct CholArgs {
     int nblk, n, N, nsys;
 };
 void launch_chol(const CholArgs& a, cudaStream_t st);
+// W = L^-1 in the same padded block layout as L ([nsys][tri_blocks][2304])
+void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, int nsys, cudaStream_t st);
 
 struct SolveArgs {
-    const double* Lp; const double* Linvp; const double* lam;   // as above
+    const double* Wp;      // [nsys][tri_blocks][2304]  W = L^-1 (k_trinv)
+    const double* lam;     // [nsys][Np]
     const double* Rfix;    // [nsys][Tp][Np] complex: B^H N^-1 (w d)   (+ frozen noise term in numpy mode)
-    const double* eta;     // [nsys][Tp][Np] complex or null: extra right-hand-side term added to Rfix
     const double* wa;      // [nsys][Tp][Np] complex or null: Q^H omega_a (rows < n)
     double* X;             // [nsys][Tp][Np] complex: solution [ytilde ; f]
     double* Ssc;           // [nsys][Tp][n]  complex: lambda * ytilde (signal in the S eigenbasis)
@@ -67,6 +69,8 @@ struct SolveArgs {
     int nblk, n, N, Tp, ntiles, nsys;
     int T;                 // valid times (t >= T are padding: zero RHS)
     int philox_wa;         // 1: add xi ~ CN(0, I) (Philox) to y = L^-1 r before the backward pass
+    int stages;            // ring depth (set by launch_solve)
+    int rows_per_round;    // times staged through the ring area per round (set by launch_solve)
     int cg_compat;         // 1: scale each column by the scalar CG model (hp_math.h:cg_theta)
     uint32_t key0, key1, iter;
     const int* chain_ids;  // [nsys] global chain id for the philox counter (or null -> sys index)

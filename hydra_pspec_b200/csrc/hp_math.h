@@ -77,6 +77,30 @@ HP_HD void normal_pair(u32x4 r, double& n0, double& n1) {
     n1 = rad * s;
 }
 
+// Two independent N(0,1) with the transcendental part in single precision.  Used for the O(N T)
+// fluctuation draws of the GCR step, where the FP64 pipe is the bottleneck (it is shared with DMMA):
+// a draw is a random number, its low-order bits carry no information, and a 2^-24 relative
+// discretisation of the variate is ~5 orders of magnitude below any Monte-Carlo error.  The radius
+// keeps the full 53-bit range of u1 (ln u1 = ln m + e ln 2 with u1 = m 2^e split exactly), so the
+// tails reach 8.5 sigma as in the double-precision version.
+HP_HD void normal_pair_fast(u32x4 r, double& n0, double& n1) {
+    double u1 = 1.0 - u53(r.x, r.y);  // (0,1]
+    int e;
+    float m = (float)frexp(u1, &e);   // u1 = m 2^e, m in [0.5, 1]
+    float u2 = (float)(r.z >> 8) * (1.0f / 16777216.0f) + (float)(r.w >> 8) * (1.0f / 16777216.0f / 16777216.0f);
+    float lnu = logf(m) + (float)e * 0.69314718055994530942f;
+    float rad = sqrtf(-2.0f * lnu);
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * u2, &s, &c);
+#else
+    s = sinf(6.283185307179586f * u2);
+    c = cosf(6.283185307179586f * u2);
+#endif
+    n0 = (double)(rad * c);
+    n1 = (double)(rad * s);
+}
+
 // Gamma(alpha, 1) for alpha >= 1 (Marsaglia & Tsang 2000).  Consumes philox blocks
 // (c0, c1, sub, c3) with sub = 0, 1, 2, ...
 HP_HD double gamma_mt(double alpha, uint32_t c0, uint32_t c1, uint32_t c3, uint32_t k0, uint32_t k1) {

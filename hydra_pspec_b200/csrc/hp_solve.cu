@@ -1,31 +1,42 @@
-// hp_solve.cu -- k_solve: two-sided triangular solve of the factored GCR system for all times.
+// hp_solve.cu -- k_solve: the GCR solve for all times of a baseline as two triangular block products.
 //
-// Replaces the per-time preconditioned CG of the reference (gcr_fgmodes_1d, pspec.py:151-235):
-// with M = L L^H from k_chol, every time sample is a right-hand side of the same system.
+// Replaces the per-time preconditioned CG of the reference (gcr_fgmodes_1d, pspec.py:151-235).
+// With M = L L^H (k_chol) and W = L^-1 formed explicitly (k_trinv), the solution for every time
+// sample is  x = W^H (W r [+ xi]):  two block-triangular products without any dependency between
+// block rows, instead of a substitution that serialises on every diagonal block.
 //
-// CTA = (tile of 16 times, baseline).  The 16-column solution tile stays in shared memory for the
-// whole forward (L) and backward (L^H) block substitution; the 32x32 blocks of L stream from L2
-// through a 3-stage ring filled by TMA bulk copies (cp.async.bulk + mbarrier, one producer warp),
-// and eight consumer warps run the block products on the FP64 tensor pipe (DMMA.8x8x4), each on an
-// 8x8 complex tile with four independent accumulators.
+// CTA = (tile of 16 times, baseline).  The 16-column tile (right-hand sides, then y = W r, then
+// x = W^H y, all in place) stays in shared memory; the 32x32 blocks of W stream from L2 through a
+// ring filled by TMA bulk copies (cp.async.bulk + mbarrier, one producer warp); eight consumer
+// warps run the block products on the FP64 tensor pipe (DMMA.8x8x4), each on an 8x8 complex tile
+// with four independent accumulators.  In-place works because pass 1 walks the block rows downwards
+// (y_i overwrites r_i once every warp of the column group is past the diagonal block of row i) and
+// pass 2 upwards; the only synchronisation per block row is a split-phase mbarrier (arrive after
+// the diagonal block, wait before the write), which is hidden behind the rest of the row.
 //
 // Right-hand sides are built on the fly (never stored):
 //     injected draws :  r = lam * Rfix + wa                      (Rfix carries B^H N^-1/2 omega_b)
-//     Philox         :  r = lam * Rfix, and xi ~ CN(0, I) is added to y = L^-1 r before the
-//                       backward pass.  Since cov(lam B^H N^-1/2 omega_b + omega_a) = M = L L^H, this
-//                       is the same distribution as drawing omega_a, omega_b (pspec.py:215-222) and
-//                       needs no transform of the noise realisation.
+//     Philox         :  r = lam * Rfix, and xi ~ CN(0, I) is added to y = L^-1 r before the second
+//                       product.  Since cov(lam B^H N^-1/2 omega_b + omega_a) = M = L L^H, this is the
+//                       same distribution as drawing omega_a, omega_b (pspec.py:215-222) and needs no
+//                       transform of the noise realisation.
 #include "hp_kernels.cuh"
 #include "hp_math.h"
 #include "hp_mma.cuh"
+#include <cstdlib>
 
 namespace hp {
 
 namespace {
 
-constexpr int kLdX = 20;       // 16 + 4 doubles, == 4 mod 16
-constexpr int kStages = 3;
+constexpr int kLdX = 16;       // solution tile: 16 columns, no padding; XOR-swizzled (xs) instead
+constexpr int kMaxStages = 6;
 constexpr int kConsumers = 256;
+
+// Shared-memory index of element (row, col) of a 16-column tile.  The column is XORed with
+// 4 (row & 3): a DMMA B-fragment load (4 consecutive rows x 8 columns per half-warp pair) then
+// touches all 32 banks exactly once, with no padding columns.
+__device__ __forceinline__ int xs(int row, int col) { return row * kLdX + (col ^ ((row & 3) << 2)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -53,22 +64,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// all eight consumer warps (the producer warp never takes part)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+// the four warps that own the same eight columns of the solution tile (ids 1 and 2)
+__device__ __forceinline__ void group_sync(int tj) { asm volatile("bar.sync %0, 128;" ::"r"(1 + tj) : "memory"); }
 
 // acc[0] += Ar.Br, acc[1] += Ai.Bi, acc[2] += Ar.Bi, acc[3] += Ai.Br  over k in [k0, k1) (multiples of 4).
 //   A element (row g, k): AT ? A[k * lda + g] : A[g * lda + k]   (pointers already offset to the warp's rows)
-//   B element (k, col g): B[k * ldb + g]
+//   B element (k, col): swizzled 16-column tile, B[xs(k, col)]; Br/Bi point at row 0 of the k range's
+//   block (a multiple of 4 rows), bcol = this lane's column already XORed with 4 q.
 template <bool AT>
 __device__ __forceinline__ void tile_mma(double (&acc)[4][2], const double* __restrict__ Ar, const double* __restrict__ Ai,
-                                         int lda, const double* __restrict__ Br, const double* __restrict__ Bi, int ldb,
+                                         int lda, const double* __restrict__ Br, const double* __restrict__ Bi, int bcol,
                                          int k0, int k1) {
     const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    constexpr int ldb = kLdX;
     const int aoff = AT ? q * lda + g : g * lda + q;
     const int astep = AT ? 4 * lda : 4;
     const double* pa_r = Ar + aoff + (AT ? k0 * lda : k0);
     const double* pa_i = Ai + aoff + (AT ? k0 * lda : k0);
-    const double* pb_r = Br + (k0 + q) * ldb + g;
-    const double* pb_i = Bi + (k0 + q) * ldb + g;
+    const double* pb_r = Br + (k0 + q) * ldb + bcol;
+    const double* pb_i = Bi + (k0 + q) * ldb + bcol;
     double ar = *pa_r, ai = *pa_i, br = *pb_r, bi = *pb_i;
 #pragma unroll 4
     for (int kk = k0; kk < k1; kk += 4) {
@@ -86,7 +102,7 @@ __device__ __forceinline__ void tile_mma(double (&acc)[4][2], const double* __re
 }
 
 struct RhsCtx {
-    const double* Rfix; const double* eta; const double* wa; const double* lam;
+    const double* Rfix; const double* wa; const double* lam;
     int Np, n, N, T, t0;
 };
 
@@ -97,7 +113,6 @@ __device__ __forceinline__ void rhs_elem(const RhsCtx& c, int row, int col, doub
     if (t >= c.T || row >= c.N) return;
     size_t off = 2 * ((size_t)t * c.Np + row);
     double2 x = *reinterpret_cast<const double2*>(c.Rfix + off);
-    if (c.eta) { double2 e = *reinterpret_cast<const double2*>(c.eta + off); x.x += e.x; x.y += e.y; }
     double l = c.lam[row];
     vr = l * x.x; vi = l * x.y;
     if (c.wa && row < c.n) { double2 wv = *reinterpret_cast<const double2*>(c.wa + off); vr += wv.x; vi += wv.y; }
@@ -105,37 +120,42 @@ __device__ __forceinline__ void rhs_elem(const RhsCtx& c, int row, int col, doub
 
 }  // namespace
 
-size_t solve_smem_bytes(int nblk) {
+static size_t solve_smem_bytes_stages(int nblk, int stages) {
     size_t Np = (size_t)nblk * 32;
-    size_t d = 2 * Np * kLdX               // X tile planes
-             + (size_t)kStages * kLBlkDoubles  // ring of L blocks
-             + 2 * 32 * kLdX               // Z
-             + 16 * 16 * 3 + 32            // reductions + theta
-             + 2 * kStages + 2;            // mbarriers
+    size_t d = 2 * Np * kLdX                   // solution tile planes
+             + (size_t)stages * kLBlkDoubles   // ring of W blocks (also the reduction scratch of the epilogue)
+             + 32                              // theta
+             + 2 * kMaxStages + 6;             // mbarriers
     return d * sizeof(double);
 }
+size_t solve_smem_bytes(int nblk) { return solve_smem_bytes_stages(nblk, 2); }  // minimum configuration
 
 __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nblk = a.nblk, Np = nblk * 32;
+    const int kStages = a.stages;
     double* ring = reinterpret_cast<double*>(smem_raw);          // [kStages][2304], 16-byte aligned for TMA
     double* Xr = ring + (size_t)kStages * kLBlkDoubles;
     double* Xi = Xr + (size_t)Np * kLdX;
-    double* Zr = Xi + (size_t)Np * kLdX;
-    double* Zi = Zr + 32 * kLdX;
-    double* red = Zi + 32 * kLdX;                                 // 16*16*3
-    double* theta = red + 16 * 16 * 3;                            // 32
-    uint64_t* full = reinterpret_cast<uint64_t*>(theta + 32);     // [kStages]
-    uint64_t* empty = full + kStages;                             // [kStages]
+    double* theta = Xi + (size_t)Np * kLdX;                       // 32
+    uint64_t* full = reinterpret_cast<uint64_t*>(theta + 32);     // [kMaxStages]
+    uint64_t* empty = full + kMaxStages;                          // [kMaxStages]
+    uint64_t* rowbar = empty + kMaxStages;                        // [2] one per column group
+    uint64_t* stagebar = rowbar + 2;                              // right-hand-side rows landed in the ring area
+    uint64_t* ringfree = rowbar + 3;                              // ... and have been moved into the tile
+    double* red = ring;                                           // 16*16*3, epilogue only (ring idle by then)
 
     const int sys = blockIdx.y, tile = blockIdx.x;
-    const double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
-    const double* Linvp = a.Linvp + (size_t)sys * nblk * kLBlkDoubles;
+    const double* Wp = a.Wp + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
     const double* lam = a.lam + (size_t)sys * Np;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }  // a.stages <= kMaxStages
+        mbar_init(&rowbar[0], 4);
+        mbar_init(&rowbar[1], 4);
+        mbar_init(stagebar, 1);
+        mbar_init(ringfree, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -143,32 +163,37 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     if (warp == 8) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
-            // pull this tile's right-hand-side rows into L2 ahead of the consumers' row-by-row loads
-            for (int t = 0; t < kTT; ++t) {
-                if (tile * kTT + t >= a.T) break;
-                const double* rrow = a.Rfix + 2 * (((size_t)sys * a.Tp + (size_t)tile * kTT + t) * Np);
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rrow), "r"((uint32_t)(Np * 16)) : "memory");
-                if (a.wa) {
-                    const double* wrow = a.wa + 2 * (((size_t)sys * a.Tp + (size_t)tile * kTT + t) * Np);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wrow), "r"((uint32_t)(Np * 16)) : "memory");
+            // The ring area first receives the tile's right-hand-side rows (Rfix[t][0..Np), one bulk copy
+            // per time, `a.rows_per_round` times per round); the consumers move them into the planar
+            // tile and hand the ring back.
+            {
+                const int T0 = tile * kTT;
+                uint32_t par = 0;
+                for (int r0 = 0; r0 < kTT; r0 += a.rows_per_round) {
+                    int nr = 0;
+                    for (int t = r0; t < min(kTT, r0 + a.rows_per_round); ++t) nr += (T0 + t < a.T) ? 1 : 0;
+                    mbar_arrive_expect_tx(stagebar, (uint32_t)nr * Np * 16);
+                    for (int t = r0; t < min(kTT, r0 + a.rows_per_round); ++t)
+                        if (T0 + t < a.T)
+                            bulk_g2s(ring + (size_t)(t - r0) * Np * 2, a.Rfix + 2 * (((size_t)sys * a.Tp + T0 + t) * Np),
+                                     (uint32_t)Np * 16, stagebar);
+                    mbar_wait(ringfree, par);
+                    par ^= 1;
                 }
             }
-            uint32_t item = 0;
+            uint32_t s = 0, round = 0;  // ring slot and how many times the ring has wrapped
             auto push = [&](const double* src) {
-                const uint32_t s = item % kStages, k = item / kStages;
-                if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+                if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
                 mbar_arrive_expect_tx(&full[s], kLBlkDoubles * 8);
                 bulk_g2s(ring + (size_t)s * kLBlkDoubles, src, kLBlkDoubles * 8, &full[s]);
-                ++item;
+                if (++s == (uint32_t)kStages) { s = 0; ++round; }
             };
-            for (int i = 0; i < nblk; ++i) {
-                for (int j = 0; j < i; ++j) push(Lp + blk_index(i, j) * kLBlkDoubles);
-                push(Linvp + (size_t)i * kLBlkDoubles);
-            }
-            for (int i = nblk - 1; i >= 0; --i) {
-                for (int j = i + 1; j < nblk; ++j) push(Lp + blk_index(j, i) * kLBlkDoubles);
-                push(Linvp + (size_t)i * kLBlkDoubles);
-            }
+            // pass 1: block rows downwards, diagonal block first
+            for (int i = nblk - 1; i >= 0; --i)
+                for (int j = i; j >= 0; --j) push(Wp + blk_index(i, j) * kLBlkDoubles);
+            // pass 2: block rows upwards; row i of W^H is column i of W, diagonal block first
+            for (int i = 0; i < nblk; ++i)
+                for (int j = i; j < nblk; ++j) push(Wp + blk_index(j, i) * kLBlkDoubles);
         }
         return;
     }
@@ -176,107 +201,123 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     // ---------------------------------------------------------------------- consumer warps
     RhsCtx rc;
     rc.Rfix = a.Rfix + 2 * (size_t)sys * a.Tp * Np;
-    rc.eta = a.eta ? a.eta + 2 * (size_t)sys * a.Tp * Np : nullptr;
     rc.wa = a.wa ? a.wa + 2 * (size_t)sys * a.Tp * Np : nullptr;
     rc.lam = lam; rc.Np = Np; rc.n = a.n; rc.N = a.N; rc.T = a.T; rc.t0 = tile * kTT;
     const uint32_t chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)sys;
     const int g = lane >> 2, q = lane & 3;
-    const int ti = warp >> 1, tj = warp & 1;  // warp tile: rows 8 ti.., cols 8 tj..
-    uint32_t item = 0;
-    auto stage_ptr = [&](uint32_t s) { return ring + (size_t)s * kLBlkDoubles; };
+    // Warp tile: rows 8 ti.., columns 8 tj...  The two column groups (tj = 0, 1) never touch each
+    // other's columns; they share only the ring.
+    const int ti = warp >> 1, tj = warp & 1;
+    const int bcol = (8 * tj + g) ^ (q << 2);  // this lane's B-fragment column in the swizzled tile
+
+    // stage the right-hand sides:  tile[row][col] = lam_row Rfix[t0 + col][row] (+ wa).  The rows arrive
+    // in the ring area by TMA (asynchronous, full DRAM burst instead of a load-use chain); a warp
+    // instruction then moves 8 consecutive rows x 4 times: conflict-free 16-byte reads, at most 2-way
+    // conflicts on the swizzled writes.
+    {
+        const int rl = lane & 7, cl = lane >> 3;
+        const double2* stage = reinterpret_cast<const double2*>(ring);
+        uint32_t par = 0;
+        for (int r0 = 0; r0 < kTT; r0 += a.rows_per_round) {
+            mbar_wait(stagebar, par);
+            par ^= 1;
+            const int ncg = a.rows_per_round / 4;  // column groups in this round
+            const int ngrp = (Np / 8) * ncg;
+            for (int grp = warp; grp < ngrp; grp += 8) {
+                const int row = 8 * (grp / ncg) + rl, tl = 4 * (grp % ncg) + cl, col = r0 + tl;
+                double vr = 0.0, vi = 0.0;
+                if (rc.t0 + col < a.T && row < a.N) {
+                    double2 x = stage[(size_t)tl * Np + row];
+                    const double l = lam[row];
+                    vr = l * x.x; vi = l * x.y;
+                    if (rc.wa && row < a.n) {
+                        double2 wv = *reinterpret_cast<const double2*>(rc.wa + 2 * ((size_t)(rc.t0 + col) * Np + row));
+                        vr += wv.x; vi += wv.y;
+                    }
+                }
+                Xr[xs(row, col)] = vr;
+                Xi[xs(row, col)] = vi;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ringfree);
+        }
+    }
+    consumer_sync();
+
+    uint32_t slot = 0, parity = 0;  // ring slot being consumed and its phase parity
     auto acquire = [&]() -> const double* {
-        const uint32_t s = item % kStages, k = item / kStages;
-        mbar_wait(&full[s], k & 1);
-        return stage_ptr(s);
+        mbar_wait(&full[slot], parity);
+        return ring + (size_t)slot * kLBlkDoubles;
     };
     auto release = [&]() {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[item % kStages]);
-        ++item;
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++slot == (uint32_t)kStages) { slot = 0; parity ^= 1; }
     };
+    uint32_t rowpar = 0;  // phase parity of this group's row barrier
 
-    // ------------------------------------------------------------------ forward:  L Y = R
-    double rn[2], in_[2];  // right-hand side of the next block row (prefetched one row ahead)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) rhs_elem(rc, 8 * ti + g, 8 * tj + 2 * q + e, rn[e], in_[e]);
-    for (int i = 0; i < nblk; ++i) {
-        double rr[2] = {rn[0], rn[1]}, ri[2] = {in_[0], in_[1]};
-        if (i + 1 < nblk) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) rhs_elem(rc, 32 * (i + 1) + 8 * ti + g, 8 * tj + 2 * q + e, rn[e], in_[e]);
-        }
-        double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        for (int j = 0; j < i; ++j) {
-            const double* blk = acquire();
-            tile_mma<false>(acc, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk,
-                            Xr + (size_t)32 * j * kLdX + 8 * tj, Xi + (size_t)32 * j * kLdX + 8 * tj, kLdX, 0, 32);
-            release();
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
-            Zr[r * kLdX + c] = rr[e] - (acc[0][e] - acc[1][e]);
-            Zi[r * kLdX + c] = ri[e] - (acc[2][e] + acc[3][e]);
-        }
-        consumer_sync();
-        {
-            const double* blk = acquire();
-            double y[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-            // Y_i = Linv_ii . Z ; Linv lower triangular: k < 8 (ti + 1)
-            tile_mma<false>(y, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk, Zr + 8 * tj, Zi + 8 * tj, kLdX,
-                            0, 8 * (ti + 1));
-            release();
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
-                double vr = y[0][e] - y[1][e], vi = y[2][e] + y[3][e];
-                if (a.philox_wa && row < a.N && rc.t0 + c < a.T) {
-                    // y += xi, xi ~ CN(0, 1): fluctuation term of the constrained realisation
-                    u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(rc.t0 + c); ctr.z = a.iter; ctr.w = chain;
-                    double n0, n1;
-                    normal_pair(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), n0, n1);
-                    vr += n0 * 0.70710678118654752440; vi += n1 * 0.70710678118654752440;
-                }
-                Xr[(size_t)row * kLdX + c] = vr;
-                Xi[(size_t)row * kLdX + c] = vi;
-            }
-        }
-        consumer_sync();
-    }
-
-    // ------------------------------------------------------------------ backward:  L^H X = Y
+    // ------------------------------------------------------------------ pass 1:  y = W r (+ xi)
     for (int i = nblk - 1; i >= 0; --i) {
         double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        for (int j = i + 1; j < nblk; ++j) {
+        {
+            const double* blk = acquire();  // W_ii, lower triangular: k < 8 (ti + 1)
+            tile_mma<false>(acc, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk, Xr + (size_t)32 * i * kLdX,
+                            Xi + (size_t)32 * i * kLdX, bcol, 0, 8 * (ti + 1));
+            release();
+            if (lane == 0) mbar_arrive(&rowbar[tj]);  // this warp no longer reads r_i
+        }
+        for (int j = i - 1; j >= 0; --j) {
             const double* blk = acquire();
-            // acc += L_ji^H . X_j :  A element (r, k) = conj(L_ji[k][r])
-            tile_mma<true>(acc, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Xr + (size_t)32 * j * kLdX + 8 * tj,
-                           Xi + (size_t)32 * j * kLdX + 8 * tj, kLdX, 0, 32);
+            tile_mma<false>(acc, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk, Xr + (size_t)32 * j * kLdX,
+                            Xi + (size_t)32 * j * kLdX, bcol, 0, 32);
             release();
         }
+        mbar_wait(&rowbar[tj], rowpar);  // all four warps of the group are past the diagonal block
+        rowpar ^= 1;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
-            // conj(A) B:  re = rr + ii, im = ri - ir
-            Zr[r * kLdX + c] = Xr[(size_t)(32 * i + r) * kLdX + c] - (acc[0][e] + acc[1][e]);
-            Zi[r * kLdX + c] = Xi[(size_t)(32 * i + r) * kLdX + c] - (acc[2][e] - acc[3][e]);
-        }
-        consumer_sync();
-        {
-            const double* blk = acquire();
-            double y[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-            // X_i = Linv_ii^H . Z ; Linv^H upper triangular: k >= 8 ti
-            tile_mma<true>(y, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Zr + 8 * tj, Zi + 8 * tj, kLdX, 8 * ti, 32);
-            release();
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
-                Xr[(size_t)row * kLdX + c] = y[0][e] + y[1][e];
-                Xi[(size_t)row * kLdX + c] = y[2][e] - y[3][e];
+            int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
+            double vr = acc[0][e] - acc[1][e], vi = acc[2][e] + acc[3][e];
+            if (a.philox_wa && row < a.N && rc.t0 + c < a.T) {
+                // y += xi, xi ~ CN(0, 1): fluctuation term of the constrained realisation
+                u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(rc.t0 + c); ctr.z = a.iter; ctr.w = chain;
+                double n0, n1;
+                normal_pair_fast(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), n0, n1);
+                vr += n0 * 0.70710678118654752440; vi += n1 * 0.70710678118654752440;
             }
+            Xr[xs(row, c)] = vr;
+            Xi[xs(row, c)] = vi;
         }
-        consumer_sync();
     }
+    group_sync(tj);  // y complete and visible within the column group
+
+    // ------------------------------------------------------------------ pass 2:  x = W^H y
+    for (int i = 0; i < nblk; ++i) {
+        double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        {
+            const double* blk = acquire();  // W_ii^H, upper triangular: k >= 8 ti ; A element (r, k) = conj(W_ii[k][r])
+            tile_mma<true>(acc, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Xr + (size_t)32 * i * kLdX,
+                           Xi + (size_t)32 * i * kLdX, bcol, 8 * ti, 32);
+            release();
+            if (lane == 0) mbar_arrive(&rowbar[tj]);
+        }
+        for (int j = i + 1; j < nblk; ++j) {
+            const double* blk = acquire();  // W_ji^H
+            tile_mma<true>(acc, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Xr + (size_t)32 * j * kLdX,
+                           Xi + (size_t)32 * j * kLdX, bcol, 0, 32);
+            release();
+        }
+        mbar_wait(&rowbar[tj], rowpar);
+        rowpar ^= 1;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
+            // conj(A) B:  re = rr + ii, im = ri - ir
+            Xr[xs(row, c)] = acc[0][e] + acc[1][e];
+            Xi[xs(row, c)] = acc[2][e] - acc[3][e];
+        }
+    }
+    consumer_sync();  // both column groups done; the ring is idle from here on
 
     // ------------------------------------------------------------------ epilogue
     if (a.cg_compat) {
@@ -288,7 +329,7 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
             double vr, vi;
             rhs_elem(rc, row, col, vr, vi);
             double w = row < a.n ? lam[row] * lam[row] : 1.0;
-            double xr = Xr[(size_t)row * kLdX + col], xi = Xi[(size_t)row * kLdX + col];
+            double xr = Xr[xs(row, col)], xi = Xi[xs(row, col)];
             sre += w * (vr * xr + vi * xi);  // conj(R) X
             sim += w * (vr * xi - vi * xr);
             sb += w * (vr * vr + vi * vi);
@@ -307,39 +348,58 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
         consumer_sync();
         for (int e = tid; e < Np * 16; e += kConsumers) {
             int row = e >> 4, col2 = e & 15;
-            double xr = Xr[(size_t)row * kLdX + col2], xi = Xi[(size_t)row * kLdX + col2];
+            double xr = Xr[xs(row, col2)], xi = Xi[xs(row, col2)];
             double tr = theta[2 * col2], tim = theta[2 * col2 + 1];
-            Xr[(size_t)row * kLdX + col2] = tr * xr - tim * xi;
-            Xi[(size_t)row * kLdX + col2] = tr * xi + tim * xr;
+            Xr[xs(row, col2)] = tr * xr - tim * xi;
+            Xi[xs(row, col2)] = tr * xi + tim * xr;
         }
         consumer_sync();
     }
-    double* Xg = a.X + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * Np;
-    double* Sg = a.Ssc ? a.Ssc + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * a.n : nullptr;
-    for (int t = 0; t < kTT; ++t) {
-        for (int row = tid; row < Np; row += kConsumers) {
-            double xr = Xr[(size_t)row * kLdX + t], xi = Xi[(size_t)row * kLdX + t];
-            *reinterpret_cast<double2*>(Xg + 2 * ((size_t)t * Np + row)) = make_double2(xr, xi);
-            if (Sg && row < a.n) {
-                double l = lam[row];
-                *reinterpret_cast<double2*>(Sg + 2 * ((size_t)t * a.n + row)) = make_double2(l * xr, l * xi);
-            }
-        }
-    }
-    double* Pp = a.Ppart + ((size_t)sys * a.ntiles + tile) * a.n;
-    for (int row = tid; row < a.n; row += kConsumers) {
-        double s = 0.0;
+    // write-out with the same 8 rows x 4 times mapping; sum_t |y|^2 per row reduced on the way
+    {
+        double* Xg = a.X + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * Np;
+        double* Sg = a.Ssc ? a.Ssc + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * a.n : nullptr;
+        double* Pp = a.Ppart + ((size_t)sys * a.ntiles + tile) * a.n;
+        const int rl = lane & 7, cl = lane >> 3;
+        for (int rg = warp; rg < Np / 8; rg += 8) {
+            const int row = 8 * rg + rl;
+            const double l = lam[row];
+            double p = 0.0;
 #pragma unroll
-        for (int t = 0; t < kTT; ++t) {
-            double xr = Xr[(size_t)row * kLdX + t], xi = Xi[(size_t)row * kLdX + t];
-            s += xr * xr + xi * xi;
+            for (int cg = 0; cg < 4; ++cg) {
+                const int t = 4 * cg + cl;
+                double xr = Xr[xs(row, t)], xi = Xi[xs(row, t)];
+                *reinterpret_cast<double2*>(Xg + 2 * ((size_t)t * Np + row)) = make_double2(xr, xi);
+                if (Sg && row < a.n) *reinterpret_cast<double2*>(Sg + 2 * ((size_t)t * a.n + row)) = make_double2(l * xr, l * xi);
+                p += xr * xr + xi * xi;
+            }
+            p += __shfl_xor_sync(0xffffffffu, p, 8);
+            p += __shfl_xor_sync(0xffffffffu, p, 16);
+            if (cl == 0 && row < a.n) Pp[row] = p;
         }
-        Pp[row] = s;
     }
 }
 
-void launch_solve(const SolveArgs& a, cudaStream_t st) {
-    size_t smem = solve_smem_bytes(a.nblk);
+void launch_solve(const SolveArgs& a_in, cudaStream_t st) {
+    SolveArgs a = a_in;
+    static int max_smem = 0;
+    if (!max_smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    // deepest ring that fits: the ring hides the L2 latency of the L-block stream
+    int stages = kMaxStages;
+    while (stages > 2 && solve_smem_bytes_stages(a.nblk, stages) > (size_t)max_smem) --stages;
+    a.stages = stages;
+    // right-hand-side rows staged per round: as many times (multiple of 4) as fit into the ring area
+    {
+        size_t ring_bytes = (size_t)stages * kLBlkDoubles * 8, row_bytes = (size_t)a.nblk * 32 * 16;
+        int rpr = (int)(ring_bytes / row_bytes) / 4 * 4;
+        a.rows_per_round = rpr >= kTT ? kTT : (rpr >= 8 ? 8 : 4);
+        if (ring_bytes < 4 * row_bytes) a.rows_per_round = 0;  // cannot happen: 2 stages hold 4 rows up to Np = 576
+    }
+    size_t smem = solve_smem_bytes_stages(a.nblk, stages);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

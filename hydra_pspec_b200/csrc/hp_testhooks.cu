@@ -35,11 +35,11 @@ int hp_test_zgemm(int M, int N, int K, const double* A, int transA, int conjA, c
 int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, const double* Rfix, const double* wa,
                        int cg_compat, double* Ldense, double* X, int* info) {
     const int N = n + m, nblk = (N + 31) / 32, Np = nblk * 32, ntiles = (T + 15) / 16, Tp = ntiles * 16;
-    double *dG, *dGp, *dlam, *dLp, *dLinv, *dR, *dW = nullptr, *dX, *dS, *dP;
+    double *dG, *dGp, *dlam, *dLp, *dLinv, *dWp, *dR, *dW = nullptr, *dX, *dS, *dP;
     int* dinfo;
     size_t tri = hp::tri_blocks(nblk) * hp::kLBlkDoubles, trig = hp::tri_blocks(nblk) * hp::kBlkDoubles;
     cudaMalloc(&dG, 16ull * N * N); cudaMalloc(&dGp, 8 * trig); cudaMalloc(&dlam, 8ull * Np); cudaMalloc(&dLp, 8 * tri);
-    cudaMalloc(&dLinv, 8ull * nblk * hp::kLBlkDoubles); cudaMalloc(&dR, 16ull * Tp * Np); cudaMalloc(&dX, 16ull * Tp * Np);
+    cudaMalloc(&dLinv, 8ull * nblk * hp::kLBlkDoubles); cudaMalloc(&dWp, 8 * tri); cudaMalloc(&dR, 16ull * Tp * Np); cudaMalloc(&dX, 16ull * Tp * Np);
     cudaMalloc(&dS, 16ull * Tp * n); cudaMalloc(&dP, 8ull * ntiles * n); cudaMalloc(&dinfo, 4);
     cudaMemset(dR, 0, 16ull * Tp * Np); cudaMemset(dlam, 0, 8ull * Np);
     cudaMemcpy(dG, G, 16ull * N * N, cudaMemcpyHostToDevice);
@@ -53,8 +53,9 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
     hp::CholArgs ca{};
     ca.Gp = dGp; ca.lam = dlam; ca.Lp = dLp; ca.Linvp = dLinv; ca.info = dinfo; ca.nblk = nblk; ca.n = n; ca.N = N; ca.nsys = 1;
     hp::launch_chol(ca, 0);
+    hp::launch_trinv(dLp, dLinv, dWp, nblk, 1, 0);
     hp::SolveArgs sa{};
-    sa.Lp = dLp; sa.Linvp = dLinv; sa.lam = dlam; sa.Rfix = dR; sa.wa = dW; sa.X = dX; sa.Ssc = dS; sa.Ppart = dP;
+    sa.Wp = dWp; sa.lam = dlam; sa.Rfix = dR; sa.wa = dW; sa.X = dX; sa.Ssc = dS; sa.Ppart = dP;
     sa.nblk = nblk; sa.n = n; sa.N = N; sa.Tp = Tp; sa.ntiles = ntiles; sa.nsys = 1; sa.T = T; sa.cg_compat = cg_compat;
     hp::launch_solve(sa, 0);
     cudaError_t e = cudaDeviceSynchronize();
@@ -75,7 +76,7 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
                 }
         }
     }
-    cudaFree(dG); cudaFree(dGp); cudaFree(dlam); cudaFree(dLp); cudaFree(dLinv); cudaFree(dR); cudaFree(dW); cudaFree(dX);
+    cudaFree(dG); cudaFree(dGp); cudaFree(dlam); cudaFree(dLp); cudaFree(dLinv); cudaFree(dWp); cudaFree(dR); cudaFree(dW); cudaFree(dX);
     cudaFree(dS); cudaFree(dP); cudaFree(dinfo);
     return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
 }

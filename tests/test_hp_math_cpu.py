@@ -27,6 +27,7 @@ def hm():
     L.hp_host_cg_theta.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p]
     L.hp_host_philox.argtypes = [C.c_uint32] * 6 + [C.c_void_p]
     L.hp_host_normals.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.hp_host_normals_fast.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.hp_host_gammas.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     return L
 
@@ -50,6 +51,21 @@ def test_normals_are_standard(hm):
     assert abs(x.var() - 1) < 4 * np.sqrt(2 / n)
     assert stats.kstest(x, "norm").pvalue > 1e-3
     assert abs(np.corrcoef(x[0::2], x[1::2])[0, 1]) < 4 / np.sqrt(n / 2)
+
+
+def test_fast_normals_are_standard(hm):
+    """Single-precision Box-Muller used for the GCR fluctuation draws (hp_math.h: normal_pair_fast)."""
+    n = 2_000_000
+    x = np.empty(n)
+    hm.hp_host_normals_fast(4321, 99, n, x.ctypes.data_as(C.c_void_p))
+    assert abs(x.mean()) < 4 / np.sqrt(n)
+    assert abs(x.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs(np.mean(x ** 4) - 3) < 4 * np.sqrt(96 / n)
+    assert stats.kstest(x, "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(x[0::2], x[1::2])[0, 1]) < 4 / np.sqrt(n / 2)
+    # tails are populated as expected: P(|x| > 4) = 6.33e-5
+    frac = np.mean(np.abs(x) > 4)
+    assert abs(frac - 6.334e-5) < 5 * np.sqrt(6.334e-5 / n)
 
 
 @pytest.mark.parametrize("alpha", [1.0, 15.0, 202.0, 1023.0])
