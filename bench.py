@@ -109,8 +109,12 @@ def _oracle_worker(args):
     from oracle import hydra_oracle as ho
     vis, flags, F, ninv_diag, lam0sq = make_baseline(seed, nt, nf, nm)
     t0 = time.perf_counter()
-    ho.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, np.diag(ninv_diag), np.zeros((2, nf)), Niter=niter, seed=seed,
-                            solver="cg")
+    for it in range(niter):
+        # each Gibbs iteration restarts from S_initial: the per-iteration cost of the reference algorithm
+        # (2 x sqrtm, pinv, Ntimes preconditioned CG solves) without the risk of its CG stagnating on a
+        # later, coloured S sample (1e5 iterations per time)
+        ho.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, np.diag(ninv_diag), np.zeros((2, nf)), Niter=1,
+                                seed=seed + it, solver="cg")
     return time.perf_counter() - t0
 
 

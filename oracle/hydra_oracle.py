@@ -166,6 +166,11 @@ def build_matrices(flags, signal_S, Ninv, fgmodes, need_pinv=True):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             Nih = scipy.linalg.sqrtm(Ni).astype(complex)
+    if not np.all(np.isfinite(Nih)) and np.count_nonzero(Ni - np.diag(np.diagonal(Ni))) == 0:
+        # scipy >= 1.13 returns NaN from sqrtm for a diagonal matrix with two zero eigenvalues in the
+        # same block (two flagged channels close together), which turns the reference's whole chain
+        # into NaN.  The principal square root of a diagonal PSD matrix is the element-wise one.
+        Nih = np.diag(np.sqrt(np.diagonal(Ni))).astype(complex)
     A = np.zeros((nfreqs + nmodes,) * 2, dtype=complex)
     SNi = S @ Ni
     FhNi = fgmodes.conj().T @ Ni

@@ -113,3 +113,16 @@ def test_chains_are_independent_and_seeded():
         assert np.array_equal(x, y)                   # same seed -> bit-identical
     assert not np.array_equal(a[0], c[0])             # different seed
     assert not np.array_equal(a[0], a[1])             # identical data, different chain id -> different draws
+
+
+def test_driver_run_baselines_single_rank():
+    from hydra_pspec_b200 import driver
+    nt, nf, nm = 16, 16, 2
+    bls = []
+    for i in range(3):
+        vis, flags, F, Ninv, prior = make_problem(20 + i, nt, nf, nm, 1)
+        bls.append(dict(vis=vis, flags=flags, fgmodes=F, ninv_diag=np.real(np.diag(Ninv)).copy(), lam0sq=np.ones(nf),
+                        ps_prior=prior))
+    ps, lp = driver.run_baselines(bls, Niter=5, seed=3)
+    assert ps.shape == (3, 5, nf) and lp.shape == (3, 5)
+    assert np.all(np.isfinite(ps)) and np.all(ps > 0) and np.all(np.isfinite(lp))
