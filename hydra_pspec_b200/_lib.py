@@ -24,6 +24,11 @@ class HPConfig(C.Structure):
     ]
 
 
+class HPHostSink(C.Structure):
+    _fields_ = [("signal_ps", C.c_void_p), ("ln_post", C.c_void_p), ("signal_cr", C.c_void_p),
+                ("fg_amps", C.c_void_p), ("chisq", C.c_void_p), ("iters", C.c_int)]
+
+
 class HydraLibError(RuntimeError):
     pass
 
@@ -38,6 +43,7 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "hp_engine_set_draws": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hp_engine_run": (C.c_int, [C.c_void_p, C.c_int]),
+    "hp_engine_run_to_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(HPHostSink)]),
     "hp_engine_gcr": (C.c_int, [C.c_void_p]),
     "hp_engine_sync": (C.c_int, [C.c_void_p]),
     "hp_engine_iterations_done": (C.c_int, [C.c_void_p]),

@@ -99,10 +99,6 @@ struct Basis {
     double* Gp = nullptr;    // [C][tri][2048]
     double* Rfix = nullptr;  // [C][Tp][Np]
     double* wa = nullptr;    // [C][Tp][Np]   injected mode: Q^H omega_a
-    void release() {
-        cudaFree(Bmat); cudaFree(Gp); cudaFree(Rfix); cudaFree(wa);
-        Bmat = Gp = Rfix = wa = nullptr;
-    }
 };
 
 enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4 };
@@ -113,6 +109,7 @@ struct hp_engine {
     hp_config cfg;
     int C, T, n, m, N, nblk, Np, Tp, ntiles;
     cudaStream_t st = nullptr;
+    cudaStream_t copy_st = nullptr;  // device-to-host streaming of the per-iteration outputs
     bool own_stream = false;
     double *Fop = nullptr, *U = nullptr;
     Basis bF, b0;
@@ -125,6 +122,7 @@ struct hp_engine {
     double* sdraws = nullptr;
     double *ps_out = nullptr, *lnpost_out = nullptr, *cr_out = nullptr, *fg_out = nullptr, *chisq_out = nullptr;
     double *Gd = nullptr, *stage = nullptr, *vecn = nullptr;  // set-up scratch
+    void* arena = nullptr;   // one device allocation holds every buffer below
     hp::FftPlan plan{};
     bool fft_ok = false;
     int ntilesE = 0;
@@ -159,6 +157,36 @@ struct hp_engine {
     }
 };
 
+namespace {
+// Collects buffer requests, then serves them all from one cudaMalloc (engine creation / teardown is
+// part of the end-to-end path: one allocation and one free instead of ~45).
+struct ArenaPlan {
+    struct Req { void** p; size_t bytes; };
+    std::vector<Req> reqs;
+    template <typename T>
+    void want(T** p, size_t count) { *p = nullptr; if (count) reqs.push_back({reinterpret_cast<void**>(p), count * sizeof(T)}); }
+    cudaError_t commit(void** base, cudaStream_t st) {
+        size_t total = 0;
+        for (auto& r : reqs) total += (r.bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(base, total ? total : 256);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(*base, 0, total ? total : 256, st);
+        if (e != cudaSuccess) return e;
+        size_t off = 0;
+        for (auto& r : reqs) { *r.p = static_cast<char*>(*base) + off; off += (r.bytes + 255) & ~size_t(255); }
+        return cudaSuccess;
+    }
+};
+
+void want_basis(hp_engine* e, ArenaPlan& ap, Basis& b) {
+    size_t C = e->C;
+    ap.want(&b.Bmat, 2 * C * e->n * e->Np);
+    ap.want(&b.Gp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles);
+    ap.want(&b.Rfix, 2 * C * e->Tp * e->Np);
+    if (e->cfg.rng_mode == HP_RNG_INJECTED) ap.want(&b.wa, 2 * C * e->Tp * e->Np);
+}
+}  // namespace
+
 extern "C" {
 
 const char* hp_last_error(void) { return g_err.c_str(); }
@@ -173,24 +201,10 @@ int hp_engine_destroy(hp_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->st) cudaStreamSynchronize(e->st);
     for (auto& x : e->ev) cudaEventDestroy(x);
-    e->bF.release(); e->b0.release();
-    double* ptrs[] = {e->Fop, e->U, e->lam, e->ps, e->wd, e->w, e->ninvd, e->ni, e->nu, e->Ft, e->prior, e->Lp, e->Linvp, e->Wp,
-                      e->X, e->Ssc, e->Ppart, e->Sf, e->Wm, e->Tmp, e->Em, e->Eu, e->lnp1, e->sdraws,
-                      e->ps_out, e->lnpost_out, e->cr_out, e->fg_out, e->chisq_out, e->Gd, e->stage, e->vecn,
-                      e->tw, e->Empart, e->Eupart};
-    for (double* p : ptrs) cudaFree(p);
-    cudaFree(e->info);
+    cudaFree(e->arena);
+    if (e->copy_st) cudaStreamDestroy(e->copy_st);
     if (e->own_stream) cudaStreamDestroy(e->st);
     delete e;
-    return HP_OK;
-}
-
-static int alloc_basis(hp_engine* e, Basis& b) {
-    size_t C = e->C;
-    CU_TRY(dalloc(&b.Bmat, 2 * C * e->n * e->Np));
-    CU_TRY(dalloc(&b.Gp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles));
-    CU_TRY(dalloc(&b.Rfix, 2 * C * e->Tp * e->Np));
-    if (e->cfg.rng_mode == HP_RNG_INJECTED) CU_TRY(dalloc(&b.wa, 2 * C * e->Tp * e->Np));
     return HP_OK;
 }
 
@@ -220,37 +234,46 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     if (cfg->stream) e->st = (cudaStream_t)cfg->stream;
     else { CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking)); e->own_stream = true; }
     const size_t C = e->C, n = e->n, m = e->m, Np = e->Np, Tp = e->Tp, T = e->T, I = cfg->max_iters;
-    int rc;
-#define A_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { std::string msg = std::string(#x) + ": " + cudaGetErrorString(_e); hp_engine_destroy(e); return fail(HP_ERR_CUDA, msg); } } while (0)
-    A_TRY(dalloc(&e->Fop, 2 * n * n)); A_TRY(dalloc(&e->U, 2 * n * n));
-    if ((rc = alloc_basis(e, e->bF)) != HP_OK) { hp_engine_destroy(e); return rc; }
-    if (cfg->general_basis0 && (rc = alloc_basis(e, e->b0)) != HP_OK) { hp_engine_destroy(e); return rc; }
-    A_TRY(dalloc(&e->lam, C * Np)); A_TRY(dalloc(&e->ps, C * n));
-    A_TRY(dalloc(&e->wd, 2 * C * Tp * n)); A_TRY(dalloc(&e->w, C * n)); A_TRY(dalloc(&e->ninvd, C * n));
-    A_TRY(dalloc(&e->ni, C * n)); A_TRY(dalloc(&e->nu, C * n)); A_TRY(dalloc(&e->Ft, 2 * C * (m ? m : 1) * n));
-    A_TRY(dalloc(&e->prior, C * 2 * n));
-    A_TRY(dalloc(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles));
-    A_TRY(dalloc(&e->Linvp, C * e->nblk * hp::kLBlkDoubles));
-    A_TRY(dalloc(&e->Wp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles));
-    A_TRY(dalloc(&e->info, C));
-    A_TRY(dalloc(&e->X, 2 * C * Tp * Np)); A_TRY(dalloc(&e->Ssc, 2 * C * Tp * n));
-    A_TRY(dalloc(&e->Ppart, C * e->ntiles * n)); A_TRY(dalloc(&e->Sf, 2 * C * Tp * n));
-    A_TRY(dalloc(&e->Wm, 2 * C * Tp * n)); A_TRY(dalloc(&e->Tmp, 2 * C * Tp * n));
-    A_TRY(dalloc(&e->Em, C * n)); A_TRY(dalloc(&e->Eu, C * n)); A_TRY(dalloc(&e->lnp1, C * Tp));
-    if (cfg->rng_mode != HP_RNG_PHILOX) A_TRY(dalloc(&e->sdraws, C * I * n));
-    A_TRY(dalloc(&e->ps_out, C * I * n)); A_TRY(dalloc(&e->lnpost_out, C * I));
-    if (cfg->keep & HP_KEEP_CR) A_TRY(dalloc(&e->cr_out, 2 * C * I * T * n));
-    if (cfg->keep & HP_KEEP_FG) A_TRY(dalloc(&e->fg_out, 2 * C * I * T * (m ? m : 1)));
-    if (cfg->keep & HP_KEEP_CHISQ) A_TRY(dalloc(&e->chisq_out, C * I * T * n));
-    A_TRY(dalloc(&e->Gd, 2 * (size_t)e->N * e->N));
-    A_TRY(dalloc(&e->stage, 2 * (T * n > n * n ? T * n : n * n)));
-    A_TRY(dalloc(&e->vecn, 4 * n));
     e->fft_ok = hp::make_fft_plan(e->n, &e->plan) && hp::postfft_smem_bytes(e->n, e->m) <= (size_t)max_smem &&
                 !cfg->force_dense_transforms;
     e->ntilesE = hp::postfft_tiles(e->T);
-    A_TRY(dalloc(&e->tw, 2 * n));
-    A_TRY(dalloc(&e->Empart, C * e->ntilesE * n)); A_TRY(dalloc(&e->Eupart, C * e->ntilesE * n));
-#undef A_TRY
+    const bool dense = !e->fft_ok;                       // dense-transform scratch
+    const bool need_ssc = dense || cfg->general_basis0;  // lam * ytilde as input of the dense back-transform
+    ArenaPlan ap;
+    ap.want(&e->Fop, 2 * n * n); ap.want(&e->U, 2 * n * n);
+    want_basis(e, ap, e->bF);
+    if (cfg->general_basis0) want_basis(e, ap, e->b0);
+    ap.want(&e->lam, C * Np); ap.want(&e->ps, C * n);
+    ap.want(&e->wd, 2 * C * Tp * n); ap.want(&e->w, C * n); ap.want(&e->ninvd, C * n);
+    ap.want(&e->ni, C * n); ap.want(&e->nu, C * n); ap.want(&e->Ft, 2 * C * (m ? m : 1) * n);
+    ap.want(&e->prior, C * 2 * n);
+    ap.want(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
+    ap.want(&e->Linvp, C * e->nblk * hp::kLBlkDoubles);
+    ap.want(&e->Wp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
+    ap.want(&e->info, C);
+    ap.want(&e->X, 2 * C * Tp * Np);
+    if (need_ssc) ap.want(&e->Ssc, 2 * C * Tp * n);
+    ap.want(&e->Ppart, C * e->ntiles * n); ap.want(&e->Sf, 2 * C * Tp * n);
+    if (dense) { ap.want(&e->Wm, 2 * C * Tp * n); ap.want(&e->Tmp, 2 * C * Tp * n); ap.want(&e->Em, C * n); ap.want(&e->Eu, C * n); }
+    ap.want(&e->lnp1, C * Tp);
+    if (cfg->rng_mode != HP_RNG_PHILOX) ap.want(&e->sdraws, C * I * n);
+    ap.want(&e->ps_out, C * I * n); ap.want(&e->lnpost_out, C * I);
+    if (cfg->keep & HP_KEEP_CR) ap.want(&e->cr_out, 2 * C * I * T * n);
+    if (cfg->keep & HP_KEEP_FG) ap.want(&e->fg_out, 2 * C * I * T * (m ? m : 1));
+    if (cfg->keep & HP_KEEP_CHISQ) ap.want(&e->chisq_out, C * I * T * n);
+    ap.want(&e->Gd, 2 * (size_t)e->N * e->N);
+    ap.want(&e->stage, 2 * (T * n > n * n ? T * n : n * n));
+    ap.want(&e->vecn, 4 * n);
+    ap.want(&e->tw, 2 * n);
+    ap.want(&e->Empart, C * e->ntilesE * n); ap.want(&e->Eupart, C * e->ntilesE * n);
+    {
+        cudaError_t ce = ap.commit(&e->arena, e->st);
+        if (ce != cudaSuccess) {
+            std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(ce);
+            hp_engine_destroy(e);
+            return fail(HP_ERR_CUDA, msg);
+        }
+    }
     e->flagged.assign(C, 0);
     e->have_omega.assign(C, 0);
     hp::launch_fourier_operator(e->Fop, e->n, 1.0, e->st);
@@ -496,14 +519,11 @@ int hp_engine_gcr(hp_engine* e) {
     return HP_OK;
 }
 
-int hp_engine_run(hp_engine* e, int niter) {
-    if (!e) return fail(HP_ERR_ARG, "null engine");
-    if (niter < 0 || e->out_pos + niter > e->cfg.max_iters)
-        return fail(HP_ERR_ARG, "hp_engine_run: would exceed max_iters (use hp_engine_rewind)");
-    CU_TRY(cudaSetDevice(e->cfg.device));
+// one Gibbs iteration of all chains (gibbs_step_fgmodes, pspec.py:377-490), enqueued on e->st
+static void enqueue_iteration(hp_engine* e) {
     const size_t n = e->n, m = e->m, T = e->T, Tp = e->Tp, I = e->cfg.max_iters;
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
-    for (int k = 0; k < niter; ++k) {
+    {
         const int it = e->out_pos;
         const bool general = e->cfg.general_basis0 && e->iter == 0;
         Basis& b = general ? e->b0 : e->bF;
@@ -534,6 +554,62 @@ int hp_engine_run(hp_engine* e, int niter) {
         e->iter++;
         e->out_pos++;
     }
+}
+
+int hp_engine_run(hp_engine* e, int niter) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (niter < 0 || e->out_pos + niter > e->cfg.max_iters)
+        return fail(HP_ERR_ARG, "hp_engine_run: would exceed max_iters (use hp_engine_rewind)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    for (int k = 0; k < niter; ++k) enqueue_iteration(e);
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
+    if (!e || !sink) return fail(HP_ERR_ARG, "null argument");
+    if (niter < 0 || e->out_pos + niter > e->cfg.max_iters || e->out_pos + niter > sink->iters)
+        return fail(HP_ERR_ARG, "hp_engine_run_to_host: would exceed max_iters / sink capacity");
+    if ((sink->signal_cr && !e->cr_out) || (sink->fg_amps && !e->fg_out) || (sink->chisq && !e->chisq_out))
+        return fail(HP_ERR_ARG, "hp_engine_run_to_host: sink asks for an output that is not kept (cfg.keep)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    if (!e->copy_st) CU_TRY(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+    const size_t n = e->n, m = e->m, T = e->T, I = e->cfg.max_iters, HI = sink->iters;
+    const int first = e->out_pos;
+    std::vector<cudaEvent_t> evs;
+    for (int k = 0; k < niter; ++k) {
+        const size_t it = e->out_pos;
+        enqueue_iteration(e);
+        cudaEvent_t ev;
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        evs.push_back(ev);
+        CU_TRY(cudaEventRecord(ev, e->st));
+        CU_TRY(cudaStreamWaitEvent(e->copy_st, ev, 0));
+        // this iteration's big arrays leave over PCIe while the next iteration computes
+        for (size_t c = 0; c < (size_t)e->C; ++c) {
+            if (sink->signal_cr)
+                CU_TRY(cudaMemcpyAsync(sink->signal_cr + 2 * ((c * HI + it) * T * n), e->cr_out + 2 * ((c * I + it) * T * n),
+                                       T * n * 16, cudaMemcpyDeviceToHost, e->copy_st));
+            if (sink->fg_amps && m)
+                CU_TRY(cudaMemcpyAsync(sink->fg_amps + 2 * ((c * HI + it) * T * m), e->fg_out + 2 * ((c * I + it) * T * m),
+                                       T * m * 16, cudaMemcpyDeviceToHost, e->copy_st));
+            if (sink->chisq)
+                CU_TRY(cudaMemcpyAsync(sink->chisq + (c * HI + it) * T * n, e->chisq_out + (c * I + it) * T * n, T * n * 8,
+                                       cudaMemcpyDeviceToHost, e->copy_st));
+        }
+    }
+    if (niter > 0) {
+        for (size_t c = 0; c < (size_t)e->C; ++c) {
+            if (sink->signal_ps)
+                CU_TRY(cudaMemcpyAsync(sink->signal_ps + (c * HI + first) * n, e->ps_out + (c * I + first) * n,
+                                       (size_t)niter * n * 8, cudaMemcpyDeviceToHost, e->copy_st));
+            if (sink->ln_post)
+                CU_TRY(cudaMemcpyAsync(sink->ln_post + c * HI + first, e->lnpost_out + c * I + first, (size_t)niter * 8,
+                                       cudaMemcpyDeviceToHost, e->copy_st));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(e->copy_st));
+    for (auto ev : evs) cudaEventDestroy(ev);
     CU_TRY(cudaGetLastError());
     return HP_OK;
 }

@@ -242,6 +242,32 @@ class GibbsEngine:
     def run(self, niter):
         _lib.check(_lib.lib().hp_engine_run(self._h, int(niter)))
 
+    def host_buffers(self, iters=None, pinned=True):
+        """Host arrays ``[nchains][iters][...]`` for :meth:`run_to_host` (page-locked by default)."""
+        iters = self.max_iters if iters is None else iters
+        mk = _lib.pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
+        C, T, n, m = self.nchains, self.ntimes, self.nfreqs, self.nmodes
+        out = {"signal_ps": mk((C, iters, n), np.float64), "ln_post": mk((C, iters), np.float64)}
+        if "cr" in self.keep:
+            out["signal_cr"] = mk((C, iters, T, n), np.complex128)
+        if "fg" in self.keep:
+            out["fg_amps"] = mk((C, iters, T, m), np.complex128)
+        if "chisq" in self.keep:
+            out["chisq"] = mk((C, iters, T, n), np.float64)
+        return out
+
+    def run_to_host(self, niter, bufs):
+        """Run ``niter`` iterations and stream every iteration's arrays into ``bufs`` (from
+        :meth:`host_buffers`) while the next iteration computes; returns when all data has landed."""
+        sink = _lib.HPHostSink()
+        for k in ("signal_ps", "ln_post", "signal_cr", "fg_amps", "chisq"):
+            a = bufs.get(k)
+            if a is not None:
+                assert a.flags["C_CONTIGUOUS"] and a.shape[0] == self.nchains
+                setattr(sink, k, a.ctypes.data)
+        sink.iters = int(bufs["signal_ps"].shape[1])
+        _lib.check(_lib.lib().hp_engine_run_to_host(self._h, int(niter), _lib.C.byref(sink)))
+
     def gcr(self):
         _lib.check(_lib.lib().hp_engine_gcr(self._h))
 
@@ -472,29 +498,28 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
                                ("cr", "fg", "chisq"), seed, device, s_uniforms=u)
     write_time = 0.0
     try:
-        if verbose:
-            print("Iter     ln Post")
-            print("-----    -------")
+        bufs = eng.host_buffers(Niter)
         done = 0
         while done < Niter:
             chunk = min(write_Niter, Niter - done) if out_dir is not None else Niter - done
-            eng.run(chunk)
+            eng.run_to_host(chunk, bufs)
             done += chunk
             if out_dir is not None:
                 t0 = time.perf_counter()
-                utils.write_numpy_files(out_dir, eng.signal_cr(0), eng.signal_S(0), eng.signal_ps(0), eng.fg_amps(0),
-                                        eng.chisq(0), eng.ln_post(0))
+                utils.write_numpy_files(out_dir, bufs["signal_cr"][0, :done], eng.signal_S(0), bufs["signal_ps"][0, :done],
+                                        bufs["fg_amps"][0, :done], bufs["chisq"][0, :done], bufs["ln_post"][0, :done])
                 write_time += time.perf_counter() - t0
         bad = eng.info()
         if np.any(bad != 0):
             raise np.linalg.LinAlgError("GCR system not positive definite (Cholesky failed in block column "
                                         f"{int(bad[0]) - 1})")
-        signal_cr = eng.signal_cr(0)
+        # copies: the page-locked staging arrays are released with the engine's buffers
+        signal_cr = np.array(bufs["signal_cr"][0])
         signal_S = eng.signal_S(0)
-        signal_ps = eng.signal_ps(0)
-        fg_amps = eng.fg_amps(0)
-        chisq = eng.chisq(0)
-        ln_post = eng.ln_post(0)
+        signal_ps = np.array(bufs["signal_ps"][0])
+        fg_amps = np.array(bufs["fg_amps"][0])
+        chisq = np.array(bufs["chisq"][0])
+        ln_post = np.array(bufs["ln_post"][0])
     finally:
         eng.close()
     if verbose:

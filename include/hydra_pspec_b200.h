@@ -99,6 +99,15 @@ int hp_engine_set_draws(hp_engine* e, int chain, const double* omega_a, const do
 /* Run `niter` Gibbs iterations (gibbs_step_fgmodes, pspec.py:377-490) for all chains.
  * Asynchronous on the engine's stream. */
 int hp_engine_run(hp_engine* e, int niter);
+/* Host destinations of the sample arrays (page-locked memory recommended: hp_pinned_alloc).  Layout
+ * [nchains][iters][...] with the shapes of hp_buffer; NULL = not wanted. */
+typedef struct hp_host_sink {
+    double* signal_ps; double* ln_post; double* signal_cr; double* fg_amps; double* chisq;
+    int iters;           /* capacity (second dimension) of the host arrays */
+} hp_host_sink;
+/* hp_engine_run + copy-out: every iteration's arrays are streamed to the host on a second stream
+ * while the next iteration computes.  Returns when everything has landed. */
+int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink);
 /* Only the GCR step (gcr_fgmodes, pspec.py:238-310) with the current spectrum; results in
  * HP_BUF_LAST_CR / HP_BUF_LAST_FG. */
 int hp_engine_gcr(hp_engine* e);
