@@ -19,7 +19,8 @@ class HPConfig(C.Structure):
     _fields_ = [
         ("device", C.c_int), ("nchains", C.c_int), ("ntimes", C.c_int), ("nfreqs", C.c_int),
         ("nmodes", C.c_int), ("rng_mode", C.c_int), ("cg_compat", C.c_int), ("refresh_omega", C.c_int),
-        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("force_dense_transforms", C.c_int),
+        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("dense_noise", C.c_int),
+        ("force_dense_transforms", C.c_int),
         ("seed", C.c_uint64), ("stream", C.c_void_p),
     ]
 
@@ -41,6 +42,7 @@ _SIGNATURES = {
     "hp_engine_destroy": (C.c_int, [C.c_void_p]),
     "hp_engine_load_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_engine_load_chain_dense": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9),
     "hp_engine_set_draws": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hp_engine_run": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_engine_run_to_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(HPHostSink)]),

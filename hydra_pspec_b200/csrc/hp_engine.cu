@@ -92,6 +92,34 @@ __global__ void k_scale_vec(double* out, const double* in, double s, int n) {
     if (k < n) out[k] = in[k] * s;
 }
 
+// NiD[x][y] = w[x] w[y] Ninv[x][y]   (flags applied to rows and columns)
+__global__ void k_mask_dense(double* NiD, const double* Ninv, const double* w, int n) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    int x = (int)(e / n), y = (int)(e % n);
+    double s = w[x] * w[y];
+    NiD[2 * e] = s * Ninv[2 * e];
+    NiD[2 * e + 1] = s * Ninv[2 * e + 1];
+}
+// out[t] = Re sum_x conj(A[t][x]) B[t][x]
+__global__ void k_rowdot(const double* A, const double* B, double* out, int T, int Tp, int n) {
+    const int sys = blockIdx.y, t = blockIdx.x;
+    const double* a = A + 2 * (((size_t)sys * Tp + t) * n);
+    const double* b = B + 2 * (((size_t)sys * Tp + t) * n);
+    double acc = 0.0;
+    if (t < T)
+        for (int x = threadIdx.x; x < n; x += blockDim.x) acc += a[2 * x] * b[2 * x] + a[2 * x + 1] * b[2 * x + 1];
+    __shared__ double red[8];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s2 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s2 += red[i];
+        out[(size_t)sys * Tp + t] = s2;
+    }
+}
+
 inline unsigned nblocks(long long tot, int bs = 256) { return (unsigned)((tot + bs - 1) / bs); }
 
 struct Basis {
@@ -116,6 +144,7 @@ struct hp_engine {
     double *lam = nullptr, *ps = nullptr;
     double *wd = nullptr, *w = nullptr, *ninvd = nullptr, *ni = nullptr, *nu = nullptr, *Ft = nullptr, *prior = nullptr;
     double *Lp = nullptr, *Linvp = nullptr, *Wp = nullptr;
+    double *NiD = nullptr, *NihD = nullptr, *Td = nullptr, *Rm = nullptr, *Yd = nullptr;  // dense (non-diagonal) noise
     int* info = nullptr;
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
     double *Em = nullptr, *Eu = nullptr, *lnp1 = nullptr;
@@ -256,6 +285,11 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->Ppart, C * e->ntiles * n); ap.want(&e->Sf, 2 * C * Tp * n);
     if (dense) { ap.want(&e->Wm, 2 * C * Tp * n); ap.want(&e->Tmp, 2 * C * Tp * n); ap.want(&e->Em, C * n); ap.want(&e->Eu, C * n); }
     ap.want(&e->lnp1, C * Tp);
+    if (cfg->dense_noise) {
+        ap.want(&e->NiD, 2 * C * n * n);
+        if (cfg->rng_mode == HP_RNG_INJECTED) ap.want(&e->NihD, 2 * C * n * n);
+        ap.want(&e->Td, 2 * n * Np); ap.want(&e->Rm, 2 * C * Tp * n); ap.want(&e->Yd, 2 * C * Tp * n);
+    }
     if (cfg->rng_mode != HP_RNG_PHILOX) ap.want(&e->sdraws, C * I * n);
     ap.want(&e->ps_out, C * I * n); ap.want(&e->lnpost_out, C * I);
     if (cfg->keep & HP_KEEP_CR) ap.want(&e->cr_out, 2 * C * I * T * n);
@@ -287,33 +321,58 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     return HP_OK;
 }
 
-// G = B^H diag(ni) B (packed), Rfix = B^H diag(ni) (w d)^T  for chain c in basis b
+// G = B^H Ni B (packed), Rfix = B^H Ni (w d)^T  for chain c in basis b; Ni diagonal or dense
 static int build_basis_products(hp_engine* e, Basis& b, int c) {
     const int n = e->n, N = e->N, Np = e->Np, T = e->T;
     double* Bm = b.Bmat + 2 * (size_t)c * n * Np;
+    const bool dn = e->cfg.dense_noise != 0;
+    const double* NiD = dn ? e->NiD + 2 * (size_t)c * n * n : nullptr;
     hp::ZgemmArgs g{};
     g.A = Bm; g.sAi = 1; g.sAk = Np; g.bsA = 0; g.conjA = 1;
-    g.B = Bm; g.sBk = Np; g.sBj = 1; g.bsB = 0; g.conjB = 0;
     g.C = e->Gd; g.sCi = N; g.sCj = 1; g.bsC = 0;
-    g.dk = e->ni + (size_t)c * n; g.bsD = 0;
     g.M = N; g.N = N; g.K = n; g.accumulate = 0; g.alpha = 1.0; g.batch = 1;
+    if (dn) {
+        hp::ZgemmArgs t1{};   // Td = Ni B
+        t1.A = NiD; t1.sAi = n; t1.sAk = 1;
+        t1.B = Bm; t1.sBk = Np; t1.sBj = 1;
+        t1.C = e->Td; t1.sCi = Np; t1.sCj = 1;
+        t1.M = n; t1.N = N; t1.K = n; t1.alpha = 1.0; t1.batch = 1;
+        hp::launch_zgemm(t1, e->st);
+        g.B = e->Td; g.sBk = Np; g.sBj = 1;
+    } else {
+        g.B = Bm; g.sBk = Np; g.sBj = 1; g.bsB = 0; g.conjB = 0;
+        g.dk = e->ni + (size_t)c * n; g.bsD = 0;
+    }
     hp::launch_zgemm(g, e->st);
     hp::launch_pack_lower(e->Gd, N, 0, b.Gp + (size_t)c * hp::tri_blocks(e->nblk) * hp::kBlkDoubles, N, e->nblk, 1, e->st);
     hp::ZgemmArgs r{};
-    r.A = e->wd + 2 * (size_t)c * e->Tp * n; r.sAi = n; r.sAk = 1; r.conjA = 0;
     r.B = Bm; r.sBk = Np; r.sBj = 1; r.conjB = 1;
     r.C = b.Rfix + 2 * (size_t)c * e->Tp * Np; r.sCi = Np; r.sCj = 1;
-    r.dk = e->ni + (size_t)c * n;
     r.M = T; r.N = N; r.K = n; r.accumulate = 0; r.alpha = 1.0; r.batch = 1;
+    if (dn) {
+        hp::ZgemmArgs y{};    // Yd = (w d) Ni^T
+        y.A = e->wd + 2 * (size_t)c * e->Tp * n; y.sAi = n; y.sAk = 1;
+        y.B = NiD; y.sBk = 1; y.sBj = n;
+        y.C = e->Yd + 2 * (size_t)c * e->Tp * n; y.sCi = n; y.sCj = 1;
+        y.M = T; y.N = n; y.K = n; y.alpha = 1.0; y.batch = 1;
+        hp::launch_zgemm(y, e->st);
+        r.A = e->Yd + 2 * (size_t)c * e->Tp * n; r.sAi = n; r.sAk = 1;
+    } else {
+        r.A = e->wd + 2 * (size_t)c * e->Tp * n; r.sAi = n; r.sAk = 1; r.conjA = 0;
+        r.dk = e->ni + (size_t)c * n;
+    }
     hp::launch_zgemm(r, e->st);
     CU_TRY(cudaGetLastError());
     return HP_OK;
 }
 
-int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* flags, const double* fgmodes,
-                         const double* ninv_diag, const double* basis0, const double* lam0sq, const double* ps_prior) {
+static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t* flags, const double* fgmodes,
+                           const double* ninv_diag, const double* ninv_dense, const double* nih_dense, const double* basis0,
+                           const double* lam0sq, const double* ps_prior) {
     if (!e || !vis || !flags || !ninv_diag || !lam0sq || (e->m > 0 && !fgmodes))
         return fail(HP_ERR_ARG, "hp_engine_load_chain: null argument");
+    if ((e->cfg.dense_noise != 0) != (ninv_dense != nullptr))
+        return fail(HP_ERR_ARG, "hp_engine_load_chain: dense noise needs cfg.dense_noise and hp_engine_load_chain_dense");
     if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "hp_engine_load_chain: chain index out of range");
     if (e->cfg.general_basis0 && !basis0) return fail(HP_ERR_ARG, "hp_engine_load_chain: general_basis0 set but basis0 is NULL");
     CU_TRY(cudaSetDevice(e->cfg.device));
@@ -335,6 +394,16 @@ int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* 
                                                e->nu + (size_t)c * n, n);
     if (ps_prior) CU_TRY(cudaMemcpyAsync(e->prior + (size_t)c * 2 * n, ps_prior, 2 * n * sizeof(double), cudaMemcpyHostToDevice, st));
     else CU_TRY(cudaMemsetAsync(e->prior + (size_t)c * 2 * n, 0, 2 * n * sizeof(double), st));
+    if (ninv_dense) {
+        CU_TRY(cudaMemcpyAsync(e->stage, ninv_dense, 2 * (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_mask_dense<<<nblocks((long long)n * n), 256, 0, st>>>(e->NiD + 2 * (size_t)c * n * n, e->stage, e->w + (size_t)c * n, n);
+        CU_TRY(cudaStreamSynchronize(st));
+        if (e->NihD) {
+            if (!nih_dense) return fail(HP_ERR_ARG, "injected-draw mode with dense noise needs the square root of the flagged N^-1");
+            CU_TRY(cudaMemcpyAsync(e->NihD + 2 * (size_t)c * n * n, nih_dense, 2 * (size_t)n * n * sizeof(double),
+                                   cudaMemcpyHostToDevice, st));
+        }
+    }
     // bases
     double* BF = e->bF.Bmat + 2 * (size_t)c * n * Np;
     k_basis_fourier<<<nblocks((long long)n * n), 256, 0, st>>>(BF, e->U, n, Np);
@@ -364,6 +433,18 @@ int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* 
     return HP_OK;
 }
 
+int hp_engine_load_chain(hp_engine* e, int c, const double* vis, const uint8_t* flags, const double* fgmodes,
+                         const double* ninv_diag, const double* basis0, const double* lam0sq, const double* ps_prior) {
+    return load_chain_impl(e, c, vis, flags, fgmodes, ninv_diag, nullptr, nullptr, basis0, lam0sq, ps_prior);
+}
+
+int hp_engine_load_chain_dense(hp_engine* e, int c, const double* vis, const uint8_t* flags, const double* fgmodes,
+                               const double* ninv_diag, const double* ninv_dense, const double* nih_dense,
+                               const double* basis0, const double* lam0sq, const double* ps_prior) {
+    if (!ninv_dense) return fail(HP_ERR_ARG, "hp_engine_load_chain_dense: ninv_dense is NULL");
+    return load_chain_impl(e, c, vis, flags, fgmodes, ninv_diag, ninv_dense, nih_dense, basis0, lam0sq, ps_prior);
+}
+
 int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double* omega_b, const double* s_draws,
                         int n_draw_iters) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
@@ -381,13 +462,23 @@ int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double
         for (int which = 0; which < (e->cfg.general_basis0 ? 2 : 1); ++which) {
             Basis& b = which ? e->b0 : e->bF;
             double* Bm = b.Bmat + 2 * (size_t)c * n * Np;
-            // Rfix += B^H nu omega_b
+            // Rfix += B^H N^-1/2 omega_b
             CU_TRY(cudaMemcpyAsync(e->stage, omega_b, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
             hp::ZgemmArgs r{};
             r.A = e->stage; r.sAi = n; r.sAk = 1;
             r.B = Bm; r.sBk = Np; r.sBj = 1; r.conjB = 1;
             r.C = b.Rfix + 2 * (size_t)c * Tp * Np; r.sCi = Np; r.sCj = 1;
-            r.dk = e->nu + (size_t)c * n;
+            if (e->cfg.dense_noise) {
+                hp::ZgemmArgs y{};   // Yd = omega_b Nih^T
+                y.A = e->stage; y.sAi = n; y.sAk = 1;
+                y.B = e->NihD + 2 * (size_t)c * n * n; y.sBk = 1; y.sBj = n;
+                y.C = e->Yd + 2 * (size_t)c * Tp * n; y.sCi = n; y.sCj = 1;
+                y.M = T; y.N = n; y.K = n; y.alpha = 1.0; y.batch = 1;
+                hp::launch_zgemm(y, st);
+                r.A = e->Yd + 2 * (size_t)c * Tp * n;
+            } else {
+                r.dk = e->nu + (size_t)c * n;
+            }
             r.M = T; r.N = e->N; r.K = n; r.accumulate = 1; r.alpha = 1.0; r.batch = 1;
             hp::launch_zgemm(r, st);
             CU_TRY(cudaStreamSynchronize(st));
@@ -414,6 +505,19 @@ struct IterOut {
     double* fg; long long fg_bs;
     double* chisq; long long chisq_bs;
 };
+
+// dense noise: first ln_post term  sum_x,y conj(wr_x) N^-1_xy wr_y  per time (pspec.py:474-478)
+static void enqueue_dense_lnp1(hp_engine* e) {
+    e->prof_begin(CLS_TRANSFORM);
+    hp::ZgemmArgs y{};
+    y.A = e->Rm; y.sAi = e->n; y.sAk = 1; y.bsA = (long long)e->Tp * e->n;
+    y.B = e->NiD; y.sBk = 1; y.sBj = e->n; y.bsB = (long long)e->n * e->n;
+    y.C = e->Yd; y.sCi = e->n; y.sCj = 1; y.bsC = (long long)e->Tp * e->n;
+    y.M = e->T; y.N = e->n; y.K = e->n; y.alpha = 1.0; y.batch = e->C;
+    hp::launch_zgemm(y, e->st);
+    k_rowdot<<<dim3(e->Tp, e->C), 128, 0, e->st>>>(e->Rm, e->Yd, e->lnp1, e->T, e->Tp, e->n);
+    e->prof_end(CLS_TRANSFORM, 2);
+}
 
 // GCR step (gcr_fgmodes) and everything of gibbs_step_fgmodes up to the power-spectrum draw:
 // chol + solve + back-transform + residual statistics.  `b` is the basis in use.
@@ -468,12 +572,13 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o) {
         pa.plan = e->plan; pa.tw = e->tw; pa.X = e->X; pa.lam = e->lam; pa.Sf = o.sf; pa.sf_bs = o.sf_bs;
         pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
         pa.fg_out = o.fg; pa.fg_bs = o.fg_bs; pa.chisq_out = o.chisq; pa.chisq_bs = o.chisq_bs;
-        pa.lnp1 = e->lnp1;
+        pa.lnp1 = e->lnp1; pa.Rm = e->cfg.dense_noise ? e->Rm : nullptr;
         pa.Empart = e->any_flagged ? e->Empart : nullptr;
         pa.Eupart = general ? e->Eupart : nullptr;
         pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C; pa.do_inverse = fused_inverse ? 1 : 0;
         hp::launch_post_fft(pa, e->st);
         e->prof_end(CLS_POST, 1);
+        if (e->cfg.dense_noise) enqueue_dense_lnp1(e);
         return;
     }
     // dense fallback for Nfreqs with a large prime factor
@@ -481,10 +586,11 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o) {
     hp::PostArgs pa{};
     pa.Sf = o.sf; pa.sf_bs = o.sf_bs; pa.X = e->X; pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
     pa.fg_out = o.fg; pa.fg_bs = o.fg_bs; pa.chisq_out = o.chisq; pa.chisq_bs = o.chisq_bs;
-    pa.Wm = e->any_flagged ? e->Wm : nullptr; pa.Rm = nullptr; pa.lnp1 = e->lnp1;
+    pa.Wm = e->any_flagged ? e->Wm : nullptr; pa.Rm = e->cfg.dense_noise ? e->Rm : nullptr; pa.lnp1 = e->lnp1;
     pa.n = e->n; pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C;
     hp::launch_post(pa, e->st);
     e->prof_end(CLS_POST, 1);
+    if (e->cfg.dense_noise) enqueue_dense_lnp1(e);
     if (e->any_flagged || general) {
         e->prof_begin(CLS_TRANSFORM);
         int nl2 = 0;

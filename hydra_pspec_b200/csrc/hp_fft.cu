@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
                 if (t0 + t < a.T) {
                     if (a.chisq_out) a.chisq_out[(size_t)sys * a.chisq_bs + (size_t)(t0 + t) * n + x] = r2 * ndx;
                     part[t] += wx * ndx * r2;
+                    if (a.Rm)
+                        *reinterpret_cast<double2*>(a.Rm + 2 * (((size_t)sys * a.Tp + t0 + t) * n + x)) = make_double2(wx * rr, wx * ri);
                 }
                 obuf[(size_t)t * n + x] = cmul2(make_double2(wx * s.x, wx * s.y), pre);
             }

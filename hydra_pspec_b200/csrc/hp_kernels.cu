@@ -419,6 +419,10 @@ __global__ void __launch_bounds__(128) k_post(PostArgs a) {
         if (t < a.T) {
             if (a.chisq_out) a.chisq_out[(size_t)sys * a.chisq_bs + (size_t)t * a.n + x] = r2 * nd[x];
             part += w[x] * nd[x] * r2;
+            if (a.Rm) {
+                double* p = a.Rm + 2 * (((size_t)sys * a.Tp + t) * a.n + x);
+                p[0] = w[x] * rr; p[1] = w[x] * ri;
+            }
         }
         if (a.Wm) {
             double* p = a.Wm + 2 * (((size_t)sys * a.Tp + t) * a.n + x);

@@ -138,6 +138,7 @@ struct PostFftArgs {
     const double* wd; const double* w; const double* ninvd;
     double* fg_out; double* chisq_out; long long fg_bs, chisq_bs;
     double* lnp1;          // [nsys][Tp]
+    double* Rm;            // [nsys][Tp][n] complex or null: w * resid (dense noise: ln_post term via k_zgemm)
     double* Empart;        // [nsys][tiles][n] or null
     double* Eupart;        // [nsys][tiles][n] or null
     int m, Np, T, Tp, nsys, do_inverse;

@@ -152,17 +152,33 @@ def _analyse_signal_cov(S):
     return np.ascontiguousarray(V, dtype=np.complex128), np.ascontiguousarray(w, dtype=np.float64)
 
 
-def _diag_noise(Ninv, nfreqs):
+def _noise_model(Ninv, flags, nfreqs, need_sqrt):
+    """Split the inverse noise covariance into what the device needs.
+
+    Returns ``(ninv_diag, ninv_dense, nih_dense)``: the real diagonal (chi^2 weights, pspec.py:452) and,
+    for a non-diagonal ``Ninv``, the full matrix plus -- only when the reference's draws are injected
+    (``need_sqrt``) -- the principal square root of the flagged matrix (pspec.py:362).  With flagged
+    channels and a non-diagonal ``Ninv`` the flags are applied to rows *and* columns (the reference's
+    ``flags.T * Ninv * flags`` masks columns only, its own FIXME at pspec.py:361; the two agree without
+    flags or for a diagonal ``Ninv``).
+    """
     Ninv = np.asarray(Ninv)
     if Ninv.ndim == 3:
         raise NotImplementedError("per-time Ninv (Ntimes, Nfreqs, Nfreqs) is not supported by the reference's "
                                   "build_matrices either (pspec.py:361)")
     if Ninv.shape != (nfreqs, nfreqs):
         raise ValueError("Ninv shape must be (Nfreqs, Nfreqs)")
-    d = np.diagonal(Ninv)
-    if np.any(Ninv - np.diag(d) != 0):
-        raise NotImplementedError("non-diagonal Ninv is not yet supported on the device path")
-    return np.ascontiguousarray(np.real(d), dtype=np.float64)
+    d = np.ascontiguousarray(np.real(np.diagonal(Ninv)), dtype=np.float64)
+    if not np.any(Ninv - np.diag(np.diagonal(Ninv)) != 0):
+        return d, None, None
+    dense = np.ascontiguousarray(Ninv, dtype=np.complex128)
+    nih = None
+    if need_sqrt:
+        w = np.asarray(flags).astype(float)
+        Ni = w[:, None] * dense * w[None, :]
+        ev, V = np.linalg.eigh(0.5 * (Ni + Ni.conj().T))
+        nih = np.ascontiguousarray((V * np.sqrt(np.clip(ev, 0.0, None))) @ V.conj().T)
+    return d, dense, nih
 
 
 # --------------------------------------------------------------------------------------------
@@ -175,7 +191,7 @@ class GibbsEngine:
 
     def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
                  refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
-                 stream=None, profile=False, force_dense_transforms=False):
+                 stream=None, profile=False, force_dense_transforms=False, dense_noise=False):
         self._h = None
         L = _lib.lib()
         cfg = _lib.HPConfig()
@@ -193,6 +209,7 @@ class GibbsEngine:
         cfg.general_basis0 = int(bool(general_basis0))
         cfg.profile = int(bool(profile))
         cfg.force_dense_transforms = int(bool(force_dense_transforms))
+        cfg.dense_noise = int(bool(dense_noise))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.stream = stream
         h = _lib.C.c_void_p()
@@ -216,7 +233,8 @@ class GibbsEngine:
             pass
 
     # -- loading
-    def load_chain(self, chain, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=None, basis0=None):
+    def load_chain(self, chain, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=None, basis0=None, ninv_dense=None,
+                   nih_dense=None):
         T, n, m = self.ntimes, self.nfreqs, self.nmodes
         vis = _lib.c128(vis)
         assert vis.shape == (T, n)
@@ -228,6 +246,13 @@ class GibbsEngine:
         l0 = _lib.f64(lam0sq)
         pr = None if ps_prior is None else _lib.f64(ps_prior)
         b0 = None if basis0 is None else _lib.c128(basis0)
+        if ninv_dense is not None:
+            nD = _lib.c128(ninv_dense)
+            nH = None if nih_dense is None else _lib.c128(nih_dense)
+            _lib.check(_lib.lib().hp_engine_load_chain_dense(self._h, int(chain), _lib.ptr(vis), _lib.ptr(fl), _lib.ptr(F),
+                                                             _lib.ptr(nd), _lib.ptr(nD), _lib.ptr(nH), _lib.ptr(b0),
+                                                             _lib.ptr(l0), _lib.ptr(pr)))
+            return
         _lib.check(_lib.lib().hp_engine_load_chain(self._h, int(chain), _lib.ptr(vis), _lib.ptr(fl), _lib.ptr(F),
                                                    _lib.ptr(nd), _lib.ptr(b0), _lib.ptr(l0), _lib.ptr(pr)))
 
@@ -378,7 +403,7 @@ def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng,
     vis = np.asarray(vis)
     ntimes, nfreqs = vis.shape
     nmodes = np.asarray(fgmodes).shape[1]
-    ninv_diag = _diag_noise(Ninv, nfreqs)
+    ninv_diag, ninv_dense, nih_dense = _noise_model(Ninv, flags, nfreqs, need_sqrt=(rng == "numpy" and not map_estimate))
     basis0, lam0sq = _analyse_signal_cov(S)
     if solver is None:
         solver = "reference-cg" if rng == "numpy" else "exact"
@@ -387,8 +412,9 @@ def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng,
     eng = GibbsEngine(1, ntimes, nfreqs, nmodes, max_iters, rng=rng, cg_compat=(solver == "reference-cg"),
                       refresh_omega=(rng == "philox"), keep=keep, general_basis0=basis0 is not None,
                       seed=0 if seed is None else seed, device=device,
-                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS)
-    eng.load_chain(0, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=ps_prior, basis0=basis0)
+                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS, dense_noise=ninv_dense is not None)
+    eng.load_chain(0, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=ps_prior, basis0=basis0, ninv_dense=ninv_dense,
+                   nih_dense=nih_dense)
     if rng == "numpy":
         if map_estimate:
             oma = omb = None  # pspec.py:210-212

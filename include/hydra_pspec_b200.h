@@ -59,6 +59,7 @@ typedef struct hp_config {
     int general_basis0;  /* 1: S_initial is not delay-diagonal; hp_engine_load_chain gets its
                             eigenvectors (first iteration runs in that basis) */
     int profile;         /* 1: record per-kernel CUDA-event timings (hp_engine_kernel_ms) */
+    int dense_noise;     /* 1: chains are loaded with hp_engine_load_chain_dense (non-diagonal N^-1) */
     int force_dense_transforms; /* 1: apply the Fourier operator as dense products even when Nfreqs has
                             an FFT plan (the path used for Nfreqs with a prime factor > 31); tests */
     uint64_t seed;       /* Philox key */
@@ -86,6 +87,16 @@ int hp_engine_destroy(hp_engine* e);
 int hp_engine_load_chain(hp_engine* e, int chain, const double* vis, const uint8_t* flags, const double* fgmodes,
                          const double* ninv_diag, const double* basis0, const double* lam0sq,
                          const double* ps_prior);
+
+/* Same with a non-diagonal inverse noise covariance (cfg.dense_noise = 1):
+ *   ninv_diag  [Nfreqs] real diagonal of N^-1 (the reference's chi^2 weights, pspec.py:452)
+ *   ninv_dense [Nfreqs][Nfreqs] complex128 Hermitian N^-1; the flags are applied to rows and columns
+ *   nih_dense  [Nfreqs][Nfreqs] complex128 principal square root of the flagged N^-1 (pspec.py:362);
+ *              only read in HP_RNG_INJECTED mode, NULL otherwise (the Philox path never needs it)
+ */
+int hp_engine_load_chain_dense(hp_engine* e, int chain, const double* vis, const uint8_t* flags, const double* fgmodes,
+                               const double* ninv_diag, const double* ninv_dense, const double* nih_dense,
+                               const double* basis0, const double* lam0sq, const double* ps_prior);
 
 /* Injected draws (HP_RNG_INJECTED).
  *   omega_a, omega_b [Ntimes][Nfreqs] complex128: the unit complex Gaussians of pspec.py:215-217

@@ -149,7 +149,7 @@ def sample_S(s=None, sk=None, prior=None, u=None):
 
 # ----------------------------------------------------------------------------
 # pspec.py:325-374
-def build_matrices(flags, signal_S, Ninv, fgmodes, need_pinv=True):
+def build_matrices(flags, signal_S, Ninv, fgmodes, need_pinv=True, symmetric_flags=False):
     """Operators of the GCR system for one flag vector.
 
     Returns dict(Sh, S, Ni, Nih, A, Ai).  ``Ni[i, j] = Ninv[i, j] * flags[j]``
@@ -161,11 +161,20 @@ def build_matrices(flags, signal_S, Ninv, fgmodes, need_pinv=True):
     Sh = scipy.linalg.sqrtm(signal_S).astype(complex)
     S = np.array(signal_S, dtype=complex)
     Ni = (fl * Ninv * fl).astype(complex)
+    if symmetric_flags:
+        # flags on rows and columns (what the CUDA path does for a non-diagonal Ninv; identical to the
+        # reference's column-only masking when Ninv is diagonal or nothing is flagged)
+        Ni = (fl[:, None] * Ninv * fl[None, :]).astype(complex)
     with np.errstate(all="ignore"):
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             Nih = scipy.linalg.sqrtm(Ni).astype(complex)
+    if symmetric_flags:
+        # Schur-based sqrtm loses half the digits on a singular matrix (flagged rows/columns are zero):
+        # take the Hermitian PSD square root from the eigendecomposition instead.
+        ev, V = np.linalg.eigh(0.5 * (Ni + Ni.conj().T))
+        Nih = (V * np.sqrt(np.clip(ev, 0.0, None))) @ V.conj().T
     if not np.all(np.isfinite(Nih)) and np.count_nonzero(Ni - np.diag(np.diagonal(Ni))) == 0:
         # scipy >= 1.13 returns NaN from sqrtm for a diagonal matrix with two zero eigenvalues in the
         # same block (two flagged channels close together), which turns the reference's whole chain
@@ -226,7 +235,7 @@ def gcr_fgmodes(vis, w, mats, fgmodes, oma=None, omb=None, map_estimate=False, s
 
 # pspec.py:377-490
 def gibbs_step_fgmodes(vis, flags, signal_S, fgmodes, Ninv, ps_prior, oma, omb, u,
-                       map_estimate=False, solver="cg"):
+                       map_estimate=False, solver="cg", symmetric_flags=False):
     """One Gibbs iteration.  ``vis`` is already multiplied by the flags (pspec.py:613).
 
     Returns signal_cr, S_sample, ps_sample, fg_amps, chisq, ln_post.
@@ -242,11 +251,11 @@ def gibbs_step_fgmodes(vis, flags, signal_S, fgmodes, Ninv, ps_prior, oma, omb, 
         for t in range(ntimes):
             key = flags[t].tobytes()
             if key not in cache:
-                cache[key] = build_matrices(flags[t], signal_S, Ninv, fgmodes, need_pinv)
+                cache[key] = build_matrices(flags[t], signal_S, Ninv, fgmodes, need_pinv, symmetric_flags)
             mats.append(cache[key])
         w = [flags[t] for t in range(ntimes)]
     else:
-        mats = build_matrices(flags, signal_S, Ninv, fgmodes, need_pinv)
+        mats = build_matrices(flags, signal_S, Ninv, fgmodes, need_pinv, symmetric_flags)
         w = flags
     cr = gcr_fgmodes(vis, w, mats, fgmodes, oma, omb, map_estimate=map_estimate, solver=solver)
     signal_cr = cr[:, :nfreqs]
@@ -269,7 +278,7 @@ def gibbs_step_fgmodes(vis, flags, signal_S, fgmodes, Ninv, ps_prior, oma, omb, 
 
 # pspec.py:493-658
 def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=100, seed=None,
-                         map_estimate=False, solver="cg", draws=None):
+                         map_estimate=False, solver="cg", draws=None, symmetric_flags=False):
     """Chain for one baseline, reference draw sequence (or ``draws=(oma, omb, u[Niter, Nfreqs])``).
 
     Returns signal_cr[Niter], signal_S (last), signal_ps[Niter], fg_amps[Niter],
@@ -297,7 +306,7 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
         u = sd.next(nfreqs) if u_all is None else u_all[i]
         signal_cr[i], signal_S, signal_ps[i], fg_amps[i], chisq[i], ln_post[i] = gibbs_step_fgmodes(
             visf, flags, signal_S, fgmodes, Ninv, ps_prior, oma, omb, u,
-            map_estimate=map_estimate, solver=solver)
+            map_estimate=map_estimate, solver=solver, symmetric_flags=symmetric_flags)
     return signal_cr, signal_S, signal_ps, fg_amps, chisq, ln_post
 
 

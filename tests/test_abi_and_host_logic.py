@@ -110,8 +110,16 @@ def test_host_helpers_match_reference(golden_dir):
         assert abs(pspec.inversion_sample_invgamma(alpha, beta, lo, hi) - want) < 1e-13 * want
 
 
-def test_dense_noise_is_refused_loudly():
+def test_noise_model_split():
     from hydra_pspec_b200 import pspec
-    N = np.eye(4) + 0.1
+    d, dense, nih = pspec._noise_model(np.diag([1.0, 2.0, 3.0]), np.ones(3, bool), 3, True)
+    assert dense is None and nih is None and np.array_equal(d, [1.0, 2.0, 3.0])
+    X = np.random.default_rng(0).standard_normal((4, 9))
+    N = X @ X.T
+    fl = np.array([True, False, True, True])
+    d, dense, nih = pspec._noise_model(N, fl, 4, True)
+    Ni = fl[:, None] * N * fl[None, :]
+    assert np.allclose(nih @ nih, Ni) and np.allclose(nih, nih.conj().T) and np.allclose(d, np.diag(N))
+    assert pspec._noise_model(N, fl, 4, False)[2] is None
     with pytest.raises(NotImplementedError):
-        pspec._diag_noise(N, 4)
+        pspec._noise_model(np.zeros((5, 4, 4)), fl, 4, False)
