@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--nfg", type=int, default=32)
     ap.add_argument("--e2e-baselines", type=int, default=32)
     ap.add_argument("--e2e-iters", type=int, default=16)
+    ap.add_argument("--substreams", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -173,6 +174,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     nt, nf, nm, B = args.ntimes, args.nfreq, args.nfg, args.baselines_per_gpu
     K, W = args.steps, max(args.warmup, 3)
+    KP = 3  # extra, untimed steps on a single stream for the per-kernel CUDA-event timings
     N = nf + nm
     # a non-default torch stream: the engine launches on it, and torch.cuda.Event times it
     tstream = torch.cuda.Stream()
@@ -184,8 +186,8 @@ def run_b200(args):
             dist.barrier()
 
     # ---- resident chains (baselines are independent: rank r holds global baselines r*B .. r*B+B-1)
-    eng = pspec.GibbsEngine(B, nt, nf, nm, max_iters=K + W, rng="philox", cg_compat=False, refresh_omega=True,
-                            keep=(), seed=1234 + rank, device=local_rank, stream=stream)
+    eng = pspec.GibbsEngine(B, nt, nf, nm, max_iters=K + W + KP, rng="philox", cg_compat=False, refresh_omega=True,
+                            keep=(), seed=1234 + rank, device=local_rank, stream=stream, substreams=args.substreams)
     t_load = time.perf_counter()
     for c in range(B):
         vis, flags, F, ninv_diag, lam0sq = make_baseline(rank * B + c, nt, nf, nm)
@@ -197,8 +199,6 @@ def run_b200(args):
     torch.cuda.synchronize()
     barrier()
     l0 = eng.launch_count
-    eng.set_profile(True)
-    eng.kernel_ms(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         ev0.record()
@@ -208,10 +208,15 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - l0
+    # per-kernel durations: same engine, sub-batches off so that the kernels do not overlap
+    eng.set_substreams(1)
+    eng.set_profile(True)
+    eng.kernel_ms(reset=True)
+    eng.run(KP)
     kms = eng.kernel_ms(reset=True)
     eng.set_profile(False)
     bad = int(np.count_nonzero(eng.info()))
-    ps_last = eng.signal_ps(0, W + K - 1, 1)
+    ps_last = eng.signal_ps(0, W + K + KP - 1, 1)
     finite = bool(np.all(np.isfinite(ps_last)))
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -231,7 +236,8 @@ def run_b200(args):
                        "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2",
         "flops_per_launch": flops_per_launch,
         "step_share": {k: v[0] / max(sum(x[0] for x in kms.values()), 1e-9) for k, v in kms.items()},
-        "kernel_ms_per_step": {k: v[0] / K for k, v in kms.items()},
+        "kernel_ms_per_step": {k: v[0] / KP for k, v in kms.items()},
+        "kernel_timing": f"CUDA events around each launch, {KP} extra steps on one stream after the timed region",
     }
     step_flops = (8.0 * N ** 3 / 3 + 8.0 * N * N * nt) * B
     roofline["step_tflops"] = step_flops * K / (ms_max * 1e-3) * 1e-12
@@ -304,7 +310,7 @@ def run_b200(args):
             "config": {"workload": f"HERA-like (BASELINE.json configs[3]): {B} baselines per GPU "
                                    f"(1024 / 8), Nfreq={nf} Ntimes={nt} Nfg={nm}, time-invariant flags (5 %), "
                                    "diagonal noise, device Philox draws, exact solves",
-                       "baselines_per_gpu": B, "parallelism": f"baseline-sharded x{world}, no hot-path collective",
+                       "baselines_per_gpu": B, "substreams": args.substreams, "parallelism": f"baseline-sharded x{world}, no hot-path collective",
                        "l2": f"per-step working set ~{B * 16 * (4 * nt * N + 4 * nt * nf) / 2**30:.1f} GiB per GPU >> 126 MB L2",
                        "outputs_kept": "signal_ps + ln_post per iteration (value); full reference return set (e2e)",
                        "load_s": round(t_load, 2)},

@@ -19,7 +19,7 @@ class HPConfig(C.Structure):
     _fields_ = [
         ("device", C.c_int), ("nchains", C.c_int), ("ntimes", C.c_int), ("nfreqs", C.c_int),
         ("nmodes", C.c_int), ("rng_mode", C.c_int), ("cg_compat", C.c_int), ("refresh_omega", C.c_int),
-        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("dense_noise", C.c_int),
+        ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("substreams", C.c_int), ("dense_noise", C.c_int),
         ("force_dense_transforms", C.c_int),
         ("seed", C.c_uint64), ("stream", C.c_void_p),
     ]
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "hp_engine_read_signal_S": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hp_engine_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_engine_kernel_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hp_engine_set_substreams": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_engine_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_engine_launch_count": (C.c_longlong, [C.c_void_p]),
     "hp_kernel_class_name": (C.c_char_p, [C.c_int]),

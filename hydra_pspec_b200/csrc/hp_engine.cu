@@ -138,6 +138,10 @@ struct hp_engine {
     int C, T, n, m, N, nblk, Np, Tp, ntiles;
     cudaStream_t st = nullptr;
     cudaStream_t copy_st = nullptr;  // device-to-host streaming of the per-iteration outputs
+    std::vector<cudaStream_t> sub_st;   // cfg.substreams > 1: one stream per sub-batch of chains
+    cudaEvent_t fork_ev = nullptr;
+    int active_subs = 1 << 30;          // runtime limit on the number of sub-batches (hp_engine_set_substreams)
+    std::vector<cudaEvent_t> join_ev;
     bool own_stream = false;
     double *Fop = nullptr, *U = nullptr;
     Basis bF, b0;
@@ -171,18 +175,18 @@ struct hp_engine {
     double ms_acc[HP_NUM_KERNEL_CLASSES] = {0};
     int launch_acc[HP_NUM_KERNEL_CLASSES] = {0};
 
-    void prof_begin(int cls) {
+    void prof_begin(int cls, cudaStream_t s) {
         if (!cfg.profile || ev_cls.size() >= 8192) return;
         cudaEvent_t a, b;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, st);
+        cudaEventRecord(a, s);
         ev.push_back(a); ev.push_back(b); ev_cls.push_back(cls);
     }
-    void prof_end(int cls, int nlaunch) {
+    void prof_end(int cls, int nlaunch, cudaStream_t s) {
         launches += nlaunch;
         launch_acc[cls] += nlaunch;
         if (!cfg.profile || ev_cls.empty() || ev_cls.back() != cls) return;
-        cudaEventRecord(ev.back(), st);
+        cudaEventRecord(ev.back(), s);
     }
 };
 
@@ -232,6 +236,9 @@ int hp_engine_destroy(hp_engine* e) {
     for (auto& x : e->ev) cudaEventDestroy(x);
     cudaFree(e->arena);
     if (e->copy_st) cudaStreamDestroy(e->copy_st);
+    for (auto x : e->sub_st) cudaStreamDestroy(x);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+    for (auto x : e->join_ev) cudaEventDestroy(x);
     if (e->own_stream) cudaStreamDestroy(e->st);
     delete e;
     return HP_OK;
@@ -310,6 +317,17 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     }
     e->flagged.assign(C, 0);
     e->have_omega.assign(C, 0);
+    {
+        int ns = cfg->substreams > 1 ? (cfg->substreams < (int)C ? cfg->substreams : (int)C) : 1;
+        if (ns > 1) {
+            for (int i = 0; i < ns; ++i) {
+                cudaStream_t x; cudaEvent_t ev;
+                cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking); e->sub_st.push_back(x);
+                cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); e->join_ev.push_back(ev);
+            }
+            cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming);
+        }
+    }
     hp::launch_fourier_operator(e->Fop, e->n, 1.0, e->st);
     hp::launch_fourier_operator(e->U, e->n, 1.0 / std::sqrt((double)e->n), e->st);
     hp::launch_twiddles(e->tw, e->n, e->st);
@@ -506,112 +524,153 @@ struct IterOut {
     double* chisq; long long chisq_bs;
 };
 
+// A contiguous range of chains advanced on its own stream.  Chains are independent, so the engine
+// splits its batch into `cfg.substreams` such ranges: one range's Cholesky / FFT kernels (low tensor
+// occupancy) then overlap another range's k_solve instead of leaving the FP64 pipe idle.
+struct Sub { int c0, nc; cudaStream_t st; };
+#define OFFS(ptr, per_chain) ((ptr) ? (ptr) + (size_t)sb.c0 * (size_t)(per_chain) : nullptr)
+
 // dense noise: first ln_post term  sum_x,y conj(wr_x) N^-1_xy wr_y  per time (pspec.py:474-478)
-static void enqueue_dense_lnp1(hp_engine* e) {
-    e->prof_begin(CLS_TRANSFORM);
+static void enqueue_dense_lnp1(hp_engine* e, const Sub& sb) {
+    const size_t n = e->n, Tp = e->Tp;
+    e->prof_begin(CLS_TRANSFORM, sb.st);
     hp::ZgemmArgs y{};
-    y.A = e->Rm; y.sAi = e->n; y.sAk = 1; y.bsA = (long long)e->Tp * e->n;
-    y.B = e->NiD; y.sBk = 1; y.sBj = e->n; y.bsB = (long long)e->n * e->n;
-    y.C = e->Yd; y.sCi = e->n; y.sCj = 1; y.bsC = (long long)e->Tp * e->n;
-    y.M = e->T; y.N = e->n; y.K = e->n; y.alpha = 1.0; y.batch = e->C;
-    hp::launch_zgemm(y, e->st);
-    k_rowdot<<<dim3(e->Tp, e->C), 128, 0, e->st>>>(e->Rm, e->Yd, e->lnp1, e->T, e->Tp, e->n);
-    e->prof_end(CLS_TRANSFORM, 2);
+    y.A = OFFS(e->Rm, 2 * Tp * n); y.sAi = e->n; y.sAk = 1; y.bsA = (long long)e->Tp * e->n;
+    y.B = OFFS(e->NiD, 2 * n * n); y.sBk = 1; y.sBj = e->n; y.bsB = (long long)e->n * e->n;
+    y.C = OFFS(e->Yd, 2 * Tp * n); y.sCi = e->n; y.sCj = 1; y.bsC = (long long)e->Tp * e->n;
+    y.M = e->T; y.N = e->n; y.K = e->n; y.alpha = 1.0; y.batch = sb.nc;
+    hp::launch_zgemm(y, sb.st);
+    k_rowdot<<<dim3(e->Tp, sb.nc), 128, 0, sb.st>>>(OFFS(e->Rm, 2 * Tp * n), OFFS(e->Yd, 2 * Tp * n), OFFS(e->lnp1, Tp), e->T,
+                                                   e->Tp, e->n);
+    e->prof_end(CLS_TRANSFORM, 2, sb.st);
 }
 
 // GCR step (gcr_fgmodes) and everything of gibbs_step_fgmodes up to the power-spectrum draw:
 // chol + solve + back-transform + residual statistics.  `b` is the basis in use.
-static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o) {
+static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb, uint32_t draw_iter) {
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
     const bool general = &b == &e->b0;
-    // Philox: the fluctuation term is xi ~ CN(0, I) added between the two triangular solves
-    // (hp_solve.cu); refresh_omega = 0 re-uses the same xi in every iteration.
-    const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
-    e->prof_begin(CLS_CHOL);
+    const size_t n = e->n, m = e->m, Np = e->Np, Tp = e->Tp;
+    const size_t tri = hp::tri_blocks(e->nblk);
+    e->prof_begin(CLS_CHOL, sb.st);
     hp::CholArgs ca{};
-    ca.Gp = b.Gp; ca.lam = e->lam; ca.Lp = e->Lp; ca.Linvp = e->Linvp; ca.info = e->info;
-    ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = e->C;
-    hp::launch_chol(ca, e->st);
-    hp::launch_trinv(e->Lp, e->Linvp, e->Wp, e->nblk, e->C, e->st);
-    e->prof_end(CLS_CHOL, 2);
+    ca.Gp = OFFS(b.Gp, tri * hp::kBlkDoubles); ca.lam = OFFS(e->lam, Np); ca.Lp = OFFS(e->Lp, tri * hp::kLBlkDoubles);
+    ca.Linvp = OFFS(e->Linvp, (size_t)e->nblk * hp::kLBlkDoubles); ca.info = e->info + sb.c0;
+    ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = sb.nc;
+    hp::launch_chol(ca, sb.st);
+    hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), e->nblk, sb.nc, sb.st);
+    e->prof_end(CLS_CHOL, 2, sb.st);
 
     const bool fused_inverse = e->fft_ok && !general;  // s = U^H (lam ytilde) inside k_post_fft
-    e->prof_begin(CLS_SOLVE);
+    e->prof_begin(CLS_SOLVE, sb.st);
     hp::SolveArgs sa{};
-    sa.Wp = e->Wp; sa.lam = e->lam;
-    sa.Rfix = b.Rfix;
+    sa.Wp = OFFS(e->Wp, tri * hp::kLBlkDoubles); sa.lam = OFFS(e->lam, Np);
+    sa.Rfix = OFFS(b.Rfix, 2 * Tp * Np);
     bool any_omega = false;
     for (auto h : e->have_omega) any_omega |= (h != 0);
-    sa.wa = (!philox && any_omega) ? b.wa : nullptr;
-    sa.X = e->X; sa.Ssc = fused_inverse ? nullptr : e->Ssc; sa.Ppart = e->Ppart;
-    sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = e->C; sa.T = e->T;
+    sa.wa = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
+    sa.X = OFFS(e->X, 2 * Tp * Np); sa.Ssc = fused_inverse ? nullptr : OFFS(e->Ssc, 2 * Tp * n);
+    sa.Ppart = OFFS(e->Ppart, (size_t)e->ntiles * n);
+    sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = sb.nc; sa.T = e->T;
     sa.philox_wa = philox ? 1 : 0;
     sa.cg_compat = e->cfg.cg_compat;
     sa.key0 = (uint32_t)e->cfg.seed; sa.key1 = (uint32_t)(e->cfg.seed >> 32); sa.iter = draw_iter;
-    sa.chain_ids = nullptr;
-    hp::launch_solve(sa, e->st);
-    e->prof_end(CLS_SOLVE, 1);
+    sa.chain_ids = nullptr; sa.chain0 = sb.c0;
+    hp::launch_solve(sa, sb.st);
+    e->prof_end(CLS_SOLVE, 1, sb.st);
 
+    double* sf = o.sf + 2 * (size_t)sb.c0 * (size_t)o.sf_bs;
     if (!fused_inverse) {
         // s = Q (lam * ytilde) as a dense product (general eigenbasis, or Nfreqs without an FFT plan)
-        e->prof_begin(CLS_TRANSFORM);
+        e->prof_begin(CLS_TRANSFORM, sb.st);
         hp::ZgemmArgs t{};
-        t.A = e->Ssc; t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
-        t.B = b.Bmat; t.sBk = 1; t.sBj = e->Np; t.bsB = (long long)e->n * e->Np;
-        t.C = o.sf; t.sCi = e->n; t.sCj = 1; t.bsC = o.sf_bs;
-        t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
-        hp::launch_zgemm(t, e->st);
-        e->prof_end(CLS_TRANSFORM, 1);
+        t.A = OFFS(e->Ssc, 2 * Tp * n); t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
+        t.B = OFFS(b.Bmat, 2 * n * Np); t.sBk = 1; t.sBj = e->Np; t.bsB = (long long)e->n * e->Np;
+        t.C = sf; t.sCi = e->n; t.sCj = 1; t.bsC = o.sf_bs;
+        t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = sb.nc;
+        hp::launch_zgemm(t, sb.st);
+        e->prof_end(CLS_TRANSFORM, 1, sb.st);
     }
     e->last_sf = o.sf;
     e->last_sf_bs = o.sf_bs;
+    double* fg = o.fg ? o.fg + (size_t)sb.c0 * (size_t)o.fg_bs : nullptr;
+    double* chisq = o.chisq ? o.chisq + (size_t)sb.c0 * (size_t)o.chisq_bs : nullptr;
 
     if (e->fft_ok) {
-        e->prof_begin(CLS_POST);
+        e->prof_begin(CLS_POST, sb.st);
         hp::PostFftArgs pa{};
-        pa.plan = e->plan; pa.tw = e->tw; pa.X = e->X; pa.lam = e->lam; pa.Sf = o.sf; pa.sf_bs = o.sf_bs;
-        pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
-        pa.fg_out = o.fg; pa.fg_bs = o.fg_bs; pa.chisq_out = o.chisq; pa.chisq_bs = o.chisq_bs;
-        pa.lnp1 = e->lnp1; pa.Rm = e->cfg.dense_noise ? e->Rm : nullptr;
-        pa.Empart = e->any_flagged ? e->Empart : nullptr;
-        pa.Eupart = general ? e->Eupart : nullptr;
-        pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C; pa.do_inverse = fused_inverse ? 1 : 0;
-        hp::launch_post_fft(pa, e->st);
-        e->prof_end(CLS_POST, 1);
-        if (e->cfg.dense_noise) enqueue_dense_lnp1(e);
+        pa.plan = e->plan; pa.tw = e->tw; pa.X = OFFS(e->X, 2 * Tp * Np); pa.lam = OFFS(e->lam, Np); pa.Sf = sf; pa.sf_bs = o.sf_bs;
+        pa.Ft = OFFS(e->Ft, 2 * (m ? m : 1) * n); pa.wd = OFFS(e->wd, 2 * Tp * n); pa.w = OFFS(e->w, n); pa.ninvd = OFFS(e->ninvd, n);
+        pa.fg_out = fg; pa.fg_bs = o.fg_bs; pa.chisq_out = chisq; pa.chisq_bs = o.chisq_bs;
+        pa.lnp1 = OFFS(e->lnp1, Tp); pa.Rm = e->cfg.dense_noise ? OFFS(e->Rm, 2 * Tp * n) : nullptr;
+        pa.Empart = e->any_flagged ? OFFS(e->Empart, (size_t)e->ntilesE * n) : nullptr;
+        pa.Eupart = general ? OFFS(e->Eupart, (size_t)e->ntilesE * n) : nullptr;
+        pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc; pa.do_inverse = fused_inverse ? 1 : 0;
+        hp::launch_post_fft(pa, sb.st);
+        e->prof_end(CLS_POST, 1, sb.st);
+        if (e->cfg.dense_noise) enqueue_dense_lnp1(e, sb);
         return;
     }
     // dense fallback for Nfreqs with a large prime factor
-    e->prof_begin(CLS_POST);
+    e->prof_begin(CLS_POST, sb.st);
     hp::PostArgs pa{};
-    pa.Sf = o.sf; pa.sf_bs = o.sf_bs; pa.X = e->X; pa.Ft = e->Ft; pa.wd = e->wd; pa.w = e->w; pa.ninvd = e->ninvd;
-    pa.fg_out = o.fg; pa.fg_bs = o.fg_bs; pa.chisq_out = o.chisq; pa.chisq_bs = o.chisq_bs;
-    pa.Wm = e->any_flagged ? e->Wm : nullptr; pa.Rm = e->cfg.dense_noise ? e->Rm : nullptr; pa.lnp1 = e->lnp1;
-    pa.n = e->n; pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = e->C;
-    hp::launch_post(pa, e->st);
-    e->prof_end(CLS_POST, 1);
-    if (e->cfg.dense_noise) enqueue_dense_lnp1(e);
+    pa.Sf = sf; pa.sf_bs = o.sf_bs; pa.X = OFFS(e->X, 2 * Tp * Np); pa.Ft = OFFS(e->Ft, 2 * (m ? m : 1) * n);
+    pa.wd = OFFS(e->wd, 2 * Tp * n); pa.w = OFFS(e->w, n); pa.ninvd = OFFS(e->ninvd, n);
+    pa.fg_out = fg; pa.fg_bs = o.fg_bs; pa.chisq_out = chisq; pa.chisq_bs = o.chisq_bs;
+    pa.Wm = e->any_flagged ? OFFS(e->Wm, 2 * Tp * n) : nullptr; pa.Rm = e->cfg.dense_noise ? OFFS(e->Rm, 2 * Tp * n) : nullptr;
+    pa.lnp1 = OFFS(e->lnp1, Tp);
+    pa.n = e->n; pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc;
+    hp::launch_post(pa, sb.st);
+    e->prof_end(CLS_POST, 1, sb.st);
+    if (e->cfg.dense_noise) enqueue_dense_lnp1(e, sb);
     if (e->any_flagged || general) {
-        e->prof_begin(CLS_TRANSFORM);
+        e->prof_begin(CLS_TRANSFORM, sb.st);
         int nl2 = 0;
         hp::ZgemmArgs t{};
         t.sAi = e->n; t.sAk = 1; t.bsA = (long long)e->Tp * e->n;
         t.B = e->U; t.sBk = 1; t.sBj = e->n; t.bsB = 0;
-        t.C = e->Tmp; t.sCi = e->n; t.sCj = 1; t.bsC = (long long)e->Tp * e->n;
-        t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = e->C;
+        t.C = OFFS(e->Tmp, 2 * Tp * n); t.sCi = e->n; t.sCj = 1; t.bsC = (long long)e->Tp * e->n;
+        t.M = e->T; t.N = e->n; t.K = e->n; t.accumulate = 0; t.alpha = 1.0; t.batch = sb.nc;
         if (e->any_flagged) {
-            t.A = e->Wm;
-            hp::launch_zgemm(t, e->st);
-            hp::launch_colsumsq(e->Tmp, e->Em, e->T, e->Tp, e->n, e->C, e->st);
+            t.A = OFFS(e->Wm, 2 * Tp * n);
+            hp::launch_zgemm(t, sb.st);
+            hp::launch_colsumsq(OFFS(e->Tmp, 2 * Tp * n), OFFS(e->Em, n), e->T, e->Tp, e->n, sb.nc, sb.st);
             nl2 += 2;
         }
         if (general) {
-            t.A = o.sf; t.bsA = o.sf_bs;
-            hp::launch_zgemm(t, e->st);
-            hp::launch_colsumsq(e->Tmp, e->Eu, e->T, e->Tp, e->n, e->C, e->st);
+            t.A = sf; t.bsA = o.sf_bs;
+            hp::launch_zgemm(t, sb.st);
+            hp::launch_colsumsq(OFFS(e->Tmp, 2 * Tp * n), OFFS(e->Eu, n), e->T, e->Tp, e->n, sb.nc, sb.st);
             nl2 += 2;
         }
-        e->prof_end(CLS_TRANSFORM, nl2);
+        e->prof_end(CLS_TRANSFORM, nl2, sb.st);
+    }
+}
+
+// sub-batches of the engine: [c0, c0 + nc) on stream st (the engine's own stream when there is one range)
+static std::vector<Sub> make_subs(hp_engine* e) {
+    std::vector<Sub> v;
+    int ns = e->active_subs < (int)e->sub_st.size() ? e->active_subs : (int)e->sub_st.size();
+    if (ns <= 1) { v.push_back({0, e->C, e->st}); return v; }
+    int base = e->C / ns, rem = e->C % ns, c0 = 0;
+    for (int i = 0; i < ns; ++i) {
+        int nc = base + (i < rem ? 1 : 0);
+        if (nc > 0) v.push_back({c0, nc, e->sub_st[i]});
+        c0 += nc;
+    }
+    return v;
+}
+// fork: every sub-stream waits for what is already enqueued on the engine stream; join: the reverse
+static void fork_subs(hp_engine* e, const std::vector<Sub>& subs) {
+    if (subs.size() <= 1) return;
+    cudaEventRecord(e->fork_ev, e->st);
+    for (auto& sb : subs) cudaStreamWaitEvent(sb.st, e->fork_ev, 0);
+}
+static void join_subs(hp_engine* e, const std::vector<Sub>& subs) {
+    if (subs.size() <= 1) return;
+    for (size_t i = 0; i < subs.size(); ++i) {
+        cudaEventRecord(e->join_ev[i], subs[i].st);
+        cudaStreamWaitEvent(e->st, e->join_ev[i], 0);
     }
 }
 
@@ -620,54 +679,75 @@ int hp_engine_gcr(hp_engine* e) {
     CU_TRY(cudaSetDevice(e->cfg.device));
     Basis& b = (e->cfg.general_basis0 && e->iter == 0) ? e->b0 : e->bF;
     IterOut o{e->Sf, (long long)e->Tp * e->n, nullptr, 0, nullptr, 0};
-    enqueue_gcr(e, b, o);
+    const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
+    const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
+    auto subs = make_subs(e);
+    fork_subs(e, subs);
+    for (auto& sb : subs) enqueue_gcr(e, b, o, sb, draw_iter);
+    join_subs(e, subs);
     CU_TRY(cudaGetLastError());
     return HP_OK;
 }
 
 // one Gibbs iteration of all chains (gibbs_step_fgmodes, pspec.py:377-490), enqueued on e->st
-static void enqueue_iteration(hp_engine* e) {
-    const size_t n = e->n, m = e->m, T = e->T, Tp = e->Tp, I = e->cfg.max_iters;
+// one Gibbs iteration (gibbs_step_fgmodes, pspec.py:377-490) of the chains of one sub-batch
+static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t iter, uint32_t draw_iter, bool general) {
+    const size_t n = e->n, m = e->m, T = e->T, Tp = e->Tp, I = e->cfg.max_iters, Np = e->Np;
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
-    {
-        const int it = e->out_pos;
-        const bool general = e->cfg.general_basis0 && e->iter == 0;
-        Basis& b = general ? e->b0 : e->bF;
-        IterOut o{};
-        o.sf = e->cr_out ? e->cr_out + 2 * (size_t)it * T * n : e->Sf;
-        o.sf_bs = e->cr_out ? (long long)(I * T * n) : (long long)(Tp * n);
-        o.fg = e->fg_out ? e->fg_out + 2 * (size_t)it * T * m : nullptr; o.fg_bs = 2 * (long long)(I * T * m);
-        o.chisq = e->chisq_out ? e->chisq_out + (size_t)it * T * n : nullptr; o.chisq_bs = (long long)(I * T * n);
-        enqueue_gcr(e, b, o);
+    Basis& b = general ? e->b0 : e->bF;
+    IterOut o{};
+    o.sf = e->cr_out ? e->cr_out + 2 * (size_t)it * T * n : e->Sf;
+    o.sf_bs = e->cr_out ? (long long)(I * T * n) : (long long)(Tp * n);
+    o.fg = e->fg_out ? e->fg_out + 2 * (size_t)it * T * m : nullptr; o.fg_bs = 2 * (long long)(I * T * m);
+    o.chisq = e->chisq_out ? e->chisq_out + (size_t)it * T * n : nullptr; o.chisq_bs = (long long)(I * T * n);
+    enqueue_gcr(e, b, o, sb, draw_iter);
 
-        e->prof_begin(CLS_SAMPLE);
-        hp::SampleArgs sp{};
-        sp.Ppart = e->Ppart;
-        sp.ntilesE = e->fft_ok ? e->ntilesE : 0;
-        sp.Eu = e->fft_ok ? e->Eupart : e->Eu;
-        sp.Em = e->any_flagged ? (e->fft_ok ? e->Empart : e->Em) : nullptr;
-        sp.lnp1 = e->lnp1; sp.lnp1_dense = nullptr; sp.prior = e->prior;
-        sp.draws = philox ? nullptr : e->sdraws + (size_t)it * n; sp.draws_bs = (long long)(I * n);
-        sp.ps = e->ps; sp.lam = e->lam;
-        sp.ps_out = e->ps_out + (size_t)it * n; sp.ps_bs = (long long)(I * n);
-        sp.lnpost_out = e->lnpost_out + it; sp.lnpost_bs = (long long)I;
-        sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = e->C;
-        sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
-        sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = (uint32_t)e->iter;
-        sp.chain_ids = nullptr;
-        hp::launch_sample(sp, e->st);
-        e->prof_end(CLS_SAMPLE, 1);
+    e->prof_begin(CLS_SAMPLE, sb.st);
+    hp::SampleArgs sp{};
+    sp.Ppart = OFFS(e->Ppart, (size_t)e->ntiles * n);
+    sp.ntilesE = e->fft_ok ? e->ntilesE : 0;
+    sp.Eu = e->fft_ok ? OFFS(e->Eupart, (size_t)e->ntilesE * n) : OFFS(e->Eu, n);
+    sp.Em = e->any_flagged ? (e->fft_ok ? OFFS(e->Empart, (size_t)e->ntilesE * n) : OFFS(e->Em, n)) : nullptr;
+    sp.lnp1 = OFFS(e->lnp1, Tp); sp.lnp1_dense = nullptr; sp.prior = OFFS(e->prior, 2 * n);
+    sp.draws = philox ? nullptr : OFFS(e->sdraws, I * n) + (size_t)it * n; sp.draws_bs = (long long)(I * n);
+    sp.ps = OFFS(e->ps, n); sp.lam = OFFS(e->lam, Np);
+    sp.ps_out = OFFS(e->ps_out, I * n) + (size_t)it * n; sp.ps_bs = (long long)(I * n);
+    sp.lnpost_out = OFFS(e->lnpost_out, I) + it; sp.lnpost_bs = (long long)I;
+    sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = sb.nc;
+    sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
+    sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = iter;
+    sp.chain_ids = nullptr; sp.chain0 = sb.c0;
+    hp::launch_sample(sp, sb.st);
+    e->prof_end(CLS_SAMPLE, 1, sb.st);
+}
+
+// `niter` Gibbs iterations of all chains.  Sub-batches run back to back on their own streams (no
+// synchronisation between them: chains are independent); `after_iter(k)` is called on the host right
+// after iteration k of every sub-batch has been enqueued, with the engine stream joined to it.
+extern "C++" {
+template <typename F>
+static void enqueue_iterations(hp_engine* e, int niter, F&& after_iter) {
+    const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
+    auto subs = make_subs(e);
+    fork_subs(e, subs);
+    for (int k = 0; k < niter; ++k) {
+        const bool general = e->cfg.general_basis0 && e->iter == 0;
+        const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
+        for (auto& sb : subs) enqueue_iteration_sub(e, sb, e->out_pos, (uint32_t)e->iter, draw_iter, general);
         e->iter++;
         e->out_pos++;
+        if (after_iter(k)) { join_subs(e, subs); after_iter(-1 - k); if (k + 1 < niter) fork_subs(e, subs); }
     }
+    join_subs(e, subs);
 }
+}  // extern "C++"
 
 int hp_engine_run(hp_engine* e, int niter) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
     if (niter < 0 || e->out_pos + niter > e->cfg.max_iters)
         return fail(HP_ERR_ARG, "hp_engine_run: would exceed max_iters (use hp_engine_rewind)");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    for (int k = 0; k < niter; ++k) enqueue_iteration(e);
+    enqueue_iterations(e, niter, [](int) { return false; });
     CU_TRY(cudaGetLastError());
     return HP_OK;
 }
@@ -683,26 +763,36 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
     const size_t n = e->n, m = e->m, T = e->T, I = e->cfg.max_iters, HI = sink->iters;
     const int first = e->out_pos;
     std::vector<cudaEvent_t> evs;
-    for (int k = 0; k < niter; ++k) {
-        const size_t it = e->out_pos;
-        enqueue_iteration(e);
+    cudaError_t cerr = cudaSuccess;
+    enqueue_iterations(e, niter, [&](int k) -> bool {
+        if (k >= 0) return true;  // ask for a join after every iteration, then get called back with -1 - k
+        const size_t it = (size_t)e->out_pos - 1;
+        cudaEvent_t ev;
+        if ((cerr = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return false;
+        evs.push_back(ev);
+        cudaEventRecord(ev, e->st);
+        cudaStreamWaitEvent(e->copy_st, ev, 0);
+        // this iteration's big arrays leave over PCIe while the next iteration computes
+        for (size_t c = 0; c < (size_t)e->C && cerr == cudaSuccess; ++c) {
+            if (sink->signal_cr)
+                cerr = cudaMemcpyAsync(sink->signal_cr + 2 * ((c * HI + it) * T * n), e->cr_out + 2 * ((c * I + it) * T * n),
+                                       T * n * 16, cudaMemcpyDeviceToHost, e->copy_st);
+            if (sink->fg_amps && m && cerr == cudaSuccess)
+                cerr = cudaMemcpyAsync(sink->fg_amps + 2 * ((c * HI + it) * T * m), e->fg_out + 2 * ((c * I + it) * T * m),
+                                       T * m * 16, cudaMemcpyDeviceToHost, e->copy_st);
+            if (sink->chisq && cerr == cudaSuccess)
+                cerr = cudaMemcpyAsync(sink->chisq + (c * HI + it) * T * n, e->chisq_out + (c * I + it) * T * n, T * n * 8,
+                                       cudaMemcpyDeviceToHost, e->copy_st);
+        }
+        return false;
+    });
+    if (cerr != cudaSuccess) return fail(HP_ERR_CUDA, std::string("hp_engine_run_to_host: ") + cudaGetErrorString(cerr));
+    {
         cudaEvent_t ev;
         CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         evs.push_back(ev);
         CU_TRY(cudaEventRecord(ev, e->st));
         CU_TRY(cudaStreamWaitEvent(e->copy_st, ev, 0));
-        // this iteration's big arrays leave over PCIe while the next iteration computes
-        for (size_t c = 0; c < (size_t)e->C; ++c) {
-            if (sink->signal_cr)
-                CU_TRY(cudaMemcpyAsync(sink->signal_cr + 2 * ((c * HI + it) * T * n), e->cr_out + 2 * ((c * I + it) * T * n),
-                                       T * n * 16, cudaMemcpyDeviceToHost, e->copy_st));
-            if (sink->fg_amps && m)
-                CU_TRY(cudaMemcpyAsync(sink->fg_amps + 2 * ((c * HI + it) * T * m), e->fg_out + 2 * ((c * I + it) * T * m),
-                                       T * m * 16, cudaMemcpyDeviceToHost, e->copy_st));
-            if (sink->chisq)
-                CU_TRY(cudaMemcpyAsync(sink->chisq + (c * HI + it) * T * n, e->chisq_out + (c * I + it) * T * n, T * n * 8,
-                                       cudaMemcpyDeviceToHost, e->copy_st));
-        }
     }
     if (niter > 0) {
         for (size_t c = 0; c < (size_t)e->C; ++c) {
@@ -717,6 +807,12 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
     CU_TRY(cudaStreamSynchronize(e->copy_st));
     for (auto ev : evs) cudaEventDestroy(ev);
     CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_engine_set_substreams(hp_engine* e, int n) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    e->active_subs = n < 1 ? 1 : n;
     return HP_OK;
 }
 

@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(1024) k_sample(SampleArgs a) {
     const double* prior = a.prior + (size_t)sys * 2 * n;
     const double* draws = a.draws ? a.draws + (size_t)sys * a.draws_bs : nullptr;
     const double alpha = (double)a.T - 1.0;  // pspec.py:108
-    const uint32_t chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)sys;
+    const uint32_t chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)(a.chain0 + sys);
 
     double lp2 = 0.0;  // sum_k E_k / Lambda'_k
     for (int k0 = 0; k0 < n; k0 += 1024) {

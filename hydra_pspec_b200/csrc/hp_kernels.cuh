@@ -73,7 +73,8 @@ struct SolveArgs {
     int rows_per_round;    // times staged through the ring area per round (set by launch_solve)
     int cg_compat;         // 1: scale each column by the scalar CG model (hp_math.h:cg_theta)
     uint32_t key0, key1, iter;
-    const int* chain_ids;  // [nsys] global chain id for the philox counter (or null -> sys index)
+    const int* chain_ids;  // [nsys] global chain id for the philox counter (or null -> chain0 + sys index)
+    int chain0;
 };
 void launch_solve(const SolveArgs& a, cudaStream_t st);
 size_t solve_smem_bytes(int nblk);
@@ -116,6 +117,7 @@ struct SampleArgs {
     int ntilesE;           // > 0: Em / Eu are per-tile partial sums [nsys][ntilesE][n]
     uint32_t key0, key1, iter;
     const int* chain_ids;
+    int chain0;
     long long ps_bs, lnpost_bs, draws_bs;
 };
 void launch_sample(const SampleArgs& a, cudaStream_t st);

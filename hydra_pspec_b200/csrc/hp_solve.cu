@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     rc.Rfix = a.Rfix + 2 * (size_t)sys * a.Tp * Np;
     rc.wa = a.wa ? a.wa + 2 * (size_t)sys * a.Tp * Np : nullptr;
     rc.lam = lam; rc.Np = Np; rc.n = a.n; rc.N = a.N; rc.T = a.T; rc.t0 = tile * kTT;
-    const uint32_t chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)sys;
+    const uint32_t chain = a.chain_ids ? (uint32_t)a.chain_ids[sys] : (uint32_t)(a.chain0 + sys);
     const int g = lane >> 2, q = lane & 3;
     // Warp tile: rows 8 ti.., columns 8 tj...  The two column groups (tj = 0, 1) never touch each
     // other's columns; they share only the ring.

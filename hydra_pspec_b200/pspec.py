@@ -191,7 +191,7 @@ class GibbsEngine:
 
     def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
                  refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
-                 stream=None, profile=False, force_dense_transforms=False, dense_noise=False):
+                 stream=None, profile=False, force_dense_transforms=False, dense_noise=False, substreams=1):
         self._h = None
         L = _lib.lib()
         cfg = _lib.HPConfig()
@@ -210,6 +210,7 @@ class GibbsEngine:
         cfg.profile = int(bool(profile))
         cfg.force_dense_transforms = int(bool(force_dense_transforms))
         cfg.dense_noise = int(bool(dense_noise))
+        cfg.substreams = int(substreams)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.stream = stream
         h = _lib.C.c_void_p()
@@ -309,6 +310,9 @@ class GibbsEngine:
     @property
     def launch_count(self):
         return _lib.lib().hp_engine_launch_count(self._h)
+
+    def set_substreams(self, n):
+        _lib.check(_lib.lib().hp_engine_set_substreams(self._h, int(n)))
 
     def set_profile(self, on):
         _lib.check(_lib.lib().hp_engine_set_profile(self._h, int(bool(on))))

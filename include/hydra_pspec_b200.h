@@ -59,6 +59,8 @@ typedef struct hp_config {
     int general_basis0;  /* 1: S_initial is not delay-diagonal; hp_engine_load_chain gets its
                             eigenvectors (first iteration runs in that basis) */
     int profile;         /* 1: record per-kernel CUDA-event timings (hp_engine_kernel_ms) */
+    int substreams;      /* > 1: advance the chains as this many independent sub-batches on separate streams
+                            (overlaps one sub-batch's factorisation / FFT kernels with another's solve) */
     int dense_noise;     /* 1: chains are loaded with hp_engine_load_chain_dense (non-diagonal N^-1) */
     int force_dense_transforms; /* 1: apply the Fourier operator as dense products even when Nfreqs has
                             an FFT plan (the path used for Nfreqs with a prime factor > 31); tests */
@@ -137,6 +139,8 @@ int hp_engine_info(hp_engine* e, int* info_host);
 
 /* Accumulated device time per kernel class since creation or the last call with reset=1 (needs cfg.profile). */
 int hp_engine_kernel_ms(hp_engine* e, double* ms, int* launches, int reset);
+/* Use at most n of the cfg.substreams sub-batches from now on (1 = everything on the engine stream). */
+int hp_engine_set_substreams(hp_engine* e, int n);
 /* Switch the per-kernel event timing on or off at run time. */
 int hp_engine_set_profile(hp_engine* e, int on);
 /* Total kernel launches issued by hp_engine_run / hp_engine_gcr so far. */
