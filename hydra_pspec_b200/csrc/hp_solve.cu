@@ -7,12 +7,10 @@
 //
 // CTA = (tile of 16 times, baseline).  The 16-column tile (right-hand sides, then y = W r, then
 // x = W^H y, all in place) stays in shared memory; the 32x32 blocks of W stream from L2 through a
-// ring filled by TMA bulk copies (cp.async.bulk + mbarrier, one producer warp); eight consumer
+// ring filled by TMA bulk copies (cp.async.bulk + mbarrier, one producer warp); sixteen consumer
 // warps run the block products on the FP64 tensor pipe (DMMA.8x8x4), each on an 8x8 complex tile,
 // three real products per complex one (3M scheme, see tile_mma).  In-place works because pass 1 walks the block rows downwards
-// (y_i overwrites r_i once every warp of the column group is past the diagonal block of row i) and
-// pass 2 upwards; the only synchronisation per block row is a split-phase mbarrier (arrive after
-// the diagonal block, wait before the write), which is hidden behind the rest of the row.
+// (y_i overwrites r_i after the column group's barrier that ends block row i) and pass 2 upwards.
 //
 // Right-hand sides are built on the fly (never stored):
 //     injected draws :  r = lam * Rfix + wa                      (Rfix carries B^H N^-1/2 omega_b)
@@ -31,7 +29,8 @@ namespace {
 
 constexpr int kLdX = 16;       // solution tile: 16 columns, no padding; XOR-swizzled (xs) instead
 constexpr int kMaxStages = 6;
-constexpr int kConsumers = 256;
+constexpr int kConsumers = 512;                      // 16 consumer warps: 8 tiles x 2 halves of K
+constexpr int kScratchDoubles = 2 * 8 * 32 * 3;      // [K half][tile][lane][P1..P3]: the element handed to the other half
 
 // Shared-memory index of element (row, col) of a 16-column tile.  The column is XORed with
 // 4 (row & 3): a DMMA B-fragment load (4 consecutive rows x 8 columns per half-warp pair) then
@@ -65,9 +64,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 // all eight consumer warps (the producer warp never takes part)
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
-// the four warps that own the same eight columns of the solution tile (ids 1 and 2)
-__device__ __forceinline__ void group_sync(int tj) { asm volatile("bar.sync %0, 128;" ::"r"(1 + tj) : "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
+// the eight warps that own the same eight columns of the solution tile (ids 1 and 2)
+__device__ __forceinline__ void group_sync(int tj) { asm volatile("bar.sync %0, 256;" ::"r"(1 + tj) : "memory"); }
 
 // Complex block product with three real DMMAs per k-step instead of four (the "3M" scheme of
 // zgemm3m):  P1 = Ar.Br,  P2 = Ai.Bi,  P3 = (Ar + s Ai).(Br + Bi)  with s = +1, or -1 for conj(A):
@@ -131,20 +130,22 @@ static size_t solve_smem_bytes_stages(int nblk, int stages) {
     size_t Np = (size_t)nblk * 32;
     size_t d = 2 * Np * kLdX                   // solution tile planes
              + (size_t)stages * kLBlkDoubles   // ring of W blocks (also the reduction scratch of the epilogue)
+             + 2 * kScratchDoubles             // K-half exchange buffer, double buffered by block-row parity
              + 32                              // theta
              + 2 * kMaxStages + 6;             // mbarriers
     return d * sizeof(double);
 }
 size_t solve_smem_bytes(int nblk) { return solve_smem_bytes_stages(nblk, 2); }  // minimum configuration
 
-__global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
+__global__ void __launch_bounds__(544) k_solve(SolveArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nblk = a.nblk, Np = nblk * 32;
     const int kStages = a.stages;
     double* ring = reinterpret_cast<double*>(smem_raw);          // [kStages][2304], 16-byte aligned for TMA
     double* Xr = ring + (size_t)kStages * kLBlkDoubles;
     double* Xi = Xr + (size_t)Np * kLdX;
-    double* theta = Xi + (size_t)Np * kLdX;                       // 32
+    double* scratch = Xi + (size_t)Np * kLdX;                     // 2 * kScratchDoubles (double buffered by row parity)
+    double* theta = scratch + 2 * kScratchDoubles;                // 32
     uint64_t* full = reinterpret_cast<uint64_t*>(theta + 32);     // [kMaxStages]
     uint64_t* empty = full + kMaxStages;                          // [kMaxStages]
     uint64_t* rowbar = empty + kMaxStages;                        // [2] one per column group
@@ -158,16 +159,16 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }  // a.stages <= kMaxStages
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 16); }  // a.stages <= kMaxStages
         mbar_init(&rowbar[0], 4);
         mbar_init(&rowbar[1], 4);
         mbar_init(stagebar, 1);
-        mbar_init(ringfree, 8);
+        mbar_init(ringfree, 16);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
             // The ring area first receives the tile's right-hand-side rows (Rfix[t][0..Np), one bulk copy
@@ -214,7 +215,12 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
     const int g = lane >> 2, q = lane & 3;
     // Warp tile: rows 8 ti.., columns 8 tj...  The two column groups (tj = 0, 1) never touch each
     // other's columns; they share only the ring.
-    const int ti = warp >> 1, tj = warp & 1;
+    // Sixteen warps: tile (ti, tj) of the 32 x 16 block row and K half kh (k in [16 kh, 16 kh + 16) of
+    // every block).  Two warps per tile double the warps per scheduler (the per-warp instruction stream
+    // between DMMAs, not the tensor pipe or shared-memory bandwidth, limited the 8-warp version); the two
+    // halves swap one element each at the end of a block row and finish one element apiece.
+    const int wt = warp & 7, kh = warp >> 3;
+    const int ti = wt >> 1, tj = wt & 1;
     const int bcol = (8 * tj + g) ^ (q << 2);  // this lane's B-fragment column in the swizzled tile
 
     // stage the right-hand sides:  tile[row][col] = lam_row Rfix[t0 + col][row] (+ wa).  The rows arrive
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
             par ^= 1;
             const int ncg = a.rows_per_round / 4;  // column groups in this round
             const int ngrp = (Np / 8) * ncg;
-            for (int grp = warp; grp < ngrp; grp += 8) {
+            for (int grp = warp; grp < ngrp; grp += 16) {
                 const int row = 8 * (grp / ncg) + rl, tl = 4 * (grp % ncg) + cl, col = r0 + tl;
                 double vr = 0.0, vi = 0.0;
                 if (rc.t0 + col < a.T && row < a.N) {
@@ -261,30 +267,46 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
         if (lane == 0) mbar_arrive(&empty[slot]);
         if (++slot == (uint32_t)kStages) { slot = 0; parity ^= 1; }
     };
-    uint32_t rowpar = 0;  // phase parity of this group's row barrier
+    // End of a block row: the two K halves of a tile exchange partial sums through shared memory (each
+    // hands over the element of its lane pair that the other half finishes).  The exchange buffer
+    // alternates with the row parity, so the only synchronisation is the column group's barrier between
+    // writing and reading it; that barrier also guarantees that every warp of the group is done reading
+    // block row i before it is overwritten in place (later rows of the pass never read it).
+    uint32_t rowpar = 0;
+    auto exchange = [&](double (&acc)[3][2], double (&P)[3]) {
+        double* buf = scratch + (size_t)rowpar * kScratchDoubles;
+        double* mine = buf + (((size_t)kh * 8 + wt) * 32 + lane) * 3;          // what I hand over
+        const double* theirs = buf + (((size_t)(kh ^ 1) * 8 + wt) * 32 + lane) * 3;  // what my partner hands me
+#pragma unroll
+        for (int p = 0; p < 3; ++p) mine[p] = kh ? acc[p][0] : acc[p][1];  // half 0 keeps element 0, half 1 element 1
+        group_sync(tj);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) P[p] = (kh ? acc[p][1] : acc[p][0]) + theirs[p];
+        rowpar ^= 1;
+    };
 
     // ------------------------------------------------------------------ pass 1:  y = W r (+ xi)
     for (int i = nblk - 1; i >= 0; --i) {
         double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
         {
             const double* blk = acquire();  // W_ii, lower triangular: k < 8 (ti + 1)
-            tile_mma<false>(acc, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk, Xr + (size_t)32 * i * kLdX,
-                            Xi + (size_t)32 * i * kLdX, bcol, 0, 8 * (ti + 1));
+            const int k0 = 16 * kh, k1 = min(16 * kh + 16, 8 * (ti + 1));
+            if (k0 < k1)
+                tile_mma<false>(acc, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk, Xr + (size_t)32 * i * kLdX,
+                                Xi + (size_t)32 * i * kLdX, bcol, k0, k1);
             release();
-            if (lane == 0) mbar_arrive(&rowbar[tj]);  // this warp no longer reads r_i
         }
         for (int j = i - 1; j >= 0; --j) {
             const double* blk = acquire();
             tile_mma<false>(acc, blk + 8 * ti * kLdBlk, blk + kLPlane + 8 * ti * kLdBlk, kLdBlk, Xr + (size_t)32 * j * kLdX,
-                            Xi + (size_t)32 * j * kLdX, bcol, 0, 32);
+                            Xi + (size_t)32 * j * kLdX, bcol, 16 * kh, 16 * kh + 16);
             release();
         }
-        mbar_wait(&rowbar[tj], rowpar);  // all four warps of the group are past the diagonal block
-        rowpar ^= 1;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
-            double vr = acc[0][e] - acc[1][e], vi = acc[2][e] - acc[0][e] - acc[1][e];
+        double P[3];
+        exchange(acc, P);
+        {
+            const int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + kh;
+            double vr = P[0] - P[1], vi = P[2] - P[0] - P[1];
             if (a.philox_wa && row < a.N && rc.t0 + c < a.T) {
                 // y += xi, xi ~ CN(0, 1): fluctuation term of the constrained realisation
                 u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(rc.t0 + c); ctr.z = a.iter; ctr.w = chain;
@@ -303,25 +325,25 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
         double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
         {
             const double* blk = acquire();  // W_ii^H, upper triangular: k >= 8 ti ; A element (r, k) = conj(W_ii[k][r])
-            tile_mma<true>(acc, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Xr + (size_t)32 * i * kLdX,
-                           Xi + (size_t)32 * i * kLdX, bcol, 8 * ti, 32);
+            const int k0 = max(16 * kh, 8 * ti), k1 = 16 * kh + 16;
+            if (k0 < k1)
+                tile_mma<true>(acc, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Xr + (size_t)32 * i * kLdX,
+                               Xi + (size_t)32 * i * kLdX, bcol, k0, k1);
             release();
-            if (lane == 0) mbar_arrive(&rowbar[tj]);
         }
         for (int j = i + 1; j < nblk; ++j) {
             const double* blk = acquire();  // W_ji^H
             tile_mma<true>(acc, blk + 8 * ti, blk + kLPlane + 8 * ti, kLdBlk, Xr + (size_t)32 * j * kLdX,
-                           Xi + (size_t)32 * j * kLdX, bcol, 0, 32);
+                           Xi + (size_t)32 * j * kLdX, bcol, 16 * kh, 16 * kh + 16);
             release();
         }
-        mbar_wait(&rowbar[tj], rowpar);
-        rowpar ^= 1;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + e;
+        double P[3];
+        exchange(acc, P);
+        {
+            const int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + kh;
             // conj(A) B:  re = P1 + P2, im = P3 - P1 + P2
-            Xr[xs(row, c)] = acc[0][e] + acc[1][e];
-            Xi[xs(row, c)] = acc[2][e] - acc[0][e] + acc[1][e];
+            Xr[xs(row, c)] = P[0] + P[1];
+            Xi[xs(row, c)] = P[2] - P[0] + P[1];
         }
     }
     consumer_sync();  // both column groups done; the ring is idle from here on
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
         //   weights lam^2 on the signal rows, 1 on the foreground rows ("CG model").
         int col = tid & 15, rg = tid >> 4;
         double sre = 0.0, sim = 0.0, sb = 0.0;
-        for (int row = rg; row < a.N; row += 16) {
+        for (int row = rg; row < a.N; row += kConsumers / 16) {
             double vr, vi;
             rhs_elem(rc, row, col, vr, vi);
             double w = row < a.n ? lam[row] * lam[row] : 1.0;
@@ -345,7 +367,7 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
         consumer_sync();
         if (tid < 16) {
             double cre = 0.0, cim = 0.0, b2 = 0.0;
-            for (int r2 = 0; r2 < 16; ++r2) {
+            for (int r2 = 0; r2 < kConsumers / 16; ++r2) {
                 cre += red[(r2 * 16 + tid) * 3 + 0]; cim += red[(r2 * 16 + tid) * 3 + 1]; b2 += red[(r2 * 16 + tid) * 3 + 2];
             }
             cplx c; c.re = cre; c.im = cim;
@@ -368,7 +390,7 @@ __global__ void __launch_bounds__(288) k_solve(SolveArgs a) {
         double* Sg = a.Ssc ? a.Ssc + 2 * ((size_t)sys * a.Tp + (size_t)tile * kTT) * a.n : nullptr;
         double* Pp = a.Ppart + ((size_t)sys * a.ntiles + tile) * a.n;
         const int rl = lane & 7, cl = lane >> 3;
-        for (int rg = warp; rg < Np / 8; rg += 8) {
+        for (int rg = warp; rg < Np / 8; rg += 16) {
             const int row = 8 * rg + rl;
             const double l = lam[row];
             double p = 0.0;
@@ -412,7 +434,7 @@ void launch_solve(const SolveArgs& a_in, cudaStream_t st) {
         cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_smem = smem;
     }
-    k_solve<<<dim3(a.ntiles, a.nsys), 288, smem, st>>>(a);
+    k_solve<<<dim3(a.ntiles, a.nsys), 544, smem, st>>>(a);
 }
 
 }  // namespace hp
