@@ -168,14 +168,21 @@ void launch_fill(double* p, double v, size_t count, cudaStream_t st) {
 // blocks; M is never materialised (G blocks are scaled by lam on the fly).  Off-diagonal work
 // is DMMA; the 32x32 diagonal factorisation and its triangular inverse are done by all 256
 // threads in shared memory.
+constexpr int kCT = 512;  // threads of k_chol / k_trinv: 16 warps, one 8x8 tile of a 32x32 block each
+
+// global L block -> shared memory, async, by all kCT threads
+__device__ __forceinline__ void load_block_async_ct(double* s, const double* g) {
+    for (int c = threadIdx.x; c < kLBlkDoubles / 2; c += kCT) cp_async16(s + 2 * c, g + 2 * c);
+}
+
 struct CholSmem {
-    double Ar[32 * kLdBlk], Ai[32 * kLdBlk];  // contiguous (Ar, Ai) == one padded L block
-    double Br[32 * kLdBlk], Bi[32 * kLdBlk];
-    double Vr[32 * kLdBlk], Vi[32 * kLdBlk];  // inverse of the current diagonal block
-    double redr[8 * 32], redi[8 * 32];
+    double A[2][kLBlkDoubles];   // L_ij (double buffered); A[0] also holds the block being finished
+    double B[2][kLBlkDoubles];   // L_kj (double buffered)
+    double V[kLBlkDoubles];      // inverse of the current diagonal block
+    double redr[16 * 32], redi[16 * 32];
 };
 
-__global__ void __launch_bounds__(256) k_chol(CholArgs a) {
+__global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CholSmem& s = *reinterpret_cast<CholSmem*>(smem_raw);
     const int sys = blockIdx.x;
@@ -186,93 +193,105 @@ __global__ void __launch_bounds__(256) k_chol(CholArgs a) {
     const double* lam = a.lam + (size_t)sys * Np;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int ti = warp >> 1, tj = warp & 1;  // warp tile: rows 8 ti .. +8, cols 16 tj .. +16
+    const int ti = warp >> 2, tj = warp & 3;  // warp tile: rows 8 ti .. +8, cols 8 tj .. +8
+    double* Ar = s.A[0];
+    double* Ai = s.A[0] + kLPlane;
+    double* Vr = s.V;
+    double* Vi = s.V + kLPlane;
     int bad = 0;
 
     for (int k = 0; k < nblk; ++k) {
         for (int i = k; i < nblk; ++i) {
-            double cr[1][2][2], ci[1][2][2];
-            warp_zero<1, 2>(cr, ci);
-            for (int j = 0; j < k; ++j) {
-                __syncthreads();
-                load_block_async(s.Ar, Lp + blk_index(i, j) * kLBlkDoubles);
-                if (i != k) load_block_async(s.Br, Lp + blk_index(k, j) * kLBlkDoubles);
+            double cr[1][1][2], ci[1][1][2];
+            warp_zero<1, 1>(cr, ci);
+            // acc = sum_{j<k} L_ij . L_kj^H, operand blocks double buffered through cp.async
+            if (k > 0) {
+                __syncthreads();  // buffers free (previous block finished)
+                load_block_async_ct(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
+                if (i != k) load_block_async_ct(s.B[0], Lp + blk_index(k, 0) * kLBlkDoubles);
                 cp_async_commit();
-                cp_async_wait<0>();
+            }
+            for (int j = 0; j < k; ++j) {
+                const int st = j & 1;
+                if (j + 1 < k) {
+                    load_block_async_ct(s.A[st ^ 1], Lp + blk_index(i, j + 1) * kLBlkDoubles);
+                    if (i != k) load_block_async_ct(s.B[st ^ 1], Lp + blk_index(k, j + 1) * kLBlkDoubles);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
                 __syncthreads();
-                const double* br = (i != k) ? s.Br : s.Ar;
-                const double* bi = (i != k) ? s.Bi : s.Ai;
-                // acc += L_ij . L_kj^H
-                warp_zgemm<1, 2, false, false, true, true>(cr, ci, s.Ar + 8 * ti * kLdBlk, s.Ai + 8 * ti * kLdBlk, kLdBlk,
-                                                           br + 16 * tj * kLdBlk, bi + 16 * tj * kLdBlk, kLdBlk, 32);
+                const double* ar = s.A[st];
+                const double* br = (i != k) ? s.B[st] : s.A[st];
+                warp_zgemm<1, 1, false, false, true, true>(cr, ci, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                           br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk, kLdBlk, 32);
+                __syncthreads();  // stage st may be overwritten by the load issued in the next iteration
             }
             // C = M_ik - acc, M_ik = J + lam_i G_ik lam_k
             const double* Gb = Gp + blk_index(i, k) * kBlkDoubles;
-            __syncthreads();  // all warps done with the operand buffers
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    int r = 8 * ti + g, c = 16 * tj + 8 * j + 2 * q + e;
-                    int gi = 32 * i + r, gj = 32 * k + c;
-                    double sc = lam[gi] * lam[gj];
-                    double vr = sc * Gb[r * 32 + c], vi = sc * Gb[1024 + r * 32 + c];
-                    if (gi == gj && (gi < a.n || gi >= a.N)) vr += 1.0;
-                    s.Ar[r * kLdBlk + c] = vr - cr[0][j][e];
-                    s.Ai[r * kLdBlk + c] = vi - ci[0][j][e];
-                }
+            for (int e = 0; e < 2; ++e) {
+                int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+                int gi = 32 * i + r, gj = 32 * k + c;
+                double sc = lam[gi] * lam[gj];
+                double vr = sc * Gb[r * 32 + c], vi = sc * Gb[1024 + r * 32 + c];
+                if (gi == gj && (gi < a.n || gi >= a.N)) vr += 1.0;
+                Ar[r * kLdBlk + c] = vr - cr[0][0][e];
+                Ai[r * kLdBlk + c] = vi - ci[0][0][e];
+            }
             __syncthreads();
             if (i == k) {
                 // ---- unblocked Cholesky of the 32x32 diagonal block (lower), in place
                 for (int c = 0; c < 32; ++c) {
                     if (tid < 32) {
                         int r = tid;
-                        double piv = s.Ar[c * kLdBlk + c];
+                        double piv = Ar[c * kLdBlk + c];
                         if (!(piv > 0.0)) bad = k + 1;
                         double d = sqrt(piv);
-                        if (r == c) { s.Ar[c * kLdBlk + c] = d; s.Ai[c * kLdBlk + c] = 0.0; }
-                        else if (r > c) { s.Ar[r * kLdBlk + c] /= d; s.Ai[r * kLdBlk + c] /= d; }
-                        else { s.Ar[r * kLdBlk + c] = 0.0; s.Ai[r * kLdBlk + c] = 0.0; }
+                        if (r == c) { Ar[c * kLdBlk + c] = d; Ai[c * kLdBlk + c] = 0.0; }
+                        else if (r > c) { Ar[r * kLdBlk + c] /= d; Ai[r * kLdBlk + c] /= d; }
+                        else { Ar[r * kLdBlk + c] = 0.0; Ai[r * kLdBlk + c] = 0.0; }
                     }
                     __syncthreads();
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        int e = tid + 256 * rr;
+                    for (int rr = 0; rr < 1024 / kCT; ++rr) {
+                        int e = tid + kCT * rr;
                         int r = e >> 5, c2 = e & 31;
                         if (c2 > c && r >= c2) {
-                            double xr = s.Ar[r * kLdBlk + c], xi = s.Ai[r * kLdBlk + c];
-                            double yr = s.Ar[c2 * kLdBlk + c], yi = s.Ai[c2 * kLdBlk + c];
+                            double xr = Ar[r * kLdBlk + c], xi = Ai[r * kLdBlk + c];
+                            double yr = Ar[c2 * kLdBlk + c], yi = Ai[c2 * kLdBlk + c];
                             // A[r][c2] -= x * conj(y)
-                            s.Ar[r * kLdBlk + c2] -= xr * yr + xi * yi;
-                            s.Ai[r * kLdBlk + c2] -= xi * yr - xr * yi;
+                            Ar[r * kLdBlk + c2] -= xr * yr + xi * yi;
+                            Ai[r * kLdBlk + c2] -= xi * yr - xr * yi;
                         }
                     }
                     __syncthreads();
                 }
                 // ---- V = L_kk^-1 by row recursion:  V[r][c] = -(sum_{p=c}^{r-1} L[r][p] V[p][c]) / L[r][r]
-                for (int e = tid; e < 32 * kLdBlk; e += 256) { s.Vr[e] = 0.0; s.Vi[e] = 0.0; }
+                for (int e = tid; e < kLBlkDoubles; e += kCT) s.V[e] = 0.0;
                 __syncthreads();
                 for (int r = 0; r < 32; ++r) {
                     int c = tid & 31, part = tid >> 5;
                     double sr = 0.0, si = 0.0;
-                    for (int p = c + ((part - c) & 7); p < r; p += 8) {
-                        double lr = s.Ar[r * kLdBlk + p], li = s.Ai[r * kLdBlk + p];
-                        double vr = s.Vr[p * kLdBlk + c], vi = s.Vi[p * kLdBlk + c];
+                    for (int p = c + ((part - c) & 15); p < r; p += 16) {
+                        double lr = Ar[r * kLdBlk + p], li = Ai[r * kLdBlk + p];
+                        double vr = Vr[p * kLdBlk + c], vi = Vi[p * kLdBlk + c];
                         sr += lr * vr - li * vi;
                         si += lr * vi + li * vr;
                     }
                     s.redr[part * 32 + c] = sr; s.redi[part * 32 + c] = si;
                     __syncthreads();
                     if (tid < 32) {
-                        double d = s.Ar[r * kLdBlk + r];
+                        double d = Ar[r * kLdBlk + r];
                         if (c < r) {
                             double tr = 0.0, tim = 0.0;
 #pragma unroll
-                            for (int pp = 0; pp < 8; ++pp) { tr += s.redr[pp * 32 + c]; tim += s.redi[pp * 32 + c]; }
-                            s.Vr[r * kLdBlk + c] = -tr / d;
-                            s.Vi[r * kLdBlk + c] = -tim / d;
+                            for (int pp = 0; pp < 16; ++pp) { tr += s.redr[pp * 32 + c]; tim += s.redi[pp * 32 + c]; }
+                            Vr[r * kLdBlk + c] = -tr / d;
+                            Vi[r * kLdBlk + c] = -tim / d;
                         } else if (c == r) {
-                            s.Vr[r * kLdBlk + r] = 1.0 / d;
+                            Vr[r * kLdBlk + r] = 1.0 / d;
                         }
                     }
                     __syncthreads();
@@ -280,23 +299,20 @@ __global__ void __launch_bounds__(256) k_chol(CholArgs a) {
                 // write L_kk and V to global
                 double* Lb = Lp + blk_index(k, k) * kLBlkDoubles;
                 double* Vb = Linvp + (size_t)k * kLBlkDoubles;
-                for (int e = tid; e < kLBlkDoubles; e += 256) {  // (Ar, Ai) and (Vr, Vi) are contiguous padded blocks
-                    Lb[e] = s.Ar[e];
-                    Vb[e] = s.Vr[e];
+                for (int e = tid; e < kLBlkDoubles; e += kCT) {
+                    Lb[e] = s.A[0][e];
+                    Vb[e] = s.V[e];
                 }
             } else {
                 // L_ik = C . V^H
-                double dr[1][2][2], di[1][2][2];
-                warp_zero<1, 2>(dr, di);
-                warp_zgemm<1, 2, false, false, true, true>(dr, di, s.Ar + 8 * ti * kLdBlk, s.Ai + 8 * ti * kLdBlk, kLdBlk,
-                                                           s.Vr + 16 * tj * kLdBlk, s.Vi + 16 * tj * kLdBlk, kLdBlk, 32);
+                double dr[1][1][2], di[1][1][2];
+                warp_zero<1, 1>(dr, di);
+                warp_zgemm<1, 1, false, false, true, true>(dr, di, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk,
+                                                           Vr + 8 * tj * kLdBlk, Vi + 8 * tj * kLdBlk, kLdBlk, 32);
                 double* Lb = Lp + blk_index(i, k) * kLBlkDoubles;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    int r = 8 * ti + g, c = 16 * tj + 8 * j + 2 * q;
-                    *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][j][0], dr[0][j][1]);
-                    *reinterpret_cast<double2*>(Lb + kLPlane + r * kLdBlk + c) = make_double2(di[0][j][0], di[0][j][1]);
-                }
+                int r = 8 * ti + g, c = 8 * tj + 2 * q;
+                *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
+                *reinterpret_cast<double2*>(Lb + kLPlane + r * kLdBlk + c) = make_double2(di[0][0][0], di[0][0][1]);
             }
         }
     }
@@ -310,7 +326,7 @@ void launch_chol(const CholArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
         attr_set = true;
     }
-    k_chol<<<a.nsys, 256, sizeof(CholSmem), st>>>(a);
+    k_chol<<<a.nsys, kCT, sizeof(CholSmem), st>>>(a);
 }
 
 // ==========================================================================================
@@ -320,12 +336,12 @@ void launch_chol(const CholArgs& a, cudaStream_t st) {
 // With W explicit, both triangular solves of k_solve become plain block products without any
 // dependency between block rows.
 struct TrinvSmem {
-    double A[kLBlkDoubles];   // L_ik, later the accumulated sum (as B operand)
-    double B[kLBlkDoubles];   // W_kj
-    double V[kLBlkDoubles];   // V_ii
+    double A[2][kLBlkDoubles];   // L_ik (double buffered); A[0] later holds the accumulated sum (as B operand)
+    double B[2][kLBlkDoubles];   // W_kj (double buffered)
+    double V[kLBlkDoubles];      // V_ii
 };
 
-__global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lp_all, const double* __restrict__ Linvp_all,
+__global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all, const double* __restrict__ Linvp_all,
                                                double* Wp_all, int nblk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrinvSmem& s = *reinterpret_cast<TrinvSmem*>(smem_raw);
@@ -335,47 +351,49 @@ __global__ void __launch_bounds__(256) k_trinv(const double* __restrict__ Lp_all
     double* Wp = Wp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int ti = warp >> 1, tj = warp & 1;
+    const int ti = warp >> 2, tj = warp & 3;
     // W_jj = V_jj
-    for (int e = tid; e < kLBlkDoubles; e += 256) Wp[blk_index(j, j) * kLBlkDoubles + e] = Vp[(size_t)j * kLBlkDoubles + e];
+    for (int e = tid; e < kLBlkDoubles; e += kCT) Wp[blk_index(j, j) * kLBlkDoubles + e] = Vp[(size_t)j * kLBlkDoubles + e];
     for (int i = j + 1; i < nblk; ++i) {
-        double cr[1][2][2], ci[1][2][2];
-        warp_zero<1, 2>(cr, ci);
-        for (int k = j; k < i; ++k) {
-            __syncthreads();  // previous operands consumed; W_kj written by this CTA is visible
-            load_block_async(s.A, Lp + blk_index(i, k) * kLBlkDoubles);
-            load_block_async(s.B, Wp + blk_index(k, j) * kLBlkDoubles);
-            cp_async_commit();
-            cp_async_wait<0>();
-            __syncthreads();
-            warp_zgemm<1, 2, false, false, false, false>(cr, ci, s.A + 8 * ti * kLdBlk, s.A + kLPlane + 8 * ti * kLdBlk, kLdBlk,
-                                                         s.B + 16 * tj, s.B + kLPlane + 16 * tj, kLdBlk, 32);
-        }
-        __syncthreads();
-        load_block_async(s.V, Vp + (size_t)i * kLBlkDoubles);
+        double cr[1][1][2], ci[1][1][2];
+        warp_zero<1, 1>(cr, ci);
+        __syncthreads();  // buffers free; W blocks written by this CTA so far are visible
+        load_block_async_ct(s.V, Vp + (size_t)i * kLBlkDoubles);
+        load_block_async_ct(s.A[0], Lp + blk_index(i, j) * kLBlkDoubles);
+        load_block_async_ct(s.B[0], Wp + blk_index(j, j) * kLBlkDoubles);
         cp_async_commit();
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int r = 8 * ti + g, c = 16 * tj + 8 * jj + 2 * q + e;
-                s.A[r * kLdBlk + c] = -cr[0][jj][e];
-                s.A[kLPlane + r * kLdBlk + c] = -ci[0][jj][e];
+        for (int k = j; k < i; ++k) {
+            const int st = (k - j) & 1;
+            // W_{k+1, j} was written at the end of the previous i iteration (k + 1 <= i - 1) -- visible
+            if (k + 1 < i) {
+                load_block_async_ct(s.A[st ^ 1], Lp + blk_index(i, k + 1) * kLBlkDoubles);
+                load_block_async_ct(s.B[st ^ 1], Wp + blk_index(k + 1, j) * kLBlkDoubles);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
-        cp_async_wait<0>();
-        __syncthreads();
-        double dr[1][2][2], di[1][2][2];
-        warp_zero<1, 2>(dr, di);
-        // V_ii is lower triangular: rows 8 ti.. only need k < 8 (ti + 1)
-        warp_zgemm<1, 2, false, false, false, false>(dr, di, s.V + 8 * ti * kLdBlk, s.V + kLPlane + 8 * ti * kLdBlk, kLdBlk,
-                                                     s.A + 16 * tj, s.A + kLPlane + 16 * tj, kLdBlk, 8 * (ti + 1));
-        double* Wb = Wp + blk_index(i, j) * kLBlkDoubles;
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            int r = 8 * ti + g, c = 16 * tj + 8 * jj + 2 * q;
-            *reinterpret_cast<double2*>(Wb + r * kLdBlk + c) = make_double2(dr[0][jj][0], dr[0][jj][1]);
-            *reinterpret_cast<double2*>(Wb + kLPlane + r * kLdBlk + c) = make_double2(di[0][jj][0], di[0][jj][1]);
+            __syncthreads();
+            warp_zgemm<1, 1, false, false, false, false>(cr, ci, s.A[st] + 8 * ti * kLdBlk, s.A[st] + kLPlane + 8 * ti * kLdBlk,
+                                                         kLdBlk, s.B[st] + 8 * tj, s.B[st] + kLPlane + 8 * tj, kLdBlk, 32);
+            __syncthreads();
         }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+            s.A[0][r * kLdBlk + c] = -cr[0][0][e];
+            s.A[0][kLPlane + r * kLdBlk + c] = -ci[0][0][e];
+        }
+        __syncthreads();
+        double dr[1][1][2], di[1][1][2];
+        warp_zero<1, 1>(dr, di);
+        // V_ii is lower triangular: rows 8 ti.. only need k < 8 (ti + 1)
+        warp_zgemm<1, 1, false, false, false, false>(dr, di, s.V + 8 * ti * kLdBlk, s.V + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                     s.A[0] + 8 * tj, s.A[0] + kLPlane + 8 * tj, kLdBlk, 8 * (ti + 1));
+        double* Wb = Wp + blk_index(i, j) * kLBlkDoubles;
+        int r = 8 * ti + g, c = 8 * tj + 2 * q;
+        *reinterpret_cast<double2*>(Wb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
+        *reinterpret_cast<double2*>(Wb + kLPlane + r * kLdBlk + c) = make_double2(di[0][0][0], di[0][0][1]);
     }
 }
 
@@ -385,7 +403,7 @@ void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, i
         cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrinvSmem));
         attr_set = true;
     }
-    k_trinv<<<dim3(nblk, nsys), 256, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, nblk);
+    k_trinv<<<dim3(nblk, nsys), kCT, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, nblk);
 }
 
 // ==========================================================================================
