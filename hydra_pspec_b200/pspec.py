@@ -557,3 +557,99 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
             print(f"{i + 1:<9d}{lp:<12.1f}")
         print()
     return signal_cr, signal_S, signal_ps, fg_amps, chisq, ln_post, write_time
+
+
+def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=None, keep=("cr", "fg", "chisq"),
+                       write_Niter=100, map_estimate=False, device=0, verbose=False):
+    """Advance the Gibbs chains of several baselines of identical shape together on one GPU.
+
+    This is the batched form of the reference's per-rank loop over baselines
+    (run-hydra-pspec.py:487-557): ``baselines`` is a list of dicts with the arguments of
+    :func:`gibbs_sample_with_fg` (``vis, flags, S_initial, fgmodes, Ninv, ps_prior`` and optionally
+    ``out_dir``); all chains live in one :class:`GibbsEngine` and every kernel launch covers all of
+    them.  Returns one ``gibbs_sample_with_fg``-style tuple per baseline (arrays that were not kept
+    are ``None``).  With ``rng="numpy"`` each chain gets the reference's draws for ``seed`` (every
+    baseline the same streams, as in the reference, where each chain reseeds numpy).
+    """
+    if not baselines:
+        return []
+    if map_estimate:
+        Niter = 1
+        write_Niter = 1
+    nb = len(baselines)
+    ntimes, nfreqs = np.asarray(baselines[0]["vis"]).shape
+    nmodes = np.asarray(baselines[0]["fgmodes"]).shape[1]
+    if solver is None:
+        solver = "reference-cg" if rng == "numpy" else "exact"
+    if solver not in ("reference-cg", "exact"):
+        raise ValueError("solver must be 'reference-cg' or 'exact'")
+    prep = []
+    for b in baselines:
+        vis = np.asarray(b["vis"])
+        assert vis.shape == (ntimes, nfreqs), "all baselines of a batch must have the same (Ntimes, Nfreqs)"
+        flags = np.asarray(b["flags"])
+        assert flags.shape == (nfreqs,), "`flags` array must have shape (Nfreqs,)"
+        F = np.asarray(b["fgmodes"])
+        assert F.shape == (nfreqs, nmodes), "fgmodes must have shape (Nfreqs, Nmodes)"
+        S0 = b.get("S_initial")
+        basis0, lam0sq = _analyse_signal_cov(np.eye(nfreqs) if S0 is None else S0)
+        nd, nD, nH = _noise_model(b["Ninv"], flags, nfreqs, need_sqrt=(rng == "numpy" and not map_estimate))
+        prep.append(dict(vis=vis * flags, flags=flags, F=F, basis0=basis0, lam0sq=lam0sq, nd=nd, nD=nD, nH=nH,
+                         prior=_check_prior(b.get("ps_prior"), nfreqs)))
+    general = any(p["basis0"] is not None for p in prep)
+    dense = any(p["nD"] is not None for p in prep)
+    eng = GibbsEngine(nb, ntimes, nfreqs, nmodes, Niter, rng=rng, cg_compat=(solver == "reference-cg"),
+                      refresh_omega=(rng == "philox"), keep=keep, general_basis0=general,
+                      seed=0 if seed is None else seed, device=device, force_dense_transforms=_FORCE_DENSE_TRANSFORMS,
+                      dense_noise=dense)
+    write_times = [0.0] * nb
+    try:
+        if rng == "numpy":
+            oma, omb = (None, None) if map_estimate else _reference_gcr_draws(ntimes, nfreqs)
+            if map_estimate:
+                u = np.array([np.random.uniform() for _ in range(nfreqs)])[None, :]
+            else:
+                u = np.random.RandomState(seed).uniform(size=(Niter, nfreqs))
+        for c, p in enumerate(prep):
+            b0, nD, nH = p["basis0"], p["nD"], p["nH"]
+            if general and b0 is None:
+                b0 = np.ascontiguousarray(_unitary_dft(nfreqs).conj().T)
+            if dense and nD is None:
+                nD = np.diag(p["nd"]).astype(np.complex128)
+                if rng == "numpy" and not map_estimate:
+                    nH = np.diag(np.sqrt(p["nd"] * p["flags"].astype(float))).astype(np.complex128)
+            eng.load_chain(c, p["vis"], p["flags"], p["F"], p["nd"], p["lam0sq"], ps_prior=p["prior"], basis0=b0,
+                           ninv_dense=nD, nih_dense=nH)
+            if rng == "numpy":
+                eng.set_draws(c, oma, omb, _s_draws_from_uniforms(u, p["prior"], ntimes))
+        bufs = eng.host_buffers(Niter)
+        done = 0
+        any_out = any(b.get("out_dir") is not None for b in baselines)
+        while done < Niter:
+            chunk = min(write_Niter, Niter - done) if any_out else Niter - done
+            eng.run_to_host(chunk, bufs)
+            done += chunk
+            for c, b in enumerate(baselines):
+                if b.get("out_dir") is None:
+                    continue
+                t0 = time.perf_counter()
+                z = lambda k: bufs[k][c, :done] if k in bufs else np.zeros(0)  # noqa: E731
+                utils.write_numpy_files(b["out_dir"], z("signal_cr"), eng.signal_S(c), bufs["signal_ps"][c, :done],
+                                        z("fg_amps"), z("chisq"), bufs["ln_post"][c, :done])
+                write_times[c] += time.perf_counter() - t0
+        bad = eng.info()
+        if np.any(bad != 0):
+            c = int(np.flatnonzero(bad)[0])
+            raise np.linalg.LinAlgError(f"GCR system of baseline {c} of the batch is not positive definite "
+                                        f"(Cholesky failed in block column {int(bad[c]) - 1})")
+        out = []
+        for c in range(nb):
+            g = lambda k: np.array(bufs[k][c]) if k in bufs else None  # noqa: E731
+            out.append((g("signal_cr"), eng.signal_S(c), g("signal_ps"), g("fg_amps"), g("chisq"), g("ln_post"),
+                        write_times[c]))
+    finally:
+        eng.close()
+    if verbose:
+        for c in range(nb):
+            print(f"baseline {c}: ln_post[-1] = {out[c][5][-1]:.1f}")
+    return out
