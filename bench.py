@@ -170,6 +170,11 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (hydra_pspec_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: anything libraries print at the fd level while the job runs
+    # (NCCL's "NCCL version ..." banner on a box with NCCL_DEBUG set) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     nt, nf, nm, B = args.ntimes, args.nfreq, args.nfg, args.baselines_per_gpu
@@ -317,7 +322,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(), "chol_failures": bad, "finite": finite,
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

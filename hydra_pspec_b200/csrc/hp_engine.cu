@@ -46,6 +46,33 @@ __global__ void k_mask_cols(double* A, const double* w, int rows, int n) {
     A[2 * e + 1] *= w[x];
 }
 
+// A[e] *= W[e]  (A complex, W real, same shape): per-time flags
+__global__ void k_mask_elem(double* A, const double* W, long long count) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    A[2 * e] *= W[e];
+    A[2 * e + 1] *= W[e];
+}
+// out[t][x] = W[t][x] * v[x]
+__global__ void k_rowscale(double* out, const double* W, const double* v, int rows, int n) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)rows * n) return;
+    out[e] = W[e] * v[e % n];
+}
+// Bsel[x][0] = Bmat[x][0],  Bsel[x][1 + j] = Bmat[x][n + j]
+__global__ void k_select_cols(double* Bsel, const double* Bmat, int n, int m, int Np) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * (1 + m)) return;
+    int x = (int)(e / (1 + m)), j = (int)(e % (1 + m));
+    size_t src = (size_t)x * Np + (j == 0 ? 0 : n + j - 1);
+    Bsel[2 * e] = Bmat[2 * src];
+    Bsel[2 * e + 1] = Bmat[2 * src + 1];
+}
+__global__ void k_sqrt_vec(double* out, const double* in, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = sqrt(in[k]);
+}
+
 // Bmat[x][k] (k < n) = conj(U[k][x])   (Q = U^H: delay eigenbasis of a stationary S)
 __global__ void k_basis_fourier(double* Bmat, const double* U, int n, int Np) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -148,6 +175,8 @@ struct hp_engine {
     double *lam = nullptr, *ps = nullptr;
     double *wd = nullptr, *w = nullptr, *ninvd = nullptr, *ni = nullptr, *nu = nullptr, *Ft = nullptr, *prior = nullptr;
     double *Lp = nullptr, *Linvp = nullptr, *Wp = nullptr;
+    double *wT = nullptr, *Hpt = nullptr, *niT = nullptr, *Bsel = nullptr, *ptScratch = nullptr;  // per-time flags
+    int pt_ctas = 0;
     double *NiD = nullptr, *NihD = nullptr, *Td = nullptr, *Rm = nullptr, *Yd = nullptr;  // dense (non-diagonal) noise
     int* info = nullptr;
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
@@ -267,6 +296,15 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         return fail(HP_ERR_SIZE, "Nfreqs + Nmodes = " + std::to_string(e->N) +
                                      " is too large for the shared-memory resident solve tile on this device");
     }
+    if (cfg->time_flags && (cfg->general_basis0 || cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms)) {
+        delete e;
+        return fail(HP_ERR_ARG, "per-time flags need a delay-diagonal S_initial, diagonal noise, the exact solver and an "
+                                "FFT-able Nfreqs");
+    }
+    if (cfg->time_flags && (hp::pt_smem_bytes(e->nblk, e->n) > (size_t)max_smem || !hp::make_fft_plan(e->n, &e->plan))) {
+        delete e;
+        return fail(HP_ERR_SIZE, "per-time flags: Nfreqs too large for the shared-memory working set, or without an FFT plan");
+    }
     if (cfg->stream) e->st = (cudaStream_t)cfg->stream;
     else { CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking)); e->own_stream = true; }
     const size_t C = e->C, n = e->n, m = e->m, Np = e->Np, Tp = e->Tp, T = e->T, I = cfg->max_iters;
@@ -292,6 +330,14 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->Ppart, C * e->ntiles * n); ap.want(&e->Sf, 2 * C * Tp * n);
     if (dense) { ap.want(&e->Wm, 2 * C * Tp * n); ap.want(&e->Tmp, 2 * C * Tp * n); ap.want(&e->Em, C * n); ap.want(&e->Eu, C * n); }
     ap.want(&e->lnp1, C * Tp);
+    if (cfg->time_flags) {
+        e->pt_ctas = hp::pt_grid(e->C, e->T);
+        ap.want(&e->wT, C * Tp * n);
+        ap.want(&e->Hpt, 2 * C * Tp * (1 + m) * Np);
+        ap.want(&e->niT, Tp * n);
+        ap.want(&e->Bsel, 2 * n * (1 + m));
+        ap.want(&e->ptScratch, (size_t)e->pt_ctas * hp::pt_scratch_doubles_per_cta(e->nblk));
+    }
     if (cfg->dense_noise) {
         ap.want(&e->NiD, 2 * C * n * n);
         if (cfg->rng_mode == HP_RNG_INJECTED) ap.want(&e->NihD, 2 * C * n * n);
@@ -377,9 +423,24 @@ static int build_basis_products(hp_engine* e, Basis& b, int c) {
         r.A = e->Yd + 2 * (size_t)c * e->Tp * n; r.sAi = n; r.sAk = 1;
     } else {
         r.A = e->wd + 2 * (size_t)c * e->Tp * n; r.sAi = n; r.sAk = 1; r.conjA = 0;
-        r.dk = e->ni + (size_t)c * n;
+        // wd is already masked and w^2 = w: per-time flags use the unmasked diagonal
+        r.dk = e->cfg.time_flags ? e->ninvd + (size_t)c * n : e->ni + (size_t)c * n;
     }
     hp::launch_zgemm(r, e->st);
+    if (e->cfg.time_flags) {
+        // H_t = [Q|F]^H (w_t N^-1) [q_0 | F]  for every time: column 0 is the generator chat_t of the circulant
+        // signal block, the rest are the foreground columns of G_t (hp_pertime.cu)
+        const int m = e->m;
+        k_rowscale<<<nblocks((long long)T * n), 256, 0, e->st>>>(e->niT, e->wT + (size_t)c * e->Tp * n, e->ninvd + (size_t)c * n, T, n);
+        k_select_cols<<<nblocks((long long)n * (1 + m)), 256, 0, e->st>>>(e->Bsel, Bm, n, m, Np);
+        hp::ZgemmArgs h{};
+        h.A = Bm; h.sAi = 1; h.sAk = Np; h.bsA = 0; h.conjA = 1;
+        h.B = e->Bsel; h.sBk = 1 + m; h.sBj = 1; h.bsB = 0;
+        h.C = e->Hpt + 2 * (size_t)c * e->Tp * (1 + m) * Np; h.sCi = 1; h.sCj = Np; h.bsC = (long long)(1 + m) * Np;
+        h.dk = e->niT; h.bsD = n;
+        h.M = N; h.N = 1 + m; h.K = n; h.accumulate = 0; h.alpha = 1.0; h.batch = T;
+        hp::launch_zgemm(h, e->st);
+    }
     CU_TRY(cudaGetLastError());
     return HP_OK;
 }
@@ -396,9 +457,17 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     CU_TRY(cudaSetDevice(e->cfg.device));
     const int n = e->n, m = e->m, N = e->N, Np = e->Np, T = e->T, Tp = e->Tp;
     cudaStream_t st = e->st;
+    const bool pt = e->cfg.time_flags != 0;   // flags: [Ntimes][Nfreqs]
     std::vector<double> wv(n);
+    std::vector<double> wtv(pt ? (size_t)T * n : 0);
     bool anyf = false;
-    for (int x = 0; x < n; ++x) { wv[x] = flags[x] ? 1.0 : 0.0; anyf |= !flags[x]; }
+    if (pt) {
+        for (size_t i = 0; i < (size_t)T * n; ++i) { wtv[i] = flags[i] ? 1.0 : 0.0; }
+        for (int x = 0; x < n; ++x) wv[x] = 1.0;
+        anyf = true;  // the masked-signal term of ln_post is always evaluated with the per-time mask
+    } else {
+        for (int x = 0; x < n; ++x) { wv[x] = flags[x] ? 1.0 : 0.0; anyf |= !flags[x]; }
+    }
     e->flagged[c] = anyf;
     e->any_flagged = false;
     for (auto f : e->flagged) e->any_flagged |= (f != 0);
@@ -406,8 +475,10 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     CU_TRY(cudaMemcpyAsync(e->w + (size_t)c * n, wv.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(e->ninvd + (size_t)c * n, ninv_diag, n * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(wd, vis, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));  // wv is a local
-    k_mask_cols<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->w + (size_t)c * n, T, n);
+    if (pt) CU_TRY(cudaMemcpyAsync(e->wT + (size_t)c * Tp * n, wtv.data(), (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));  // wv / wtv are locals
+    if (pt) k_mask_elem<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->wT + (size_t)c * Tp * n, (long long)T * n);
+    else k_mask_cols<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->w + (size_t)c * n, T, n);
     k_noise_vectors<<<nblocks(n), 256, 0, st>>>(e->w + (size_t)c * n, e->ninvd + (size_t)c * n, e->ni + (size_t)c * n,
                                                e->nu + (size_t)c * n, n);
     if (ps_prior) CU_TRY(cudaMemcpyAsync(e->prior + (size_t)c * 2 * n, ps_prior, 2 * n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -494,6 +565,11 @@ int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double
                 y.M = T; y.N = n; y.K = n; y.alpha = 1.0; y.batch = 1;
                 hp::launch_zgemm(y, st);
                 r.A = e->Yd + 2 * (size_t)c * Tp * n;
+            } else if (e->cfg.time_flags) {
+                // N_t^-1/2 omega_b = sqrt(N^-1) (w_t omega_b)
+                k_mask_elem<<<nblocks((long long)T * n), 256, 0, st>>>(e->stage, e->wT + (size_t)c * Tp * n, (long long)T * n);
+                k_sqrt_vec<<<nblocks(n), 256, 0, st>>>(e->vecn, e->ninvd + (size_t)c * n, n);
+                r.dk = e->vecn;
             } else {
                 r.dk = e->nu + (size_t)c * n;
             }
@@ -552,6 +628,35 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     const bool general = &b == &e->b0;
     const size_t n = e->n, m = e->m, Np = e->Np, Tp = e->Tp;
     const size_t tri = hp::tri_blocks(e->nblk);
+    const bool fused_inverse = e->fft_ok && !general;  // s = U^H (lam ytilde) inside k_post_fft
+    const bool pt = e->cfg.time_flags != 0;
+    bool any_omega = false;
+    for (auto h : e->have_omega) any_omega |= (h != 0);
+    if (pt) {
+        // one factorisation + solve per (chain, time); sub-batches share the SMs, each gets its share of the
+        // persistent grid and of the scratch slots
+        const int nsub = e->C > 0 ? (e->C + sb.nc - 1) / sb.nc : 1;
+        int grid = e->pt_ctas / (nsub > 0 ? nsub : 1);
+        if (grid < 1) grid = 1;
+        const int slot0 = (int)(((long long)sb.c0 * e->pt_ctas) / e->C);
+        if (slot0 + grid > e->pt_ctas) grid = e->pt_ctas - slot0;
+        e->prof_begin(CLS_SOLVE, sb.st);
+        cudaMemsetAsync(e->info + sb.c0, 0, sizeof(int) * sb.nc, sb.st);
+        hp::PtArgs pa{};
+        pa.H = OFFS(e->Hpt, 2 * Tp * (1 + m) * Np); pa.lam = OFFS(e->lam, Np); pa.Rfix = OFFS(b.Rfix, 2 * Tp * Np);
+        pa.wa = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
+        pa.X = OFFS(e->X, 2 * Tp * Np);
+        pa.scratch = e->ptScratch + (size_t)slot0 * hp::pt_scratch_doubles_per_cta(e->nblk);
+        pa.info = e->info + sb.c0;
+        pa.nblk = e->nblk; pa.n = e->n; pa.m = e->m; pa.N = e->N; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc;
+        pa.philox_wa = philox ? 1 : 0;
+        pa.key0 = (uint32_t)e->cfg.seed; pa.key1 = (uint32_t)(e->cfg.seed >> 32); pa.iter = draw_iter;
+        pa.chain_ids = nullptr; pa.chain0 = sb.c0;
+        hp::launch_pt_cholsolve(pa, grid, sb.st);
+        // beta partial sums: Ppart[sys][0][k] = sum_t |ytilde_k|^2
+        hp::launch_colsumsq(OFFS(e->X, 2 * Tp * Np), OFFS(e->Ppart, (size_t)e->ntiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+        e->prof_end(CLS_SOLVE, 2, sb.st);
+    } else {
     e->prof_begin(CLS_CHOL, sb.st);
     hp::CholArgs ca{};
     ca.Gp = OFFS(b.Gp, tri * hp::kBlkDoubles); ca.lam = OFFS(e->lam, Np); ca.Lp = OFFS(e->Lp, tri * hp::kLBlkDoubles);
@@ -561,13 +666,10 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), e->nblk, sb.nc, sb.st);
     e->prof_end(CLS_CHOL, 2, sb.st);
 
-    const bool fused_inverse = e->fft_ok && !general;  // s = U^H (lam ytilde) inside k_post_fft
     e->prof_begin(CLS_SOLVE, sb.st);
     hp::SolveArgs sa{};
     sa.Wp = OFFS(e->Wp, tri * hp::kLBlkDoubles); sa.lam = OFFS(e->lam, Np);
     sa.Rfix = OFFS(b.Rfix, 2 * Tp * Np);
-    bool any_omega = false;
-    for (auto h : e->have_omega) any_omega |= (h != 0);
     sa.wa = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
     sa.X = OFFS(e->X, 2 * Tp * Np); sa.Ssc = fused_inverse ? nullptr : OFFS(e->Ssc, 2 * Tp * n);
     sa.Ppart = OFFS(e->Ppart, (size_t)e->ntiles * n);
@@ -578,6 +680,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     sa.chain_ids = nullptr; sa.chain0 = sb.c0;
     hp::launch_solve(sa, sb.st);
     e->prof_end(CLS_SOLVE, 1, sb.st);
+    }
 
     double* sf = o.sf + 2 * (size_t)sb.c0 * (size_t)o.sf_bs;
     if (!fused_inverse) {
@@ -601,6 +704,8 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         hp::PostFftArgs pa{};
         pa.plan = e->plan; pa.tw = e->tw; pa.X = OFFS(e->X, 2 * Tp * Np); pa.lam = OFFS(e->lam, Np); pa.Sf = sf; pa.sf_bs = o.sf_bs;
         pa.Ft = OFFS(e->Ft, 2 * (m ? m : 1) * n); pa.wd = OFFS(e->wd, 2 * Tp * n); pa.w = OFFS(e->w, n); pa.ninvd = OFFS(e->ninvd, n);
+        pa.w_bs = e->n; pa.w_ts = 0;
+        if (pt) { pa.w = OFFS(e->wT, Tp * n); pa.w_bs = (long long)e->Tp * e->n; pa.w_ts = e->n; }
         pa.fg_out = fg; pa.fg_bs = o.fg_bs; pa.chisq_out = chisq; pa.chisq_bs = o.chisq_bs;
         pa.lnp1 = OFFS(e->lnp1, Tp); pa.Rm = e->cfg.dense_noise ? OFFS(e->Rm, 2 * Tp * n) : nullptr;
         pa.Empart = e->any_flagged ? OFFS(e->Empart, (size_t)e->ntilesE * n) : nullptr;
@@ -714,6 +819,7 @@ static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t 
     sp.ps_out = OFFS(e->ps_out, I * n) + (size_t)it * n; sp.ps_bs = (long long)(I * n);
     sp.lnpost_out = OFFS(e->lnpost_out, I) + it; sp.lnpost_bs = (long long)I;
     sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = sb.nc;
+    if (e->cfg.time_flags) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
     sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
     sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = iter;
     sp.chain_ids = nullptr; sp.chain0 = sb.c0;

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* X = a.X + 2 * ((size_t)sys * a.Tp + t0) * a.Np;
     const double* lam = a.lam + (size_t)sys * a.Np;
-    const double* w = a.w + (size_t)sys * n;
+    const double* w = a.w + (size_t)sys * a.w_bs + (size_t)t0 * a.w_ts;
     const double* nd = a.ninvd + (size_t)sys * n;
     double* Sf = a.Sf + 2 * ((size_t)sys * a.sf_bs + (size_t)t0 * n);
     const double2* twg = reinterpret_cast<const double2*>(a.tw);
@@ -265,10 +265,11 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
 #pragma unroll
         for (int t = 0; t < kTP; ++t) part[t] = 0.0;
         for (int x = tid; x < n; x += 256) {
-            const double wx = w[x], ndx = nd[x];
+            const double ndx = nd[x];
             const double2 pre = shift_pre(tw, n, x);
 #pragma unroll
             for (int t = 0; t < kTP; ++t) {
+                const double wx = (a.w_ts == 0 || t0 + t < a.T) ? w[(size_t)t * a.w_ts + x] : 0.0;
                 double2 s = sbuf[(size_t)t * n + x];
                 double2 mf = obuf[(size_t)t * n + x];
                 double2 d = make_double2(0.0, 0.0);

@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
             double cr[1][1][2], ci[1][1][2];
             warp_zero<1, 1>(cr, ci);
             // acc = sum_{j<k} L_ij . L_kj^H, operand blocks double buffered through cp.async
+            __syncthreads();  // buffers free (previous block finished: its TRSM / write-out still read A[0] and V)
             if (k > 0) {
-                __syncthreads();  // buffers free (previous block finished)
                 load_block_async_ct(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
                 if (i != k) load_block_async_ct(s.B[0], Lp + blk_index(k, 0) * kLBlkDoubles);
                 cp_async_commit();
@@ -463,14 +463,14 @@ void launch_post(const PostArgs& a, cudaStream_t st) {
 }
 
 // ==========================================================================================
-__global__ void __launch_bounds__(256) k_colsumsq(const double* A, double* out, int T, int Tp, int n) {
+__global__ void __launch_bounds__(256) k_colsumsq(const double* A, double* out, int T, int Tp, int n, int ld) {
     __shared__ double red[8][33];
     const int sys = blockIdx.y;
     const int k = blockIdx.x * 32 + (threadIdx.x & 31), tg = threadIdx.x >> 5;
     double acc = 0.0;
     if (k < n)
         for (int t = tg; t < T; t += 8) {
-            const double* p = A + 2 * (((size_t)sys * Tp + t) * n + k);
+            const double* p = A + 2 * (((size_t)sys * Tp + t) * ld + k);
             acc += p[0] * p[0] + p[1] * p[1];
         }
     red[tg][threadIdx.x & 31] = acc;
@@ -482,8 +482,8 @@ __global__ void __launch_bounds__(256) k_colsumsq(const double* A, double* out, 
         out[(size_t)sys * n + k] = s;
     }
 }
-void launch_colsumsq(const double* A, double* out, int T, int Tp, int n, int nsys, cudaStream_t st) {
-    k_colsumsq<<<dim3((n + 31) / 32, nsys), 256, 0, st>>>(A, out, T, Tp, n);
+void launch_colsumsq(const double* A, double* out, int T, int Tp, int n, int nsys, cudaStream_t st, int ld) {
+    k_colsumsq<<<dim3((n + 31) / 32, nsys), 256, 0, st>>>(A, out, T, Tp, n, ld > 0 ? ld : n);
 }
 
 // ==========================================================================================

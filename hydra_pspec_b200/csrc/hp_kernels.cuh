@@ -97,8 +97,29 @@ struct PostArgs {
 };
 void launch_post(const PostArgs& a, cudaStream_t st);
 
-// out[sys][k] = sum_t |A[sys][t][k]|^2 over t < T
-void launch_colsumsq(const double* A, double* out, int T, int Tp, int n, int nsys, cudaStream_t st);
+// out[sys][k] = sum_t |A[sys][t][k]|^2 over t < T   (rows of A are ld complex elements apart; ld = 0 -> n)
+void launch_colsumsq(const double* A, double* out, int T, int Tp, int n, int nsys, cudaStream_t st, int ld = 0);
+
+// ---- per-time flags (hp_pertime.cu): one factorisation + solve per (system, time) -------------
+struct PtArgs {
+    const double* H;       // [nsys][Tp][1 + m][Np] complex: column 0 = chat_t (first n entries), column 1 + j =
+                           //   [Q|F]^H (w_t N^-1) F[:, j]
+    const double* lam;     // [nsys][Np]
+    const double* Rfix;    // [nsys][Tp][Np] complex
+    const double* wa;      // [nsys][Tp][Np] complex or null
+    double* X;             // [nsys][Tp][Np] complex: solution [ytilde ; f]
+    double* scratch;       // [grid][pt_scratch_doubles_per_cta]: factor L and the inverses of its diagonal blocks
+    int* info;             // [nsys], zeroed by the caller; atomicMax(k + 1) on a non-positive pivot in block column k
+    int nblk, n, m, N, T, Tp, nsys;
+    int philox_wa;
+    uint32_t key0, key1, iter;
+    const int* chain_ids;
+    int chain0;
+};
+size_t pt_smem_bytes(int nblk, int n);
+size_t pt_scratch_doubles_per_cta(int nblk);
+int pt_grid(int nsys, int T);   // persistent grid: 2 CTAs per SM, at most one per (system, time) pair
+void launch_pt_cholsolve(const PtArgs& a, int grid, cudaStream_t st);
 
 struct SampleArgs {
     const double* Ppart;   // [nsys][ntiles][n]  (beta_mode 0)
@@ -138,6 +159,7 @@ struct PostFftArgs {
     long long sf_bs;
     const double* Ft;      // [nsys][m][n]
     const double* wd; const double* w; const double* ninvd;
+    long long w_bs, w_ts;  // w[sys * w_bs + t * w_ts + x]: (n, 0) time-invariant flags, (Tp n, n) per-time flags
     double* fg_out; double* chisq_out; long long fg_bs, chisq_bs;
     double* lnp1;          // [nsys][Tp]
     double* Rm;            // [nsys][Tp][n] complex or null: w * resid (dense noise: ln_post term via k_zgemm)

@@ -173,6 +173,8 @@ def _noise_model(Ninv, flags, nfreqs, need_sqrt):
         return d, None, None
     dense = np.ascontiguousarray(Ninv, dtype=np.complex128)
     nih = None
+    if np.asarray(flags).ndim == 2:
+        raise NotImplementedError("per-time flags need a diagonal Ninv")
     if need_sqrt:
         w = np.asarray(flags).astype(float)
         Ni = w[:, None] * dense * w[None, :]
@@ -191,7 +193,8 @@ class GibbsEngine:
 
     def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
                  refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
-                 stream=None, profile=False, force_dense_transforms=False, dense_noise=False, substreams=1):
+                 stream=None, profile=False, force_dense_transforms=False, dense_noise=False, substreams=1,
+                 time_flags=False):
         self._h = None
         L = _lib.lib()
         cfg = _lib.HPConfig()
@@ -211,6 +214,7 @@ class GibbsEngine:
         cfg.force_dense_transforms = int(bool(force_dense_transforms))
         cfg.dense_noise = int(bool(dense_noise))
         cfg.substreams = int(substreams)
+        cfg.time_flags = int(bool(time_flags))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.stream = stream
         h = _lib.C.c_void_p()
@@ -221,6 +225,7 @@ class GibbsEngine:
         self.rng = rng
         self.keep = tuple(keep)
         self.general_basis0 = bool(general_basis0)
+        self.time_flags = bool(time_flags)
 
     def close(self):
         if self._h is not None:
@@ -240,7 +245,10 @@ class GibbsEngine:
         vis = _lib.c128(vis)
         assert vis.shape == (T, n)
         fl = np.ascontiguousarray(np.asarray(flags).astype(np.uint8))
-        assert fl.shape == (n,), "`flags` array must have shape (Nfreqs,)"
+        if self.time_flags:
+            assert fl.shape == (T, n), "`flags` array must have shape (Ntimes, Nfreqs) in per-time mode"
+        else:
+            assert fl.shape == (n,), "`flags` array must have shape (Nfreqs,)"
         F = _lib.c128(fgmodes)
         assert F.shape == (n, m), "fgmodes must have shape (Nfreqs, Nmodes)"
         nd = _lib.f64(ninv_diag)
@@ -401,22 +409,38 @@ def build_matrices(Nparams, flags, signal_S, Ninv, fgmodes):
     return GCRMatrices(flags, signal_S, Ninv, fgmodes)
 
 
+def _check_per_time_supported(solver, basis0, ninv_dense):
+    """Per-time flags ``(Ntimes, Nfreqs)`` are an extension of the reference (it asserts 1-D flags,
+    pspec.py:428, and its driver collapses them, run-hydra-pspec.py:520-526): every time gets its own
+    factorisation (csrc/hp_pertime.cu)."""
+    if solver != "exact":
+        raise NotImplementedError("per-time flags: only solver='exact' (the reference has no per-time CG to reproduce)")
+    if basis0 is not None:
+        raise NotImplementedError("per-time flags need a delay-diagonal S_initial")
+    if ninv_dense is not None:
+        raise NotImplementedError("per-time flags need a diagonal Ninv")
+
+
 def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng, solver, map_estimate, keep,
                          seed, device, s_uniforms=None):
     """Engine with one chain loaded and (numpy mode) its draws injected."""
     vis = np.asarray(vis)
     ntimes, nfreqs = vis.shape
     nmodes = np.asarray(fgmodes).shape[1]
+    per_time = np.asarray(flags).ndim == 2
     ninv_diag, ninv_dense, nih_dense = _noise_model(Ninv, flags, nfreqs, need_sqrt=(rng == "numpy" and not map_estimate))
     basis0, lam0sq = _analyse_signal_cov(S)
     if solver is None:
-        solver = "reference-cg" if rng == "numpy" else "exact"
+        solver = "reference-cg" if (rng == "numpy" and not per_time) else "exact"
     if solver not in ("reference-cg", "exact"):
         raise ValueError("solver must be 'reference-cg' or 'exact'")
+    if per_time:
+        _check_per_time_supported(solver, basis0, ninv_dense)
     eng = GibbsEngine(1, ntimes, nfreqs, nmodes, max_iters, rng=rng, cg_compat=(solver == "reference-cg"),
                       refresh_omega=(rng == "philox"), keep=keep, general_basis0=basis0 is not None,
                       seed=0 if seed is None else seed, device=device,
-                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS, dense_noise=ninv_dense is not None)
+                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=ninv_dense is not None,
+                      time_flags=per_time)
     eng.load_chain(0, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=ps_prior, basis0=basis0, ninv_dense=ninv_dense,
                    nih_dense=nih_dense)
     if rng == "numpy":
@@ -512,7 +536,7 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
     ntimes, nfreqs = vis.shape
     flags = np.asarray(flags)
     fgmodes = np.asarray(fgmodes)
-    assert flags.shape == (nfreqs,), "`flags` array must have shape (Nfreqs,)"
+    assert flags.shape in ((nfreqs,), (ntimes, nfreqs)), "`flags` array must have shape (Nfreqs,) [or (Ntimes, Nfreqs)]"
     assert fgmodes.shape[0] == nfreqs, "fgmodes must have shape (Nfreqs, Nmodes)"
     Ninv = np.asarray(Ninv)
     if len(Ninv.shape) == 3:
@@ -579,6 +603,7 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
     nb = len(baselines)
     ntimes, nfreqs = np.asarray(baselines[0]["vis"]).shape
     nmodes = np.asarray(baselines[0]["fgmodes"]).shape[1]
+    solver_default = solver is None
     if solver is None:
         solver = "reference-cg" if rng == "numpy" else "exact"
     if solver not in ("reference-cg", "exact"):
@@ -588,7 +613,7 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
         vis = np.asarray(b["vis"])
         assert vis.shape == (ntimes, nfreqs), "all baselines of a batch must have the same (Ntimes, Nfreqs)"
         flags = np.asarray(b["flags"])
-        assert flags.shape == (nfreqs,), "`flags` array must have shape (Nfreqs,)"
+        assert flags.shape in ((nfreqs,), (ntimes, nfreqs)), "`flags` array must have shape (Nfreqs,) [or (Ntimes, Nfreqs)]"
         F = np.asarray(b["fgmodes"])
         assert F.shape == (nfreqs, nmodes), "fgmodes must have shape (Nfreqs, Nmodes)"
         S0 = b.get("S_initial")
@@ -598,10 +623,18 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
                          prior=_check_prior(b.get("ps_prior"), nfreqs)))
     general = any(p["basis0"] is not None for p in prep)
     dense = any(p["nD"] is not None for p in prep)
+    per_time = any(p["flags"].ndim == 2 for p in prep)
+    if per_time:
+        if solver_default and rng == "numpy":
+            solver = "exact"
+        _check_per_time_supported(solver, True if general else None, True if dense else None)
+        for p in prep:  # a batch is per-time as a whole
+            if p["flags"].ndim == 1:
+                p["flags"] = np.broadcast_to(p["flags"], (ntimes, nfreqs)).copy()
     eng = GibbsEngine(nb, ntimes, nfreqs, nmodes, Niter, rng=rng, cg_compat=(solver == "reference-cg"),
                       refresh_omega=(rng == "philox"), keep=keep, general_basis0=general,
-                      seed=0 if seed is None else seed, device=device, force_dense_transforms=_FORCE_DENSE_TRANSFORMS,
-                      dense_noise=dense)
+                      seed=0 if seed is None else seed, device=device,
+                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=dense, time_flags=per_time)
     write_times = [0.0] * nb
     try:
         if rng == "numpy":

@@ -64,6 +64,10 @@ typedef struct hp_config {
     int dense_noise;     /* 1: chains are loaded with hp_engine_load_chain_dense (non-diagonal N^-1) */
     int force_dense_transforms; /* 1: apply the Fourier operator as dense products even when Nfreqs has
                             an FFT plan (the path used for Nfreqs with a prime factor > 31); tests */
+    int time_flags;      /* 1: flags are per time, [Ntimes][Nfreqs] (an extension: the reference collapses them to
+                            "flagged at any time", run-hydra-pspec.py:520-526).  Every (baseline, time) pair is then
+                            factored and solved on its own (csrc/hp_pertime.cu).  Needs a delay-diagonal S_initial,
+                            diagonal noise, cg_compat = 0 */
     uint64_t seed;       /* Philox key */
     void* stream;        /* cudaStream_t to launch on, or NULL for an engine-owned stream */
 } hp_config;
@@ -78,7 +82,7 @@ int hp_engine_destroy(hp_engine* e);
 /* Load one baseline (replaces the per-baseline set-up of gibbs_sample_with_fg, pspec.py:493-599,
  * and the iteration-independent half of build_matrices, pspec.py:325-374).
  *   vis        [Ntimes][Nfreqs] complex128  visibilities (NOT pre-multiplied by the flags)
- *   flags      [Nfreqs] uint8, 1 = unflagged (pspec.py:520-522)
+ *   flags      [Nfreqs] uint8, 1 = unflagged (pspec.py:520-522); [Ntimes][Nfreqs] when cfg.time_flags = 1
  *   fgmodes    [Nfreqs][Nmodes] complex128
  *   ninv_diag  [Nfreqs] diagonal of the inverse noise covariance
  *   basis0     general_basis0 ? [Nfreqs][Nfreqs] complex128 eigenvectors (columns) of S_initial : NULL

@@ -112,3 +112,14 @@ def test_cg_theta_model(golden_dir, name):
         worst_plain = max(worst_plain, rel(xd, want[t]))
     # and the plain direct solve differs from the reference by CG's own stopping error
     assert worst_plain < 5e-8
+
+
+def test_per_time_flags_extension_matches_reference_time_by_time(golden_dir):
+    """The oracle's 2-D flag extension against the unmodified reference's gcr_fgmodes_1d called one time
+    at a time with that time's operators (tests/golden/make_golden_pertime.py)."""
+    g = np.load(golden_dir / "gcr_pertime.npz")
+    nt = g["vis"].shape[0]
+    oma, omb = ho.reference_gcr_draws(*g["vis"].shape)
+    mats = [ho.build_matrices(g["flags"][t], g["S"], g["Ninv"], g["fgmodes"]) for t in range(nt)]
+    out = ho.gcr_fgmodes(g["vis"] * g["flags"], [g["flags"][t] for t in range(nt)], mats, g["fgmodes"], oma, omb, solver="cg")
+    assert np.max(np.abs(out - g["cr"])) / np.max(np.abs(g["cr"])) < 1e-12
