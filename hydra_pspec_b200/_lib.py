@@ -20,7 +20,7 @@ class HPConfig(C.Structure):
         ("device", C.c_int), ("nchains", C.c_int), ("ntimes", C.c_int), ("nfreqs", C.c_int),
         ("nmodes", C.c_int), ("rng_mode", C.c_int), ("cg_compat", C.c_int), ("refresh_omega", C.c_int),
         ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("substreams", C.c_int), ("dense_noise", C.c_int),
-        ("force_dense_transforms", C.c_int), ("time_flags", C.c_int),
+        ("force_dense_transforms", C.c_int), ("force_dense_solve", C.c_int), ("time_flags", C.c_int),
         ("seed", C.c_uint64), ("stream", C.c_void_p),
     ]
 

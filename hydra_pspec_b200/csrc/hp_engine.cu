@@ -5,6 +5,7 @@
 // (hp_kernels.cu).  The host only enqueues launches; nothing is read back between iterations.
 #include "../../include/hydra_pspec_b200.h"
 #include "hp_kernels.cuh"
+#include "hp_math.h"
 
 #include <cmath>
 #include <cstdio>
@@ -67,6 +68,61 @@ __global__ void k_select_cols(double* Bsel, const double* Bmat, int n, int m, in
     size_t src = (size_t)x * Np + (j == 0 ? 0 : n + j - 1);
     Bsel[2 * e] = Bmat[2 * src];
     Bsel[2 * e + 1] = Bmat[2 * src + 1];
+}
+// dense Np x Np (interleaved complex, row-major) from the padded packed lower-block layout; zero above the diagonal blocks
+__global__ void k_unpack_lower(const double* Wp, double* Wd, int nblk, size_t bsP) {
+    const int Np = nblk * 32;
+    const size_t sys = blockIdx.y;
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)Np * Np) return;
+    const int i = (int)(e / Np), j = (int)(e % Np), bi = i >> 5, bj = j >> 5;
+    double re = 0.0, im = 0.0;
+    if (bj <= bi) {
+        const double* blk = Wp + sys * bsP + hp::blk_index(bi, bj) * hp::kLBlkDoubles;
+        re = blk[(i & 31) * hp::kLdBlk + (j & 31)];
+        im = blk[hp::kLPlane + (i & 31) * hp::kLdBlk + (j & 31)];
+    }
+    double* o = Wd + 2 * (sys * (size_t)Np * Np + (size_t)e);
+    o[0] = re; o[1] = im;
+}
+// r[t][row] = lam[row] Rfix[t][row] (+ wa[t][row], row < n); zero for padded times
+__global__ void k_build_rhs(double* R, const double* Rfix, const double* wa, const double* lam, int n, int Np, int T, int Tp) {
+    const size_t sys = blockIdx.y;
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)Tp * Np) return;
+    const int t = (int)(e / Np), row = (int)(e % Np);
+    const size_t off = 2 * (sys * (size_t)Tp * Np + (size_t)e);
+    double vr = 0.0, vi = 0.0;
+    if (t < T) {
+        const double l = lam[sys * Np + row];
+        vr = l * Rfix[off]; vi = l * Rfix[off + 1];
+        if (wa && row < n) { vr += wa[off]; vi += wa[off + 1]; }
+    }
+    R[off] = vr; R[off + 1] = vi;
+}
+// y += xi, xi ~ CN(0, I): same Philox counter layout as k_solve
+__global__ void k_add_noise(double* Y, int N, int Np, int T, int Tp, uint32_t key0, uint32_t key1, uint32_t iter, int chain0) {
+    const size_t sys = blockIdx.y;
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)T * Np) return;
+    const int t = (int)(e / Np), row = (int)(e % Np);
+    if (row >= N) return;
+    hp::u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)t; ctr.z = iter; ctr.w = (uint32_t)(chain0 + (int)sys);
+    double n0, n1;
+    hp::normal_pair_fast(hp::philox4x32_10(ctr, key0, key1 ^ 0xA5A5A5A5u), n0, n1);
+    double* y = Y + 2 * (sys * (size_t)Tp * Np + (size_t)e);
+    y[0] += n0 * 0.70710678118654752440; y[1] += n1 * 0.70710678118654752440;
+}
+// Ssc[t][k] = lam[k] X[t][k]  (k < n)
+__global__ void k_make_ssc(double* Ssc, const double* X, const double* lam, int n, int Np, int T, int Tp) {
+    const size_t sys = blockIdx.y;
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)T * n) return;
+    const int t = (int)(e / n), k = (int)(e % n);
+    const double l = lam[sys * Np + k];
+    const double* x = X + 2 * ((sys * (size_t)Tp + t) * Np + k);
+    double* o = Ssc + 2 * ((sys * (size_t)Tp + t) * n + k);
+    o[0] = l * x[0]; o[1] = l * x[1];
 }
 __global__ void k_sqrt_vec(double* out, const double* in, int n) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +233,8 @@ struct hp_engine {
     double *Lp = nullptr, *Linvp = nullptr, *Wp = nullptr;
     double *wT = nullptr, *Hpt = nullptr, *niT = nullptr, *Bsel = nullptr, *ptScratch = nullptr;  // per-time flags
     int pt_ctas = 0;
+    bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
+    double *Wd = nullptr, *Yb = nullptr;
     double *NiD = nullptr, *NihD = nullptr, *Td = nullptr, *Rm = nullptr, *Yd = nullptr;  // dense (non-diagonal) noise
     int* info = nullptr;
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
@@ -291,10 +349,11 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     e->Tp = e->ntiles * hp::kTT;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    if (hp::solve_smem_bytes(e->nblk) > (size_t)max_smem) {
+    e->big_solve = cfg->force_dense_solve || hp::solve_smem_bytes(e->nblk) > (size_t)max_smem;
+    if (e->big_solve && cfg->cg_compat && !cfg->time_flags) {
         delete e;
-        return fail(HP_ERR_SIZE, "Nfreqs + Nmodes = " + std::to_string(e->N) +
-                                     " is too large for the shared-memory resident solve tile on this device");
+        return fail(HP_ERR_SIZE, "Nfreqs + Nmodes = " + std::to_string(e->N) + " is too large for the shared-memory resident "
+                                 "solve tile; the dense-product solve has no cg_compat mode (use the exact solver)");
     }
     if (cfg->time_flags && (cfg->general_basis0 || cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms)) {
         delete e;
@@ -330,6 +389,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->Ppart, C * e->ntiles * n); ap.want(&e->Sf, 2 * C * Tp * n);
     if (dense) { ap.want(&e->Wm, 2 * C * Tp * n); ap.want(&e->Tmp, 2 * C * Tp * n); ap.want(&e->Em, C * n); ap.want(&e->Eu, C * n); }
     ap.want(&e->lnp1, C * Tp);
+    if (e->big_solve && !cfg->time_flags) { ap.want(&e->Wd, 2 * C * Np * Np); ap.want(&e->Yb, 2 * C * Tp * Np); }
     if (cfg->time_flags) {
         e->pt_ctas = hp::pt_grid(e->C, e->T);
         ap.want(&e->wT, C * Tp * n);
@@ -666,6 +726,46 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), e->nblk, sb.nc, sb.st);
     e->prof_end(CLS_CHOL, 2, sb.st);
 
+    if (e->big_solve) {
+        // x = W^H (W r + xi) as two dense products (W unpacked to a dense lower-triangular matrix): the path for
+        // Nfreqs + Nmodes beyond k_solve's shared-memory resident tile (BASELINE.json configs[4])
+        e->prof_begin(CLS_SOLVE, sb.st);
+        const long long NN = (long long)e->Np * e->Np, TN = (long long)e->Tp * e->Np;
+        double* Wd = OFFS(e->Wd, 2 * Np * Np);
+        double* Yb = OFFS(e->Yb, 2 * Tp * Np);
+        double* X = OFFS(e->X, 2 * Tp * Np);
+        k_unpack_lower<<<dim3(nblocks(NN), sb.nc), 256, 0, sb.st>>>(OFFS(e->Wp, tri * hp::kLBlkDoubles), Wd, e->nblk,
+                                                                   tri * hp::kLBlkDoubles);
+        k_build_rhs<<<dim3(nblocks(TN), sb.nc), 256, 0, sb.st>>>(X, OFFS(b.Rfix, 2 * Tp * Np),
+                                                                (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr,
+                                                                OFFS(e->lam, Np), e->n, e->Np, e->T, e->Tp);
+        hp::ZgemmArgs y{};   // Y[t][i] = sum_j r[t][j] W[i][j]
+        y.A = X; y.sAi = e->Np; y.sAk = 1; y.bsA = TN;
+        y.B = Wd; y.sBk = 1; y.sBj = e->Np; y.bsB = NN;
+        y.C = Yb; y.sCi = e->Np; y.sCj = 1; y.bsC = TN;
+        y.M = e->T; y.N = e->Np; y.K = e->Np; y.alpha = 1.0; y.batch = sb.nc;
+        hp::launch_zgemm(y, sb.st);
+        int nl = 4;
+        if (philox) {
+            k_add_noise<<<dim3(nblocks((long long)e->T * e->Np), sb.nc), 256, 0, sb.st>>>(
+                Yb, e->N, e->Np, e->T, e->Tp, (uint32_t)e->cfg.seed, (uint32_t)(e->cfg.seed >> 32), draw_iter, sb.c0);
+            ++nl;
+        }
+        hp::ZgemmArgs x{};   // X[t][i] = sum_j y[t][j] conj(W[j][i])
+        x.A = Yb; x.sAi = e->Np; x.sAk = 1; x.bsA = TN;
+        x.B = Wd; x.sBk = e->Np; x.sBj = 1; x.bsB = NN; x.conjB = 1;
+        x.C = X; x.sCi = e->Np; x.sCj = 1; x.bsC = TN;
+        x.M = e->T; x.N = e->Np; x.K = e->Np; x.alpha = 1.0; x.batch = sb.nc;
+        hp::launch_zgemm(x, sb.st);
+        hp::launch_colsumsq(X, OFFS(e->Ppart, (size_t)e->ntiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+        ++nl;
+        if (!fused_inverse) {
+            k_make_ssc<<<dim3(nblocks((long long)e->T * e->n), sb.nc), 256, 0, sb.st>>>(OFFS(e->Ssc, 2 * Tp * n), X, OFFS(e->lam, Np),
+                                                                                       e->n, e->Np, e->T, e->Tp);
+            ++nl;
+        }
+        e->prof_end(CLS_SOLVE, nl, sb.st);
+    } else {
     e->prof_begin(CLS_SOLVE, sb.st);
     hp::SolveArgs sa{};
     sa.Wp = OFFS(e->Wp, tri * hp::kLBlkDoubles); sa.lam = OFFS(e->lam, Np);
@@ -680,6 +780,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     sa.chain_ids = nullptr; sa.chain0 = sb.c0;
     hp::launch_solve(sa, sb.st);
     e->prof_end(CLS_SOLVE, 1, sb.st);
+    }
     }
 
     double* sf = o.sf + 2 * (size_t)sb.c0 * (size_t)o.sf_bs;
@@ -819,7 +920,7 @@ static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t 
     sp.ps_out = OFFS(e->ps_out, I * n) + (size_t)it * n; sp.ps_bs = (long long)(I * n);
     sp.lnpost_out = OFFS(e->lnpost_out, I) + it; sp.lnpost_bs = (long long)I;
     sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = sb.nc;
-    if (e->cfg.time_flags) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
+    if (e->cfg.time_flags || e->big_solve) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
     sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
     sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = iter;
     sp.chain_ids = nullptr; sp.chain0 = sb.c0;

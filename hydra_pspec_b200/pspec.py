@@ -33,6 +33,7 @@ GCR_SEED_BASE = 912983  # pspec.py:153
 # Test switch: apply the Fourier operator as dense products instead of the fused FFT kernels (the
 # path Nfreqs with a prime factor > 31 takes anyway).
 _FORCE_DENSE_TRANSFORMS = False
+_FORCE_DENSE_SOLVE = False  # tests: take the large-N dense-product solve at any size
 
 
 # --------------------------------------------------------------------------------------------
@@ -194,7 +195,7 @@ class GibbsEngine:
     def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
                  refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
                  stream=None, profile=False, force_dense_transforms=False, dense_noise=False, substreams=1,
-                 time_flags=False):
+                 time_flags=False, force_dense_solve=False):
         self._h = None
         L = _lib.lib()
         cfg = _lib.HPConfig()
@@ -215,6 +216,7 @@ class GibbsEngine:
         cfg.dense_noise = int(bool(dense_noise))
         cfg.substreams = int(substreams)
         cfg.time_flags = int(bool(time_flags))
+        cfg.force_dense_solve = int(bool(force_dense_solve or _FORCE_DENSE_SOLVE))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.stream = stream
         h = _lib.C.c_void_p()

@@ -64,6 +64,8 @@ typedef struct hp_config {
     int dense_noise;     /* 1: chains are loaded with hp_engine_load_chain_dense (non-diagonal N^-1) */
     int force_dense_transforms; /* 1: apply the Fourier operator as dense products even when Nfreqs has
                             an FFT plan (the path used for Nfreqs with a prime factor > 31); tests */
+    int force_dense_solve; /* 1: run the GCR solve as dense products with W = L^-1 even when the shared-memory
+                            resident k_solve tile fits (the path Nfreqs + Nmodes > 576 takes in any case); tests */
     int time_flags;      /* 1: flags are per time, [Ntimes][Nfreqs] (an extension: the reference collapses them to
                             "flagged at any time", run-hydra-pspec.py:520-526).  Every (baseline, time) pair is then
                             factored and solved on its own (csrc/hp_pertime.cu).  Needs a delay-diagonal S_initial,
