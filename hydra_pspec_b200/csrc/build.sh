@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 for f in hp_kernels hp_solve hp_fft hp_pertime hp_engine hp_testhooks; do
-  if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ hp_kernels.cuh -nt $f.o ] || [ hp_mma.cuh -nt $f.o ] || [ hp_math.h -nt $f.o ] || [ ../../include/hydra_pspec_b200.h -nt $f.o ]; then
+  if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ hp_kernels.cuh -nt $f.o ] || [ hp_mma.cuh -nt $f.o ] || [ hp_math.h -nt $f.o ] || [ hp_diag.cuh -nt $f.o ] || [ ../../include/hydra_pspec_b200.h -nt $f.o ]; then
     $NVCC $FLAGS -c $f.cu -o $f.o &
   fi
 done

@@ -13,6 +13,7 @@
 #include "hp_kernels.cuh"
 #include "hp_math.h"
 #include "hp_mma.cuh"
+#include "hp_diag.cuh"
 
 namespace hp {
 
@@ -242,60 +243,9 @@ __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
             }
             __syncthreads();
             if (i == k) {
-                // ---- unblocked Cholesky of the 32x32 diagonal block (lower), in place
-                for (int c = 0; c < 32; ++c) {
-                    if (tid < 32) {
-                        int r = tid;
-                        double piv = Ar[c * kLdBlk + c];
-                        if (!(piv > 0.0)) bad = k + 1;
-                        double d = sqrt(piv);
-                        if (r == c) { Ar[c * kLdBlk + c] = d; Ai[c * kLdBlk + c] = 0.0; }
-                        else if (r > c) { Ar[r * kLdBlk + c] /= d; Ai[r * kLdBlk + c] /= d; }
-                        else { Ar[r * kLdBlk + c] = 0.0; Ai[r * kLdBlk + c] = 0.0; }
-                    }
-                    __syncthreads();
-#pragma unroll
-                    for (int rr = 0; rr < 1024 / kCT; ++rr) {
-                        int e = tid + kCT * rr;
-                        int r = e >> 5, c2 = e & 31;
-                        if (c2 > c && r >= c2) {
-                            double xr = Ar[r * kLdBlk + c], xi = Ai[r * kLdBlk + c];
-                            double yr = Ar[c2 * kLdBlk + c], yi = Ai[c2 * kLdBlk + c];
-                            // A[r][c2] -= x * conj(y)
-                            Ar[r * kLdBlk + c2] -= xr * yr + xi * yi;
-                            Ai[r * kLdBlk + c2] -= xi * yr - xr * yi;
-                        }
-                    }
-                    __syncthreads();
-                }
-                // ---- V = L_kk^-1 by row recursion:  V[r][c] = -(sum_{p=c}^{r-1} L[r][p] V[p][c]) / L[r][r]
-                for (int e = tid; e < kLBlkDoubles; e += kCT) s.V[e] = 0.0;
+                // ---- Cholesky of the 32x32 diagonal block and its inverse: one warp, no block barriers
+                if (warp == 0 && diag_chol_inverse_warp(Ar, Ai, Vr, Vi)) bad = k + 1;
                 __syncthreads();
-                for (int r = 0; r < 32; ++r) {
-                    int c = tid & 31, part = tid >> 5;
-                    double sr = 0.0, si = 0.0;
-                    for (int p = c + ((part - c) & 15); p < r; p += 16) {
-                        double lr = Ar[r * kLdBlk + p], li = Ai[r * kLdBlk + p];
-                        double vr = Vr[p * kLdBlk + c], vi = Vi[p * kLdBlk + c];
-                        sr += lr * vr - li * vi;
-                        si += lr * vi + li * vr;
-                    }
-                    s.redr[part * 32 + c] = sr; s.redi[part * 32 + c] = si;
-                    __syncthreads();
-                    if (tid < 32) {
-                        double d = Ar[r * kLdBlk + r];
-                        if (c < r) {
-                            double tr = 0.0, tim = 0.0;
-#pragma unroll
-                            for (int pp = 0; pp < 16; ++pp) { tr += s.redr[pp * 32 + c]; tim += s.redi[pp * 32 + c]; }
-                            Vr[r * kLdBlk + c] = -tr / d;
-                            Vi[r * kLdBlk + c] = -tim / d;
-                        } else if (c == r) {
-                            Vr[r * kLdBlk + r] = 1.0 / d;
-                        }
-                    }
-                    __syncthreads();
-                }
                 // write L_kk and V to global
                 double* Lb = Lp + blk_index(k, k) * kLBlkDoubles;
                 double* Vb = Linvp + (size_t)k * kLBlkDoubles;

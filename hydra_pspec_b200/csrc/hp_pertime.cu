@@ -23,6 +23,7 @@
 #include "hp_kernels.cuh"
 #include "hp_math.h"
 #include "hp_mma.cuh"
+#include "hp_diag.cuh"
 
 namespace hp {
 namespace {
@@ -156,59 +157,9 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
                 }
                 __syncthreads();
                 if (i == k) {
-                    // ---- unblocked Cholesky of the 32x32 diagonal block (lower), in place
-                    for (int c = 0; c < 32; ++c) {
-                        if (tid < 32) {
-                            const int r = tid;
-                            const double piv = Ar[c * kLdBlk + c];
-                            if (!(piv > 0.0)) bad = k + 1;
-                            const double d = sqrt(piv);
-                            if (r == c) { Ar[c * kLdBlk + c] = d; Ai[c * kLdBlk + c] = 0.0; }
-                            else if (r > c) { Ar[r * kLdBlk + c] /= d; Ai[r * kLdBlk + c] /= d; }
-                            else { Ar[r * kLdBlk + c] = 0.0; Ai[r * kLdBlk + c] = 0.0; }
-                        }
-                        __syncthreads();
-#pragma unroll
-                        for (int rr = 0; rr < 1024 / kPT; ++rr) {
-                            const int e = tid + kPT * rr;
-                            const int r = e >> 5, c2 = e & 31;
-                            if (c2 > c && r >= c2) {
-                                const double xr = Ar[r * kLdBlk + c], xi = Ai[r * kLdBlk + c];
-                                const double zr = Ar[c2 * kLdBlk + c], zi = Ai[c2 * kLdBlk + c];
-                                Ar[r * kLdBlk + c2] -= xr * zr + xi * zi;
-                                Ai[r * kLdBlk + c2] -= xi * zr - xr * zi;
-                            }
-                        }
-                        __syncthreads();
-                    }
-                    // ---- V = L_kk^-1 by row recursion
-                    for (int e = tid; e < kLBlkDoubles; e += kPT) s.V[e] = 0.0;
+                    // ---- Cholesky of the 32x32 diagonal block and its inverse: one warp, no block barriers
+                    if (warp == 0 && diag_chol_inverse_warp(Ar, Ai, Vr, Vi)) bad = k + 1;
                     __syncthreads();
-                    for (int r = 0; r < 32; ++r) {
-                        const int c = tid & 31, part = tid >> 5;
-                        double sr = 0.0, si = 0.0;
-                        for (int p = c + ((part - c) & 15); p < r; p += 16) {
-                            const double lr = Ar[r * kLdBlk + p], li = Ai[r * kLdBlk + p];
-                            const double vr = Vr[p * kLdBlk + c], vi = Vi[p * kLdBlk + c];
-                            sr += lr * vr - li * vi;
-                            si += lr * vi + li * vr;
-                        }
-                        redr[part * 32 + c] = sr; redi[part * 32 + c] = si;
-                        __syncthreads();
-                        if (tid < 32) {
-                            const double d = Ar[r * kLdBlk + r];
-                            if (c < r) {
-                                double tr = 0.0, tim = 0.0;
-#pragma unroll
-                                for (int pp = 0; pp < 16; ++pp) { tr += redr[pp * 32 + c]; tim += redi[pp * 32 + c]; }
-                                Vr[r * kLdBlk + c] = -tr / d;
-                                Vi[r * kLdBlk + c] = -tim / d;
-                            } else if (c == r) {
-                                Vr[r * kLdBlk + r] = 1.0 / d;
-                            }
-                        }
-                        __syncthreads();
-                    }
                     // ---- y_k = V (r_k - sum_{j<k} L_kj y_j)
                     for (int o = 8; o > 0; o >>= 1) {
                         fr += __shfl_xor_sync(0xffffffffu, fr, o);

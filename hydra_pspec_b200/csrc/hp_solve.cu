@@ -288,6 +288,18 @@ __global__ void __launch_bounds__(544) k_solve(SolveArgs a) {
     // ------------------------------------------------------------------ pass 1:  y = W r (+ xi)
     for (int i = nblk - 1; i >= 0; --i) {
         double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+        // The fluctuation draw of the element this thread finishes does not depend on the products: issue it
+        // first, so that its integer / MUFU instructions fill the issue slots between this row's DMMAs instead
+        // of running after the row's barrier with the tensor pipe idle.
+        double xi0 = 0.0, xi1 = 0.0;
+        {
+            const int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + kh;
+            if (a.philox_wa && row < a.N && rc.t0 + c < a.T) {
+                u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(rc.t0 + c); ctr.z = a.iter; ctr.w = chain;
+                normal_pair_fast(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), xi0, xi1);
+                xi0 *= 0.70710678118654752440; xi1 *= 0.70710678118654752440;
+            }
+        }
         {
             const double* blk = acquire();  // W_ii, lower triangular: k < 8 (ti + 1)
             const int k0 = 16 * kh, k1 = min(16 * kh + 16, 8 * (ti + 1));
@@ -306,14 +318,8 @@ __global__ void __launch_bounds__(544) k_solve(SolveArgs a) {
         exchange(acc, P);
         {
             const int row = 32 * i + 8 * ti + g, c = 8 * tj + 2 * q + kh;
-            double vr = P[0] - P[1], vi = P[2] - P[0] - P[1];
-            if (a.philox_wa && row < a.N && rc.t0 + c < a.T) {
-                // y += xi, xi ~ CN(0, 1): fluctuation term of the constrained realisation
-                u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(rc.t0 + c); ctr.z = a.iter; ctr.w = chain;
-                double n0, n1;
-                normal_pair_fast(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), n0, n1);
-                vr += n0 * 0.70710678118654752440; vi += n1 * 0.70710678118654752440;
-            }
+            // y += xi, xi ~ CN(0, 1): fluctuation term of the constrained realisation
+            const double vr = P[0] - P[1] + xi0, vi = P[2] - P[0] - P[1] + xi1;
             Xr[xs(row, c)] = vr;
             Xi[xs(row, c)] = vi;
         }
