@@ -36,44 +36,51 @@ __device__ double2* fft_forward(double2* src, double2* dst, int nvec, const FftP
     const int n = p.n;
     int Ns = 1;
     __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int pass = 0; pass < p.nf; ++pass) {
         const int R = p.radix[pass];
         const int nb = n / R;
         const int tstep = n / (Ns * R);
-        for (int b = threadIdx.x; b < nvec * nb; b += blockDim.x) {
-            const int v = b / nb, j = b - v * nb;
-            const int k = j % Ns;
-            const double2* s = src + (size_t)v * n + j;
-            double2* d = dst + (size_t)v * n + (j / Ns) * Ns * R + k;
-            const int tk = k * tstep;  // twiddle index step: exp(-2 pi i r k / (Ns R)) = tw[r * tk]
-            if (R == 4) {
-                double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb], a3 = s[3 * nb];
-                if (k) { a1 = cmul2(a1, tw[tk]); a2 = cmul2(a2, tw[2 * tk]); a3 = cmul2(a3, tw[3 * tk]); }
-                double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = cmul_mi(csub(a1, a3));
-                d[0] = cadd(b0, b2); d[Ns] = cadd(b1, b3); d[2 * Ns] = csub(b0, b2); d[3 * Ns] = csub(b1, b3);
-            } else if (R == 2) {
-                double2 a0 = s[0], a1 = s[nb];
-                if (k) a1 = cmul2(a1, tw[tk]);
-                d[0] = cadd(a0, a1); d[Ns] = csub(a0, a1);
-            } else if (R == 3) {
-                double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb];
-                if (k) { a1 = cmul2(a1, tw[tk]); a2 = cmul2(a2, tw[2 * tk]); }
-                const double S3 = 0.86602540378443864676;
-                double2 t1 = cadd(a1, a2), t2 = make_double2(a0.x - 0.5 * t1.x, a0.y - 0.5 * t1.y);
-                double2 t3 = make_double2(S3 * (a1.y - a2.y), -S3 * (a1.x - a2.x));  // -i sqrt(3)/2 (a1 - a2)
-                d[0] = cadd(a0, t1); d[Ns] = cadd(t2, t3); d[2 * Ns] = csub(t2, t3);
-            } else {
-                // generic radix (5, 7, 11, ...): O(R^2) with table twiddles
-                const int wstep = n / R;  // exp(-2 pi i q r / R) = tw[((q r) % R) * wstep]
-                for (int q = 0; q < R; ++q) {
-                    double2 acc = make_double2(0.0, 0.0);
-                    for (int r = 0; r < R; ++r) {
-                        double2 a = s[r * nb];
-                        int idx = r * tk + ((q * r) % R) * wstep;
-                        idx %= n;
-                        acc = cadd(acc, cmul2(a, tw[idx]));
+        const uint32_t magic = p.magic[pass];  // ceil(2^32 / Ns): j / Ns = umulhi(j, magic) for j, Ns < 2^16
+        // one warp per vector, lanes over the butterflies: no integer division in the index arithmetic
+        for (int v = warp; v < nvec; v += nwarps) {
+            const double2* sv = src + (size_t)v * n;
+            double2* dv = dst + (size_t)v * n;
+            for (int j = lane; j < nb; j += 32) {
+                const int jq = Ns > 1 ? (int)__umulhi((uint32_t)j, magic) : j;   // j / Ns
+                const int k = j - jq * Ns;                                        // j % Ns
+                const double2* s = sv + j;
+                double2* d = dv + jq * Ns * R + k;
+                const int tk = k * tstep;  // twiddle index step: exp(-2 pi i r k / (Ns R)) = tw[r * tk]
+                if (R == 4) {
+                    double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb], a3 = s[3 * nb];
+                    if (k) { a1 = cmul2(a1, tw[tk]); a2 = cmul2(a2, tw[2 * tk]); a3 = cmul2(a3, tw[3 * tk]); }
+                    double2 b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = cmul_mi(csub(a1, a3));
+                    d[0] = cadd(b0, b2); d[Ns] = cadd(b1, b3); d[2 * Ns] = csub(b0, b2); d[3 * Ns] = csub(b1, b3);
+                } else if (R == 2) {
+                    double2 a0 = s[0], a1 = s[nb];
+                    if (k) a1 = cmul2(a1, tw[tk]);
+                    d[0] = cadd(a0, a1); d[Ns] = csub(a0, a1);
+                } else if (R == 3) {
+                    double2 a0 = s[0], a1 = s[nb], a2 = s[2 * nb];
+                    if (k) { a1 = cmul2(a1, tw[tk]); a2 = cmul2(a2, tw[2 * tk]); }
+                    const double S3 = 0.86602540378443864676;
+                    double2 t1 = cadd(a1, a2), t2 = make_double2(a0.x - 0.5 * t1.x, a0.y - 0.5 * t1.y);
+                    double2 t3 = make_double2(S3 * (a1.y - a2.y), -S3 * (a1.x - a2.x));  // -i sqrt(3)/2 (a1 - a2)
+                    d[0] = cadd(a0, t1); d[Ns] = cadd(t2, t3); d[2 * Ns] = csub(t2, t3);
+                } else {
+                    // generic radix (5, 7, 11, ...): O(R^2) with table twiddles
+                    const int wstep = n / R;  // exp(-2 pi i q r / R) = tw[((q r) % R) * wstep]
+                    for (int q = 0; q < R; ++q) {
+                        double2 acc = make_double2(0.0, 0.0);
+                        for (int r = 0; r < R; ++r) {
+                            double2 a = s[r * nb];
+                            int idx = r * tk + ((q * r) % R) * wstep;
+                            idx %= n;
+                            acc = cadd(acc, cmul2(a, tw[idx]));
+                        }
+                        d[q * Ns] = acc;
                     }
-                    d[q * Ns] = acc;
                 }
             }
         }
@@ -84,8 +91,15 @@ __device__ double2* fft_forward(double2* src, double2* dst, int nvec, const FftP
     return src;
 }
 
-__device__ __forceinline__ double2 shift_pre(const double2* tw, int n, int x) {  // exp(+2 pi i h x / n)
-    return cconj(tw[(int)(((long long)(n / 2) * x) % n)]);
+// exp(+2 pi i h x / n), h = n // 2: (-1)^x for even n (no table look-up, no integer division)
+__device__ __forceinline__ double2 shift_pre(const double2* tw, int n, int x) {
+    if ((n & 1) == 0) return make_double2((x & 1) ? -1.0 : 1.0, 0.0);
+    return cconj(tw[(int)(((uint32_t)(n / 2) * (uint32_t)x) % (uint32_t)n)]);
+}
+// v * shift_pre(x)
+__device__ __forceinline__ double2 mul_shift_pre(double2 v, const double2* tw, int n, int x) {
+    if ((n & 1) == 0) return (x & 1) ? make_double2(-v.x, -v.y) : v;
+    return cmul2(v, shift_pre(tw, n, x));
 }
 
 // one warp: C (8 x 8 complex) += A (8 x K, shared, interleaved, ld in complex) . B (K x 8, global interleaved)
@@ -124,7 +138,12 @@ bool make_fft_plan(int n, FftPlan* plan) {
             plan->radix[plan->nf++] = p;
             rem /= p;
         }
-    return rem == 1 && n >= 2;
+    int Ns = 1;
+    for (int i = 0; i < plan->nf; ++i) {
+        plan->magic[i] = Ns > 1 ? (uint32_t)((0x100000000ull + (uint64_t)Ns - 1) / (uint64_t)Ns) : 0u;
+        Ns *= plan->radix[i];
+    }
+    return rem == 1 && n >= 2 && n < 65536;
 }
 
 __global__ void k_twiddles(double* tw, int n) {
@@ -164,6 +183,13 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     const double rsn = rsqrt((double)n);
     const double2 c0 = twg[(int)(((long long)(n / 2) * (n / 2)) % n)];  // exp(-2 pi i h^2 / n)
 
+    static_assert(kTP == 8, "one warp per time: 256 threads");
+    {   // the data rows are consumed last: start them on their way from DRAM to L2 now
+        const char* wdp = reinterpret_cast<const char*>(a.wd + 2 * ((size_t)sys * a.Tp + t0) * n);
+        const size_t bytes = (size_t)min(kTP, a.T - t0) * n * 16;
+        for (size_t off = (size_t)tid * 128; off < bytes; off += 256 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(wdp + off));
+    }
     for (int j = tid; j < n; j += 256) tw[j] = twg[j];
     for (int e = tid; e < kTP * ldf; e += 256) {
         int t = e / ldf, j = e - t * ldf;
@@ -176,31 +202,38 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     __syncthreads();
     double2* sbuf;
     if (a.do_inverse) {
-        // s = U^H a = conj(U conj(a)),  a = lam * ytilde
-        for (int e = tid; e < kTP * n; e += 256) {
-            int t = e / n, k = e - t * n;
-            double2 v = make_double2(0.0, 0.0);
-            if (t0 + t < a.T) {
-                v = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + k));
-                double l = lam[k];
-                v = cmul2(make_double2(l * v.x, -l * v.y), shift_pre(tw, n, k));
+        // s = U^H a = conj(U conj(a)),  a = lam * ytilde.   One warp per time (kTP == warps of the CTA).
+        {
+            const int t = warp;
+            const bool live = t0 + t < a.T;
+            for (int k = lane; k < n; k += 32) {
+                double2 v = make_double2(0.0, 0.0);
+                if (live) {
+                    v = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + k));
+                    const double l = lam[k];
+                    v = mul_shift_pre(make_double2(l * v.x, -l * v.y), tw, n, k);
+                }
+                buf0[(size_t)t * n + k] = v;
             }
-            buf0[e] = v;
         }
         double2* res = fft_forward(buf0, buf1, kTP, a.plan, tw);
-        for (int e = tid; e < kTP * n; e += 256) {
-            int t = e / n, x = e - t * n;
-            double2 post = cmul2(shift_pre(tw, n, x), c0);
-            double2 v = cconj(cmul2(res[e], post));
-            v.x *= rsn; v.y *= rsn;
-            res[e] = v;
-            if (t0 + t < a.T) *reinterpret_cast<double2*>(Sf + 2 * ((size_t)t * n + x)) = v;
+        {
+            const int t = warp;
+            const bool live = t0 + t < a.T;
+            for (int x = lane; x < n; x += 32) {
+                double2 v = cconj(cmul2(mul_shift_pre(res[(size_t)t * n + x], tw, n, x), c0));
+                v.x *= rsn; v.y *= rsn;
+                res[(size_t)t * n + x] = v;
+                if (live) *reinterpret_cast<double2*>(Sf + 2 * ((size_t)t * n + x)) = v;
+            }
         }
         sbuf = res;
     } else {
-        for (int e = tid; e < kTP * n; e += 256) {
-            int t = e / n, x = e - t * n;
-            buf0[e] = t0 + t < a.T ? *reinterpret_cast<const double2*>(Sf + 2 * ((size_t)t * n + x)) : make_double2(0.0, 0.0);
+        {
+            const int t = warp;
+            const bool live = t0 + t < a.T;
+            for (int x = lane; x < n; x += 32)
+                buf0[(size_t)t * n + x] = live ? *reinterpret_cast<const double2*>(Sf + 2 * ((size_t)t * n + x)) : make_double2(0.0, 0.0);
         }
         sbuf = buf0;
     }
@@ -266,7 +299,6 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
         for (int t = 0; t < kTP; ++t) part[t] = 0.0;
         for (int x = tid; x < n; x += 256) {
             const double ndx = nd[x];
-            const double2 pre = shift_pre(tw, n, x);
 #pragma unroll
             for (int t = 0; t < kTP; ++t) {
                 const double wx = (a.w_ts == 0 || t0 + t < a.T) ? w[(size_t)t * a.w_ts + x] : 0.0;
@@ -282,7 +314,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
                     if (a.Rm)
                         *reinterpret_cast<double2*>(a.Rm + 2 * (((size_t)sys * a.Tp + t0 + t) * n + x)) = make_double2(wx * rr, wx * ri);
                 }
-                obuf[(size_t)t * n + x] = cmul2(make_double2(wx * s.x, wx * s.y), pre);
+                obuf[(size_t)t * n + x] = mul_shift_pre(make_double2(wx * s.x, wx * s.y), tw, n, x);
             }
         }
 #pragma unroll
@@ -312,11 +344,14 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     // |U s|^2 (unmasked) for the general-basis iteration: reload s from global
     if (a.Eupart) {
         __syncthreads();
-        for (int e = tid; e < kTP * n; e += 256) {
-            int t = e / n, x = e - t * n;
-            double2 v = make_double2(0.0, 0.0);
-            if (t0 + t < a.T) v = cmul2(*reinterpret_cast<const double2*>(Sf + 2 * ((size_t)t * n + x)), shift_pre(tw, n, x));
-            buf0[e] = v;
+        {
+            const int t = warp;
+            const bool live = t0 + t < a.T;
+            for (int x = lane; x < n; x += 32) {
+                double2 v = make_double2(0.0, 0.0);
+                if (live) v = mul_shift_pre(*reinterpret_cast<const double2*>(Sf + 2 * ((size_t)t * n + x)), tw, n, x);
+                buf0[(size_t)t * n + x] = v;
+            }
         }
         double2* res = fft_forward(buf0, buf1, kTP, a.plan, tw);
         double* Ep = a.Eupart + ((size_t)sys * gridDim.x + tile) * n;

@@ -144,7 +144,7 @@ struct SampleArgs {
 void launch_sample(const SampleArgs& a, cudaStream_t st);
 
 // ---- fused FFT kernels (hp_fft.cu) ----------------------------------------------------------
-struct FftPlan { int n, nf; int radix[16]; };
+struct FftPlan { int n, nf; int radix[16]; uint32_t magic[16]; };  // magic[p] = ceil(2^32 / Ns_p)
 bool make_fft_plan(int n, FftPlan* plan);          // false: n has a prime factor > 31 (dense fallback)
 void launch_twiddles(double* tw, int n, cudaStream_t st);  // tw[j] = exp(-2 pi i j / n), interleaved
 int postfft_tiles(int T);
