@@ -236,7 +236,12 @@ def run_b200(args):
     peak = _lib.lib().hp_fp64_peak_tflops(local_rank, 0.3)
     roofline = {
         "bound": "tensor", "kernel": "k_solve", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak > 0 else None, "traffic": None,
+        "frac": achieved / peak if peak > 0 else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k_solve launch of this exact workload, from the
+        # `ncu --set full` capture summarised in profiles/r1_v5_summary.md (1.090 GB + 0.857 GB); the algorithmic
+        # bytes of a launch are Rfix in + X out + W once = 16 B * (2 T N + N^2 / 2) * B = 1.94 GB
+        "traffic": 1.947e9 if (nt, nf, nm, B) == (1024, 384, 32, 128) else None,
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
         "peak_source": "FP64 DMMA.8x8x4 issue loop measured in this run (hp_fp64_peak_tflops); "
                        "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2",
         "flops_per_launch": flops_per_launch,
@@ -244,7 +249,9 @@ def run_b200(args):
         "kernel_ms_per_step": {k: v[0] / KP for k, v in kms.items()},
         "kernel_timing": f"CUDA events around each launch, {KP} extra steps on one stream after the timed region",
     }
-    step_flops = (8.0 * N ** 3 / 3 + 8.0 * N * N * nt) * B
+    # algorithmic flops of a step: complex Cholesky N^3/6 complex MACs (= 4 N^3 / 3 real flops) + two triangular
+    # solves for T right-hand sides (N^2 T complex MACs = 8 N^2 T); the explicit W = L^-1 is an implementation choice
+    step_flops = (4.0 * N ** 3 / 3 + 8.0 * N * N * nt) * B
     roofline["step_tflops"] = step_flops * K / (ms_max * 1e-3) * 1e-12
     roofline["step_frac_of_peak"] = roofline["step_tflops"] / peak if peak > 0 else None
     try:

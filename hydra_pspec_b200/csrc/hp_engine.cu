@@ -245,7 +245,7 @@ struct hp_engine {
     void* arena = nullptr;   // one device allocation holds every buffer below
     hp::FftPlan plan{};
     bool fft_ok = false;
-    int ntilesE = 0;
+    int ntilesE = 0, ktp = 8;
     double *tw = nullptr, *Empart = nullptr, *Eupart = nullptr;
     std::vector<uint8_t> flagged;  // per chain: any channel flagged
     std::vector<uint8_t> have_omega;
@@ -360,16 +360,18 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         return fail(HP_ERR_ARG, "per-time flags need a delay-diagonal S_initial, diagonal noise, the exact solver and an "
                                 "FFT-able Nfreqs");
     }
-    if (cfg->time_flags && (hp::pt_smem_bytes(e->nblk, e->n) > (size_t)max_smem || !hp::make_fft_plan(e->n, &e->plan))) {
+    if (cfg->time_flags && (hp::pt_smem_bytes(e->nblk, e->n) > (size_t)max_smem || !hp::make_fft_plan(e->n, &e->plan) ||
+                            hp::postfft_ktp(e->n, e->m, (size_t)max_smem) == 0)) {
         delete e;
         return fail(HP_ERR_SIZE, "per-time flags: Nfreqs too large for the shared-memory working set, or without an FFT plan");
     }
     if (cfg->stream) e->st = (cudaStream_t)cfg->stream;
     else { CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking)); e->own_stream = true; }
     const size_t C = e->C, n = e->n, m = e->m, Np = e->Np, Tp = e->Tp, T = e->T, I = cfg->max_iters;
-    e->fft_ok = hp::make_fft_plan(e->n, &e->plan) && hp::postfft_smem_bytes(e->n, e->m) <= (size_t)max_smem &&
+    e->ktp = hp::postfft_ktp(e->n, e->m, (size_t)max_smem);
+    e->fft_ok = hp::make_fft_plan(e->n, &e->plan) && e->ktp > 0 &&
                 !cfg->force_dense_transforms;
-    e->ntilesE = hp::postfft_tiles(e->T);
+    e->ntilesE = hp::postfft_tiles(e->T, e->ktp > 0 ? e->ktp : 8);
     const bool dense = !e->fft_ok;                       // dense-transform scratch
     const bool need_ssc = dense || cfg->general_basis0;  // lam * ytilde as input of the dense back-transform
     ArenaPlan ap;
@@ -811,7 +813,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         pa.lnp1 = OFFS(e->lnp1, Tp); pa.Rm = e->cfg.dense_noise ? OFFS(e->Rm, 2 * Tp * n) : nullptr;
         pa.Empart = e->any_flagged ? OFFS(e->Empart, (size_t)e->ntilesE * n) : nullptr;
         pa.Eupart = general ? OFFS(e->Eupart, (size_t)e->ntilesE * n) : nullptr;
-        pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc; pa.do_inverse = fused_inverse ? 1 : 0;
+        pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc; pa.do_inverse = fused_inverse ? 1 : 0; pa.ktp = e->ktp;
         hp::launch_post_fft(pa, sb.st);
         e->prof_end(CLS_POST, 1, sb.st);
         if (e->cfg.dense_noise) enqueue_dense_lnp1(e, sb);

@@ -157,14 +157,22 @@ __global__ void k_twiddles(double* tw, int n) {
 void launch_twiddles(double* tw, int n, cudaStream_t st) { k_twiddles<<<(n + 255) / 256, 256, 0, st>>>(tw, n); }
 
 // ==========================================================================================
-constexpr int kTP = 8;  // times per CTA of the fused transform kernels
+// kTP = times per CTA of the fused transform kernel = its warp count (one warp per time): 8 normally, 4 when the
+// two ping-pong buffers of 8 times would not fit shared memory (Nfreqs = 1024)
 
-size_t postfft_smem_bytes(int n, int m) {
+size_t postfft_smem_bytes(int n, int m, int ktp) {
     int mk = ((m + 3) / 4) * 4;
-    return sizeof(double2) * ((size_t)2 * kTP * n + n + (size_t)kTP * (mk + 1)) + 64 * sizeof(double);
+    return sizeof(double2) * ((size_t)2 * ktp * n + n + (size_t)ktp * (mk + 1)) + 64 * sizeof(double);
+}
+int postfft_ktp(int n, int m, size_t max_smem) {
+    for (int ktp = 8; ktp >= 4; ktp /= 2)
+        if (postfft_smem_bytes(n, m, ktp) <= max_smem) return ktp;
+    return 0;
 }
 
-__global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
+template <int kTP>
+__global__ void __launch_bounds__(32 * kTP) k_post_fft(PostFftArgs a) {
+    constexpr int kThreads = 32 * kTP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.plan.n, m = a.m, mk = ((m + 3) / 4) * 4, ldf = mk + 1;
     double2* buf0 = reinterpret_cast<double2*>(smem_raw);
@@ -183,15 +191,14 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     const double rsn = rsqrt((double)n);
     const double2 c0 = twg[(int)(((long long)(n / 2) * (n / 2)) % n)];  // exp(-2 pi i h^2 / n)
 
-    static_assert(kTP == 8, "one warp per time: 256 threads");
     {   // the data rows are consumed last: start them on their way from DRAM to L2 now
         const char* wdp = reinterpret_cast<const char*>(a.wd + 2 * ((size_t)sys * a.Tp + t0) * n);
         const size_t bytes = (size_t)min(kTP, a.T - t0) * n * 16;
-        for (size_t off = (size_t)tid * 128; off < bytes; off += 256 * 128)
+        for (size_t off = (size_t)tid * 128; off < bytes; off += kThreads * 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(wdp + off));
     }
-    for (int j = tid; j < n; j += 256) tw[j] = twg[j];
-    for (int e = tid; e < kTP * ldf; e += 256) {
+    for (int j = tid; j < n; j += kThreads) tw[j] = twg[j];
+    for (int e = tid; e < kTP * ldf; e += kThreads) {
         int t = e / ldf, j = e - t * ldf;
         double2 v = make_double2(0.0, 0.0);
         if (j < m && t0 + t < a.T) v = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + n + j));
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
 #pragma unroll
             for (int s8 = 0; s8 < 8; ++s8) {
                 int k = kc + 4 * s8 + q;
-                af[s8] = k < mk ? fs[(size_t)g * ldf + k] : make_double2(0.0, 0.0);
+                af[s8] = (k < mk && g < kTP) ? fs[(size_t)g * ldf + k] : make_double2(0.0, 0.0);
             }
             auto load_b = [&](int ct, double2 (&b)[8]) {
                 const int x = 8 * ct + g;
@@ -264,8 +271,8 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
                 }
             };
             load_b(warp, bcur);
-            for (int ct = warp; ct < nct; ct += 8) {
-                load_b(ct + 8, bnxt);
+            for (int ct = warp; ct < nct; ct += kTP) {
+                load_b(ct + kTP, bnxt);
                 double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0}, dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0};
 #pragma unroll
                 for (int s8 = 0; s8 < 8; ++s8) {
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     int x = 8 * ct + 2 * q + e;
-                    if (x < n) {
+                    if (x < n && g < kTP) {
                         double2 v = make_double2(cr[e] - dr[e], ci[e] + di[e]);
                         if (kc) { double2 o = obuf[(size_t)g * n + x]; v.x += o.x; v.y += o.y; }
                         obuf[(size_t)g * n + x] = v;
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
             }
         }
         if (mk == 0)
-            for (int e = tid; e < kTP * n; e += 256) obuf[e] = make_double2(0.0, 0.0);
+            for (int e = tid; e < kTP * n; e += kThreads) obuf[e] = make_double2(0.0, 0.0);
     }
     __syncthreads();
     // residual, chi^2, ln-posterior partial, masked signal
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
         double part[kTP];
 #pragma unroll
         for (int t = 0; t < kTP; ++t) part[t] = 0.0;
-        for (int x = tid; x < n; x += 256) {
+        for (int x = tid; x < n; x += kThreads) {
             const double ndx = nd[x];
 #pragma unroll
             for (int t = 0; t < kTP; ++t) {
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
         __syncthreads();
         if (tid < kTP) {
             double s = 0.0;
-            for (int wv = 0; wv < 8; ++wv) s += red[wv * kTP + tid];
+            for (int wv = 0; wv < kTP; ++wv) s += red[wv * kTP + tid];
             if (t0 + tid < a.Tp) a.lnp1[(size_t)sys * a.Tp + t0 + tid] = t0 + tid < a.T ? s : 0.0;
         }
     }
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     if (a.Empart) {
         double2* res = fft_forward(obuf, sbuf, kTP, a.plan, tw);
         double* Ep = a.Empart + ((size_t)sys * gridDim.x + tile) * n;
-        for (int k = tid; k < n; k += 256) {
+        for (int k = tid; k < n; k += kThreads) {
             double acc = 0.0;
 #pragma unroll
             for (int t = 0; t < kTP; ++t) { double2 v = res[(size_t)t * n + k]; acc += v.x * v.x + v.y * v.y; }
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
         }
         double2* res = fft_forward(buf0, buf1, kTP, a.plan, tw);
         double* Ep = a.Eupart + ((size_t)sys * gridDim.x + tile) * n;
-        for (int k = tid; k < n; k += 256) {
+        for (int k = tid; k < n; k += kThreads) {
             double acc = 0.0;
 #pragma unroll
             for (int t = 0; t < kTP; ++t) { double2 v = res[(size_t)t * n + k]; acc += v.x * v.x + v.y * v.y; }
@@ -364,13 +371,18 @@ __global__ void __launch_bounds__(256) k_post_fft(PostFftArgs a) {
     }
 }
 
-int postfft_tiles(int T) { return (T + kTP - 1) / kTP; }
+int postfft_tiles(int T, int ktp) { return (T + ktp - 1) / ktp; }
 
 void launch_post_fft(const PostFftArgs& a, cudaStream_t st) {
-    size_t smem = postfft_smem_bytes(a.plan.n, a.m);
-    static size_t attr = 0;
-    if (smem > attr) { cudaFuncSetAttribute(k_post_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-    k_post_fft<<<dim3(postfft_tiles(a.T), a.nsys), 256, smem, st>>>(a);
+    const size_t smem = postfft_smem_bytes(a.plan.n, a.m, a.ktp);
+    static size_t attr8 = 0, attr4 = 0;
+    if (a.ktp == 8) {
+        if (smem > attr8) { cudaFuncSetAttribute(k_post_fft<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr8 = smem; }
+        k_post_fft<8><<<dim3(postfft_tiles(a.T, 8), a.nsys), 256, smem, st>>>(a);
+    } else {
+        if (smem > attr4) { cudaFuncSetAttribute(k_post_fft<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr4 = smem; }
+        k_post_fft<4><<<dim3(postfft_tiles(a.T, 4), a.nsys), 128, smem, st>>>(a);
+    }
 }
 
 }  // namespace hp

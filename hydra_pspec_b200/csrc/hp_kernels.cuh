@@ -147,8 +147,9 @@ void launch_sample(const SampleArgs& a, cudaStream_t st);
 struct FftPlan { int n, nf; int radix[16]; uint32_t magic[16]; };  // magic[p] = ceil(2^32 / Ns_p)
 bool make_fft_plan(int n, FftPlan* plan);          // false: n has a prime factor > 31 (dense fallback)
 void launch_twiddles(double* tw, int n, cudaStream_t st);  // tw[j] = exp(-2 pi i j / n), interleaved
-int postfft_tiles(int T);
-size_t postfft_smem_bytes(int n, int m);
+int postfft_ktp(int n, int m, size_t max_smem);   // times per CTA (8 or 4) that fit shared memory, 0 = none
+int postfft_tiles(int T, int ktp);
+size_t postfft_smem_bytes(int n, int m, int ktp);
 
 struct PostFftArgs {
     FftPlan plan;
@@ -166,6 +167,7 @@ struct PostFftArgs {
     double* Empart;        // [nsys][tiles][n] or null
     double* Eupart;        // [nsys][tiles][n] or null
     int m, Np, T, Tp, nsys, do_inverse;
+    int ktp;               // times per CTA (postfft_ktp)
 };
 void launch_post_fft(const PostFftArgs& a, cudaStream_t st);
 

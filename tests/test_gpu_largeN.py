@@ -58,9 +58,9 @@ def test_dense_product_solve_matches_oracle(nt, nf, nm, nflag, seed, dense_noise
 
 
 def test_stress_shape_1024_64_dense_noise_matches_oracle():
-    """configs[4] system size (N = 1088 > 576: no forcing needed), two times, one iteration."""
+    """configs[4] system size (N = 1088 > 576: no forcing needed), six times, one iteration."""
     from hydra_pspec_b200 import pspec
-    vis, flags, S0, F, Ninv, prior = make_case(2, 1024, 64, 7, 77, True)
+    vis, flags, S0, F, Ninv, prior = make_case(6, 1024, 64, 7, 77, True)  # 6 times: two k_post_fft<4> tiles, one partial
     want = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=1, seed=3, solver="direct", symmetric_flags=True)
     got = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=1, seed=3, verbose=False, solver="exact")
     for o, w, k in zip(got[:6], want, KEYS):
