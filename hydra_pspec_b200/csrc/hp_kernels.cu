@@ -177,10 +177,9 @@ __device__ __forceinline__ void load_block_async_ct(double* s, const double* g) 
 }
 
 struct CholSmem {
-    double A[2][kLBlkDoubles];   // L_ij (double buffered); A[0] also holds the block being finished
-    double B[2][kLBlkDoubles];   // L_kj (double buffered)
-    double V[kLBlkDoubles];      // inverse of the current diagonal block
-    double redr[16 * 32], redi[16 * 32];
+    double A[2][2 * kLBlkDoubles];   // L_ij, L_i,j+1 (double buffered, two K blocks per stage); A[0] also holds the block being finished
+    double B[2][2 * kLBlkDoubles];   // L_kj, L_k,j+1 (double buffered)
+    double V[kLBlkDoubles];          // inverse of the current diagonal block
 };
 
 __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
@@ -205,30 +204,41 @@ __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
         for (int i = k; i < nblk; ++i) {
             double cr[1][1][2], ci[1][1][2];
             warp_zero<1, 1>(cr, ci);
-            // acc = sum_{j<k} L_ij . L_kj^H, operand blocks double buffered through cp.async
-            __syncthreads();  // buffers free (previous block finished: its TRSM / write-out still read A[0] and V)
-            if (k > 0) {
-                load_block_async_ct(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
-                if (i != k) load_block_async_ct(s.B[0], Lp + blk_index(k, 0) * kLBlkDoubles);
+            double P3m[3][1][1][2];
+            warp_zero3m<1, 1>(P3m);
+            // acc = sum_{j<k} L_ij . L_kj^H.  A stage holds two consecutive K blocks of both operands (blocks j, j + 1
+            // of a block row are contiguous in the packed layout): 64 DMMAs per warp between barriers.
+            auto issue = [&](int stg, int j0) {
+                const int cnt = (k - j0 < 2 ? k - j0 : 2) * (kLBlkDoubles / 2);
+                const double* ga = Lp + blk_index(i, j0) * kLBlkDoubles;
+                const double* gb = Lp + blk_index(k, j0) * kLBlkDoubles;
+                for (int c = tid; c < cnt; c += kCT) {
+                    cp_async16(s.A[stg] + 2 * c, ga + 2 * c);
+                    if (i != k) cp_async16(s.B[stg] + 2 * c, gb + 2 * c);
+                }
                 cp_async_commit();
-            }
-            for (int j = 0; j < k; ++j) {
-                const int st = j & 1;
-                if (j + 1 < k) {
-                    load_block_async_ct(s.A[st ^ 1], Lp + blk_index(i, j + 1) * kLBlkDoubles);
-                    if (i != k) load_block_async_ct(s.B[st ^ 1], Lp + blk_index(k, j + 1) * kLBlkDoubles);
-                    cp_async_commit();
+            };
+            __syncthreads();  // buffers free (previous block finished: its TRSM / write-out still read A[0] and V)
+            if (k > 0) issue(0, 0);
+            for (int j = 0, it = 0; j < k; j += 2, ++it) {
+                const int st = it & 1;
+                if (j + 2 < k) {
+                    issue(st ^ 1, j + 2);
                     cp_async_wait<1>();
                 } else {
                     cp_async_wait<0>();
                 }
                 __syncthreads();
-                const double* ar = s.A[st];
-                const double* br = (i != k) ? s.B[st] : s.A[st];
-                warp_zgemm<1, 1, false, false, true, true>(cr, ci, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk, kLdBlk,
-                                                           br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk, kLdBlk, 32);
+                const int nb = k - j < 2 ? k - j : 2;
+                for (int h = 0; h < nb; ++h) {
+                    const double* ar = s.A[st] + h * kLBlkDoubles;
+                    const double* br = (i != k) ? s.B[st] + h * kLBlkDoubles : ar;
+                    warp_zgemm3m<1, 1, false, false, true, true>(P3m, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                               br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk, kLdBlk, 32);
+                }
                 __syncthreads();  // stage st may be overwritten by the load issued in the next iteration
             }
+            warp_zgemm3m_finish<1, 1, false, true>(P3m, cr, ci);
             // C = M_ik - acc, M_ik = J + lam_i G_ik lam_k
             const double* Gb = Gp + blk_index(i, k) * kBlkDoubles;
 #pragma unroll
@@ -257,8 +267,11 @@ __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
                 // L_ik = C . V^H
                 double dr[1][1][2], di[1][1][2];
                 warp_zero<1, 1>(dr, di);
-                warp_zgemm<1, 1, false, false, true, true>(dr, di, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk,
+            double Q3m[3][1][1][2];
+            warp_zero3m<1, 1>(Q3m);
+                warp_zgemm3m<1, 1, false, false, true, true>(Q3m, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk,
                                                            Vr + 8 * tj * kLdBlk, Vi + 8 * tj * kLdBlk, kLdBlk, 32);
+                warp_zgemm3m_finish<1, 1, false, true>(Q3m, dr, di);
                 double* Lb = Lp + blk_index(i, k) * kLBlkDoubles;
                 int r = 8 * ti + g, c = 8 * tj + 2 * q;
                 *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
@@ -307,6 +320,8 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
     for (int i = j + 1; i < nblk; ++i) {
         double cr[1][1][2], ci[1][1][2];
         warp_zero<1, 1>(cr, ci);
+            double P3m[3][1][1][2];
+            warp_zero3m<1, 1>(P3m);
         __syncthreads();  // buffers free; W blocks written by this CTA so far are visible
         load_block_async_ct(s.V, Vp + (size_t)i * kLBlkDoubles);
         load_block_async_ct(s.A[0], Lp + blk_index(i, j) * kLBlkDoubles);
@@ -324,10 +339,11 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
                 cp_async_wait<0>();
             }
             __syncthreads();
-            warp_zgemm<1, 1, false, false, false, false>(cr, ci, s.A[st] + 8 * ti * kLdBlk, s.A[st] + kLPlane + 8 * ti * kLdBlk,
+            warp_zgemm3m<1, 1, false, false, false, false>(P3m, s.A[st] + 8 * ti * kLdBlk, s.A[st] + kLPlane + 8 * ti * kLdBlk,
                                                          kLdBlk, s.B[st] + 8 * tj, s.B[st] + kLPlane + 8 * tj, kLdBlk, 32);
             __syncthreads();
         }
+        warp_zgemm3m_finish<1, 1, false, false>(P3m, cr, ci);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
@@ -337,9 +353,12 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
         __syncthreads();
         double dr[1][1][2], di[1][1][2];
         warp_zero<1, 1>(dr, di);
+            double Q3m[3][1][1][2];
+            warp_zero3m<1, 1>(Q3m);
         // V_ii is lower triangular: rows 8 ti.. only need k < 8 (ti + 1)
-        warp_zgemm<1, 1, false, false, false, false>(dr, di, s.V + 8 * ti * kLdBlk, s.V + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+        warp_zgemm3m<1, 1, false, false, false, false>(Q3m, s.V + 8 * ti * kLdBlk, s.V + kLPlane + 8 * ti * kLdBlk, kLdBlk,
                                                      s.A[0] + 8 * tj, s.A[0] + kLPlane + 8 * tj, kLdBlk, 8 * (ti + 1));
+        warp_zgemm3m_finish<1, 1, false, false>(Q3m, dr, di);
         double* Wb = Wp + blk_index(i, j) * kLBlkDoubles;
         int r = 8 * ti + g, c = 8 * tj + 2 * q;
         *reinterpret_cast<double2*>(Wb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
             for (int i = k; i < nblk; ++i) {
                 double cr[1][1][2], ci[1][1][2];
                 warp_zero<1, 1>(cr, ci);
+                double P3m[3][1][1][2];
+                warp_zero3m<1, 1>(P3m);
                 __syncthreads();  // buffers free (previous block finished: its TRSM / write-out still read A[0] and V)
                 if (k > 0) {
                     pt_load_block(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
                     __syncthreads();
                     const double* ar = s.A[st];
                     const double* br = (i != k) ? s.B[st] : s.A[st];
-                    warp_zgemm<1, 1, false, false, true, true>(cr, ci, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk,
+                    warp_zgemm3m<1, 1, false, false, true, true>(P3m, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk,
                                                                kLdBlk, br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk,
                                                                kLdBlk, 32);
                     if (i == k) {
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
                     }
                     __syncthreads();  // stage st may be overwritten by the load issued in the next iteration
                 }
+                warp_zgemm3m_finish<1, 1, false, true>(P3m, cr, ci);
                 // C = M_ik - acc with M generated on the fly
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -191,8 +194,11 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
                     // L_ik = C . V^H
                     double dr[1][1][2], di[1][1][2];
                     warp_zero<1, 1>(dr, di);
-                    warp_zgemm<1, 1, false, false, true, true>(dr, di, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk,
+                    double Q3m[3][1][1][2];
+                    warp_zero3m<1, 1>(Q3m);
+                    warp_zgemm3m<1, 1, false, false, true, true>(Q3m, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk,
                                                                Vr + 8 * tj * kLdBlk, Vi + 8 * tj * kLdBlk, kLdBlk, 32);
+                    warp_zgemm3m_finish<1, 1, false, true>(Q3m, dr, di);
                     double* Lb = Lp + blk_index(i, k) * kLBlkDoubles;
                     const int r = 8 * ti + g, c = 8 * tj + 2 * q;
                     *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
