@@ -67,6 +67,9 @@ def build_parser():
     p.add_argument("--rng", choices=("numpy", "philox"), default="numpy",
                    help="numpy: the reference's random streams, chain by chain; philox: batched device draws")
     p.add_argument("--solver", choices=("reference-cg", "exact"), default=None)
+    p.add_argument("--dpss_alpha", type=float, default=None,
+                   help="without --fgmodes: use Nfgmodes DPSS modes of this bandwidth factor (hydra_pspec/dpss.py:70-73) "
+                        "instead of the reference driver's Legendre polynomials")
     p.add_argument("--time_flags", choices=("any", "per-time"), default="any",
                    help="any: a channel flagged at any time is flagged at all times (the reference, "
                         "run-hydra-pspec.py:520-526); per-time: keep the (Ntimes, Nfreqs) flags (in-painting)")
@@ -200,6 +203,9 @@ def assemble_baselines(args, antpairs, freqs, get, out_dir):
                 fgmodes = np.load(Path(args.fgmodes) / bl_str / name)
             fgmodes = fgmodes[:, :args.Nfgmodes]
             check_shape(fgmodes.shape, (Nfreqs, args.Nfgmodes), desc="fgmodes")
+        elif args.dpss_alpha is not None:
+            from hydra_pspec_b200.dpss import dpss_modes
+            fgmodes = dpss_modes(freqs.size, args.Nfgmodes, args.dpss_alpha).T
         else:
             fgmodes = np.array([scipy.special.legendre(i)(np.linspace(-1.0, 1.0, freqs.size))
                                 for i in range(args.Nfgmodes)]).T

@@ -148,3 +148,26 @@ def test_driver_batched_philox_mode(td, tmp_path):
     assert np.load(bl / "gcr-eor.npy").shape == (40, 203, 120)
     pri = slice(57, 64)
     assert np.all(ps[:, pri] >= 0.1) and np.all(ps[:, pri] <= 2.0)  # prior-bounded bins
+
+
+@pytest.mark.gpu
+def test_driver_per_time_flags_and_dpss_modes(td, tmp_path):
+    """--flags file with a different mask per time, kept per time (in-painting), DPSS foreground modes."""
+    rng = np.random.default_rng(5)
+    fl = rng.random((203, 120)) < 0.05          # True = flagged (run-hydra-pspec.py:101-107)
+    fl[:, 40] = True
+    np.save(tmp_path / "flags.npy", fl)
+    argv = ["--ant_str", "0_1", "--seed", "3", "--Niter", "6", "--dirname", "pt", "--out_dir", str(tmp_path), "--clobber",
+            "--sigcov0", str(td), "--sigcov0_file", "eor-cov.npy", "--Nfgmodes", "10", "--dpss_alpha", "4.0",
+            "--noise", str(td), "--noise_file", "noise.npy", "--noise_cov", str(td), "--noise_cov_file", "noise-cov.npy",
+            "--flags", str(tmp_path / "flags.npy"), "--time_flags", "per-time", "--rng", "philox",
+            str(td / "vis-eor-fgs.uvh5")]
+    assert drv.main(argv) == 0
+    bl = tmp_path / "pt" / "0-1"
+    ps, fg = np.load(bl / "dps-eor.npy"), np.load(bl / "fg-amps.npy")
+    assert ps.shape == (6, 120) and fg.shape == (6, 203, 10) and np.all(np.isfinite(ps)) and np.all(ps > 0)
+    # the collapsed-flags run (reference behaviour) drops every channel that is flagged at any time
+    argv[argv.index("per-time")] = "any"
+    argv[argv.index("pt")] = "anyflags"
+    with pytest.raises(Exception):
+        drv.main(argv)   # ~100 % of the channels end up flagged: the GCR system loses its data term and is refused / singular
