@@ -170,6 +170,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (hydra_pspec_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    # one process per GPU: page-locked e2e buffers next to this rank's GPU (single-GPU runs keep all host cores:
+    # the CPU baseline leg uses them)
+    numa_node = _lib.bind_to_device_numa(local_rank, verbose=True) if world > 1 else None
     # stdout carries exactly one JSON line: anything libraries print at the fd level while the job runs
     # (NCCL's "NCCL version ..." banner on a box with NCCL_DEBUG set) goes to stderr instead
     sys.stdout.flush()
@@ -304,7 +307,7 @@ def run_b200(args):
                "call": f"GibbsEngine(create) + load_chain x{Be} from pinned host arrays + run_to_host({Ke} iterations): "
                        "signal_cr/fg_amps/chisq/signal_ps/ln_post of every iteration (the reference's full return set, "
                        "10.3 MB per baseline-iteration) land in pinned host arrays; PCIe-bound",
-               "pcie_gbs": d2h * Ke / dt * 1e-9}
+               "pcie_gbs": d2h * Ke / dt * 1e-9, "numa_node": numa_node}
 
     # ---- CPU baseline on this box (rank 0, N=1 only)
     cpu = None

@@ -123,3 +123,40 @@ def pinned_empty(shape, dtype):
     import weakref
     weakref.finalize(buf, lib().hp_pinned_free, p)
     return arr
+
+
+def bind_to_device_numa(device, verbose=False):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that page-locked staging
+    buffers (first touch / cudaHostAlloc) land in that node's memory and device-to-host copies do not
+    cross the socket interconnect.  With one process per GPU on a dual-socket box this is what keeps the
+    end-to-end (PCIe-bound) rate from collapsing when all GPUs stream at once.  Best effort: returns the
+    node, or None when the topology cannot be read or the node's CPUs are not available to the process.
+    Disabled by HP_NO_NUMA_BIND=1."""
+    import os
+    import subprocess
+    if os.environ.get("HP_NO_NUMA_BIND") == "1":
+        return None
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(int(device))],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        dom, rest = out.split(":", 1)
+        bus = f"{dom[-4:]}:{rest}"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if verbose:
+            import sys
+            print(f"[numa] device {device} bus {bus} node {node}: {len(use)} of {len(allowed)} allowed CPUs on that node",
+                  file=sys.stderr)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return node
+    except Exception:  # noqa: BLE001 - topology files missing, nvidia-smi absent, ...
+        return None

@@ -244,7 +244,8 @@ def main(argv=None):
             torch.cuda.set_device(local_rank)
         dist.init_process_group(backend)
 
-    from hydra_pspec_b200 import pspec, driver, utils
+    from hydra_pspec_b200 import pspec, driver, utils, _lib
+    _lib.bind_to_device_numa(local_rank)  # page-locked output staging next to this rank's GPU
 
     time_load_start = time.perf_counter()
     # Every rank reads the (small) inputs itself: the reference's rank-0 load + MPI scatter of pickled
