@@ -1,81 +1,151 @@
-// hp_diag.cuh -- 32x32 complex diagonal block: Cholesky factor and its triangular inverse by TWO warps.
+// hp_diag.cuh -- 32x32 complex diagonal block: Cholesky factor and its triangular inverse, blocked 8x8.
 //
-// The block lives in shared memory (planar re / im, row stride kLdBlk).  The first version used all
-// 512 threads with two __syncthreads per column (128 block-wide barriers per diagonal block).  Here
-// warp 0 runs a left-looking factorisation (lane = row; row c is a broadcast read, row `lane` a
-// conflict-free strided one) and warp 1 follows one column behind with the inverse (lane = column of
-// V; a lane only re-reads its own column, and row r of L is final once warp 0 has finished column
-// r).  The two warps meet at a 64-thread named barrier once per column; nothing else in the CTA
-// synchronises.  Loads are 16-byte (two columns per step) with two independent accumulator pairs.
+// The block lives in shared memory (planar re / im, row stride kLdBlk).  History: (1) all 512 threads,
+// two __syncthreads per column (128 block-wide barriers per block); (2) a two-warp pipeline, one named
+// barrier per column, ~20 us per block (measured by removing it: 30 % of k_pt_cholsolve, 17 % of k_chol).
+// This version is a right-looking factorisation over the 4 x 4 grid of 8x8 sub-blocks:
+//
+//   for kk = 0..3:  one warp factors the 8x8 diagonal sub-block in registers (lane = row, shuffles for
+//                   the column broadcasts, fully unrolled) and inverts it;  barrier;
+//                   panel    L[R][kk]  = A[R][kk] . inv8^H          one warp per sub-block, DMMA, K = 8
+//                   trailing A[R][C]  -= L[R][kk] . L[C][kk]^H      one warp per sub-block, DMMA, K = 8
+//   inverse: V[R][R] = inv8_R;  V[R][C] = -inv8_R . sum_{C <= p < R} L[R][p] V[p][C]  by distance R - C
+//
+// 13 block-wide barriers and ~40 DMMA k-steps instead of ~1000 dependent scalar steps.
 #pragma once
 #include "hp_kernels.cuh"
+#include "hp_mma.cuh"
 
 namespace hp {
 
-constexpr int kDiagBarrier = 8;  // named barrier id shared by the two warps (ids 1..3 are k_solve's)
-
-__device__ __forceinline__ void diag_pair_sync() { asm volatile("bar.sync %0, 64;" ::"n"(kDiagBarrier) : "memory"); }
-
-// In place: lower triangle of (Ar, Ai) := L (upper part zeroed), (Vr, Vi) := L^-1 (upper part zeroed).
-// Call with warps 0 and 1 of the CTA (all 64 threads).  Returns (on warp 0) true if a pivot was not positive.
-__device__ __forceinline__ bool diag_chol_inverse_2warps(double* Ar, double* Ai, double* Vr, double* Vi) {
+// One warp.  (Ar, Ai): 8x8 Hermitian sub-block (lower part used), overwritten with its Cholesky factor (upper
+// part zeroed); (Vr, Vi): receives the inverse of the factor (upper part zeroed).  Returns true on a
+// non-positive pivot.  All 32 lanes must call; lanes >= 8 only take part in the shuffles.
+__device__ __forceinline__ bool diag_chol_inverse8(double* Ar, double* Ai, double* Vr, double* Vi) {
     const int lane = threadIdx.x & 31;
-    const int which = (threadIdx.x >> 5) & 1;
+    const int r = lane & 7;
+    const bool act = lane < 8;
     bool bad = false;
-    if (which == 0) {
-        double* rowr = Ar + lane * kLdBlk;
-        double* rowi = Ai + lane * kLdBlk;
-        for (int c = 0; c < 32; ++c) {
-            const double* cr = Ar + c * kLdBlk;
-            const double* ci = Ai + c * kLdBlk;
-            double s0r = 0.0, s0i = 0.0, s1r = 0.0, s1i = 0.0;
-            int p = 0;
-            for (; p + 1 < c; p += 2) {
-                const double2 lr = *reinterpret_cast<const double2*>(rowr + p), li = *reinterpret_cast<const double2*>(rowi + p);
-                const double2 xr = *reinterpret_cast<const double2*>(cr + p), xi = *reinterpret_cast<const double2*>(ci + p);
-                s0r += lr.x * xr.x + li.x * xi.x; s0i += li.x * xr.x - lr.x * xi.x;
-                s1r += lr.y * xr.y + li.y * xi.y; s1i += li.y * xr.y - lr.y * xi.y;
-            }
-            if (p < c) {
-                const double lr0 = rowr[p], li0 = rowi[p], xr0 = cr[p], xi0 = ci[p];
-                s0r += lr0 * xr0 + li0 * xi0; s0i += li0 * xr0 - lr0 * xi0;
-            }
-            const double xr = rowr[c] - (s0r + s1r), xi = rowi[c] - (s0i + s1i);
-            const double piv = __shfl_sync(0xffffffffu, xr, c);
-            if (!(piv > 0.0)) bad = true;
-            const double inv = rsqrt(piv), d = piv * inv;
-            if (lane == c) { rowr[c] = d; rowi[c] = 0.0; }
-            else if (lane > c) { rowr[c] = xr * inv; rowi[c] = xi * inv; }
-            else { rowr[c] = 0.0; rowi[c] = 0.0; }
+    double ar[8], ai[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { ar[c] = Ar[r * kLdBlk + c]; ai[c] = Ai[r * kLdBlk + c]; }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, ar[c], c);
+        if (!(piv > 0.0)) bad = true;
+        const double inv = rsqrt(piv);
+        double lr = ar[c] * inv, li = ai[c] * inv;
+        if (r == c) { lr = piv * inv; li = 0.0; }
+        if (r < c) { lr = 0.0; li = 0.0; }
+        ar[c] = lr; ai[c] = li;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) {
+            const double yr = __shfl_sync(0xffffffffu, lr, c2), yi = __shfl_sync(0xffffffffu, li, c2);
+            ar[c2] -= lr * yr + li * yi;     // a[r][c2] -= l[r][c] conj(l[c2][c])
+            ai[c2] -= li * yr - lr * yi;
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { Ar[r * kLdBlk + c] = ar[c]; Ai[r * kLdBlk + c] = ai[c]; }
+    }
+    __syncwarp();
+    // inverse, lane = column c:  V[q][c] = (delta_qc - sum_{p<q} L[q][p] V[p][c]) / L[q][q]   (L: broadcast reads)
+    double vr[8], vi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int p = 0; p < q; ++p) {
+            const double lr = Ar[q * kLdBlk + p], li = Ai[q * kLdBlk + p];
+            sr += lr * vr[p] - li * vi[p];
+            si += lr * vi[p] + li * vr[p];
+        }
+        const double dinv = 1.0 / Ar[q * kLdBlk + q];
+        vr[q] = r < q ? -sr * dinv : (r == q ? dinv : 0.0);
+        vi[q] = r < q ? -si * dinv : 0.0;
+    }
+    if (act) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { Vr[q * kLdBlk + r] = vr[q]; Vi[q * kLdBlk + r] = vi[q]; }
+    }
+    __syncwarp();
+    return bad;
+}
+
+// All warps of the CTA (>= 6) must call; contains __syncthreads.  In place: lower triangle of (Ar, Ai) := L
+// (upper part zeroed), (Vr, Vi) := L^-1 (upper part zeroed).  Returns (on warp 0) true if a pivot was not positive.
+__device__ __forceinline__ bool diag_chol_inverse_block(double* Ar, double* Ai, double* Vr, double* Vi) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    bool bad = false;
+    auto sub = [](double* base, int R, int C) { return base + (8 * R) * kLdBlk + 8 * C; };
+    // zero V and the strictly upper sub-blocks of A
+    for (int e = tid; e < kLBlkDoubles; e += blockDim.x) Vr[e] = 0.0;   // both planes are contiguous: Vi = Vr + kLPlane
+    if (warp < 6) {
+        const int R = warp < 3 ? 0 : (warp < 5 ? 1 : 2), C = warp < 3 ? warp + 1 : (warp < 5 ? warp - 1 : 3);
+        for (int e = lane; e < 64; e += 32) { sub(Ar, R, C)[(e >> 3) * kLdBlk + (e & 7)] = 0.0; sub(Ai, R, C)[(e >> 3) * kLdBlk + (e & 7)] = 0.0; }
+    }
+    __syncthreads();
+    for (int kk = 0; kk < 4; ++kk) {
+        if (warp == 0) bad |= diag_chol_inverse8(sub(Ar, kk, kk), sub(Ai, kk, kk), sub(Vr, kk, kk), sub(Vi, kk, kk));
+        if (kk == 3) break;
+        __syncthreads();
+        if (warp < 3 - kk) {
+            // panel: L[R][kk] = A[R][kk] . inv8^H
+            const int R = kk + 1 + warp;
+            double P[3][1][1][2], cr[1][1][2], ci[1][1][2];
+            warp_zero3m<1, 1>(P);
+            warp_zgemm3m<1, 1, false, false, true, true>(P, sub(Ar, R, kk), sub(Ai, R, kk), kLdBlk, sub(Vr, kk, kk), sub(Vi, kk, kk),
+                                                         kLdBlk, 8);
+            warp_zgemm3m_finish<1, 1, false, true>(P, cr, ci);
+            __syncwarp();  // every lane has read its fragments of A[R][kk] before it is overwritten
+            *reinterpret_cast<double2*>(sub(Ar, R, kk) + g * kLdBlk + 2 * q) = make_double2(cr[0][0][0], cr[0][0][1]);
+            *reinterpret_cast<double2*>(sub(Ai, R, kk) + g * kLdBlk + 2 * q) = make_double2(ci[0][0][0], ci[0][0][1]);
+        }
+        __syncthreads();
+        const int ntr = (3 - kk) * (4 - kk) / 2;
+        if (warp < ntr) {
+            // trailing update: A[R][C] -= L[R][kk] . L[C][kk]^H   for kk < C <= R <= 3
+            int R = kk + 1, C = kk + 1, w = warp;
+            while (w > R - (kk + 1)) { w -= R - kk; ++R; }
+            C = kk + 1 + w;
+            double P[3][1][1][2], cr[1][1][2], ci[1][1][2];
+            warp_zero3m<1, 1>(P);
+            warp_zgemm3m<1, 1, false, false, true, true>(P, sub(Ar, R, kk), sub(Ai, R, kk), kLdBlk, sub(Ar, C, kk), sub(Ai, C, kk),
+                                                         kLdBlk, 8);
+            warp_zgemm3m_finish<1, 1, false, true>(P, cr, ci);
+            double2* dr = reinterpret_cast<double2*>(sub(Ar, R, C) + g * kLdBlk + 2 * q);
+            double2* di = reinterpret_cast<double2*>(sub(Ai, R, C) + g * kLdBlk + 2 * q);
+            double2 xr = *dr, xi = *di;
+            xr.x -= cr[0][0][0]; xr.y -= cr[0][0][1]; xi.x -= ci[0][0][0]; xi.y -= ci[0][0][1];
+            *dr = xr; *di = xi;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // inverse: V[R][C] = -inv8_R . sum_{C <= p < R} L[R][p] V[p][C], by distance d = R - C
+    for (int d = 1; d < 4; ++d) {
+        if (warp < 4 - d) {
+            const int C = warp, R = C + d;
+            double P[3][1][1][2], cr[1][1][2], ci[1][1][2];
+            warp_zero3m<1, 1>(P);
+            warp_zgemm3m<1, 1, false, false, false, false>(P, sub(Ar, R, C), sub(Ai, R, C), kLdBlk, sub(Vr, C, C), sub(Vi, C, C),
+                                                           kLdBlk, 8 * d);
+            warp_zgemm3m_finish<1, 1, false, false>(P, cr, ci);
+            // park T in V[R][C] (zero so far), then V[R][C] = -inv8_R . T
+            *reinterpret_cast<double2*>(sub(Vr, R, C) + g * kLdBlk + 2 * q) = make_double2(cr[0][0][0], cr[0][0][1]);
+            *reinterpret_cast<double2*>(sub(Vi, R, C) + g * kLdBlk + 2 * q) = make_double2(ci[0][0][0], ci[0][0][1]);
             __syncwarp();
-            diag_pair_sync();  // column c of L (hence row c up to its diagonal) is final: warp 1 may take row c
+            warp_zero3m<1, 1>(P);
+            warp_zgemm3m<1, 1, false, false, false, false>(P, sub(Vr, R, R), sub(Vi, R, R), kLdBlk, sub(Vr, R, C), sub(Vi, R, C),
+                                                           kLdBlk, 8);
+            warp_zgemm3m_finish<1, 1, false, false>(P, cr, ci);
+            __syncwarp();
+            *reinterpret_cast<double2*>(sub(Vr, R, C) + g * kLdBlk + 2 * q) = make_double2(-cr[0][0][0], -cr[0][0][1]);
+            *reinterpret_cast<double2*>(sub(Vi, R, C) + g * kLdBlk + 2 * q) = make_double2(-ci[0][0][0], -ci[0][0][1]);
         }
-    } else {
-        // V = L^-1, lane = column:  V[r][lane] = (delta - sum_{p<r} L[r][p] V[p][lane]) / L[r][r]
-        for (int r = 0; r < 32; ++r) {
-            diag_pair_sync();
-            const double* lr_ = Ar + r * kLdBlk;
-            const double* li_ = Ai + r * kLdBlk;
-            double s0r = 0.0, s0i = 0.0, s1r = 0.0, s1i = 0.0;
-            int p = 0;
-            for (; p + 1 < r; p += 2) {
-                const double2 lr = *reinterpret_cast<const double2*>(lr_ + p), li = *reinterpret_cast<const double2*>(li_ + p);
-                const double vr0 = Vr[p * kLdBlk + lane], vi0 = Vi[p * kLdBlk + lane];
-                const double vr1 = Vr[(p + 1) * kLdBlk + lane], vi1 = Vi[(p + 1) * kLdBlk + lane];
-                s0r += lr.x * vr0 - li.x * vi0; s0i += lr.x * vi0 + li.x * vr0;
-                s1r += lr.y * vr1 - li.y * vi1; s1i += lr.y * vi1 + li.y * vr1;
-            }
-            if (p < r) {
-                const double lr0 = lr_[p], li0 = li_[p], vr0 = Vr[p * kLdBlk + lane], vi0 = Vi[p * kLdBlk + lane];
-                s0r += lr0 * vr0 - li0 * vi0; s0i += lr0 * vi0 + li0 * vr0;
-            }
-            const double dinv = 1.0 / lr_[r];
-            double vr = 0.0, vi = 0.0;
-            if (lane < r) { vr = -(s0r + s1r) * dinv; vi = -(s0i + s1i) * dinv; }
-            else if (lane == r) { vr = dinv; }
-            Vr[r * kLdBlk + lane] = vr;
-            Vi[r * kLdBlk + lane] = vi;
-        }
+        __syncthreads();
     }
     return bad;
 }

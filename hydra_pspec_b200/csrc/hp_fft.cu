@@ -15,6 +15,7 @@
 #include "hp_kernels.cuh"
 #include "hp_math.h"
 #include "hp_mma.cuh"
+#include <cstdlib>
 
 namespace hp {
 
@@ -165,6 +166,9 @@ size_t postfft_smem_bytes(int n, int m, int ktp) {
     return sizeof(double2) * ((size_t)2 * ktp * n + n + (size_t)ktp * (mk + 1)) + 64 * sizeof(double);
 }
 int postfft_ktp(int n, int m, size_t max_smem) {
+    static int forced = -1;   // HP_POSTFFT_KTP=4|8: experiments
+    if (forced < 0) { const char* e = getenv("HP_POSTFFT_KTP"); forced = e ? atoi(e) : 0; }
+    if ((forced == 4 || forced == 8) && postfft_smem_bytes(n, m, forced) <= max_smem) return forced;
     for (int ktp = 8; ktp >= 4; ktp /= 2)
         if (postfft_smem_bytes(n, m, ktp) <= max_smem) return ktp;
     return 0;

@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
                 }
                 __syncthreads();
                 if (i == k) {
-                    // ---- Cholesky of the 32x32 diagonal block and its inverse: two warps, no block barriers
-                    if (warp < 2 && diag_chol_inverse_2warps(Ar, Ai, Vr, Vi)) bad = k + 1;
+                    // ---- Cholesky of the 32x32 diagonal block and its inverse, blocked 8x8 (hp_diag.cuh)
+                    if (diag_chol_inverse_block(Ar, Ai, Vr, Vi)) bad = k + 1;
                     __syncthreads();
                     // ---- y_k = V (r_k - sum_{j<k} L_kj y_j)
                     for (int o = 8; o > 0; o >>= 1) {
