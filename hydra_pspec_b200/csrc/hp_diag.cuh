@@ -26,7 +26,7 @@ __device__ __forceinline__ bool diag_chol_inverse8(double* Ar, double* Ai, doubl
     const int r = lane & 7;
     const bool act = lane < 8;
     bool bad = false;
-    double ar[8], ai[8];
+    double ar[8], ai[8], dinv[8];   // dinv[c] = 1 / L[c][c], kept for the inverse (no division on its critical path)
 #pragma unroll
     for (int c = 0; c < 8; ++c) { ar[c] = Ar[r * kLdBlk + c]; ai[c] = Ai[r * kLdBlk + c]; }
 #pragma unroll
@@ -34,6 +34,7 @@ __device__ __forceinline__ bool diag_chol_inverse8(double* Ar, double* Ai, doubl
         const double piv = __shfl_sync(0xffffffffu, ar[c], c);
         if (!(piv > 0.0)) bad = true;
         const double inv = rsqrt(piv);
+        dinv[c] = inv;
         double lr = ar[c] * inv, li = ai[c] * inv;
         if (r == c) { lr = piv * inv; li = 0.0; }
         if (r < c) { lr = 0.0; li = 0.0; }
@@ -61,9 +62,8 @@ __device__ __forceinline__ bool diag_chol_inverse8(double* Ar, double* Ai, doubl
             sr += lr * vr[p] - li * vi[p];
             si += lr * vi[p] + li * vr[p];
         }
-        const double dinv = 1.0 / Ar[q * kLdBlk + q];
-        vr[q] = r < q ? -sr * dinv : (r == q ? dinv : 0.0);
-        vi[q] = r < q ? -si * dinv : 0.0;
+        vr[q] = r < q ? -sr * dinv[q] : (r == q ? dinv[q] : 0.0);
+        vi[q] = r < q ? -si * dinv[q] : 0.0;
     }
     if (act) {
 #pragma unroll
@@ -73,15 +73,16 @@ __device__ __forceinline__ bool diag_chol_inverse8(double* Ar, double* Ai, doubl
     return bad;
 }
 
-// All warps of the CTA (>= 6) must call; contains __syncthreads.  In place: lower triangle of (Ar, Ai) := L
+// All threads of the CTA must call (it contains __syncthreads); `tid` / `nthreads` identify the thread within the
+// team of >= 6 warps that owns this block (the whole CTA, or one of the lockstep teams of k_pt_cholsolve).  In place: lower triangle of (Ar, Ai) := L
 // (upper part zeroed), (Vr, Vi) := L^-1 (upper part zeroed).  Returns (on warp 0) true if a pivot was not positive.
-__device__ __forceinline__ bool diag_chol_inverse_block(double* Ar, double* Ai, double* Vr, double* Vi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ bool diag_chol_inverse_block(double* Ar, double* Ai, double* Vr, double* Vi, int tid, int nthreads) {
+    const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     bool bad = false;
     auto sub = [](double* base, int R, int C) { return base + (8 * R) * kLdBlk + 8 * C; };
     // zero V and the strictly upper sub-blocks of A
-    for (int e = tid; e < kLBlkDoubles; e += blockDim.x) Vr[e] = 0.0;   // both planes are contiguous: Vi = Vr + kLPlane
+    for (int e = tid; e < kLBlkDoubles; e += nthreads) Vr[e] = 0.0;   // both planes are contiguous: Vi = Vr + kLPlane
     if (warp < 6) {
         const int R = warp < 3 ? 0 : (warp < 5 ? 1 : 2), C = warp < 3 ? warp + 1 : (warp < 5 ? warp - 1 : 3);
         for (int e = lane; e < 64; e += 32) { sub(Ar, R, C)[(e >> 3) * kLdBlk + (e & 7)] = 0.0; sub(Ai, R, C)[(e >> 3) * kLdBlk + (e & 7)] = 0.0; }

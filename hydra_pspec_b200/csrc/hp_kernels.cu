@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
             __syncthreads();
             if (i == k) {
                 // ---- Cholesky of the 32x32 diagonal block and its inverse, blocked 8x8 (hp_diag.cuh)
-                if (diag_chol_inverse_block(Ar, Ai, Vr, Vi)) bad = k + 1;
+                if (diag_chol_inverse_block(Ar, Ai, Vr, Vi, tid, kCT)) bad = k + 1;
                 __syncthreads();
                 // write L_kk and V to global
                 double* Lb = Lp + blk_index(k, k) * kLBlkDoubles;
