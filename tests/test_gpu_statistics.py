@@ -75,6 +75,32 @@ def test_posterior_moments_agree(nflag):
     assert np.all(np.sqrt(vd) > 0.3 / np.sqrt(nt))
 
 
+def test_posterior_moments_agree_per_time_flags():
+    """Same criterion for the per-time-flags path (k_pt_cholsolve): the white draw added between the forward
+    and the backward substitution must give every time its own correctly distributed constrained realisation."""
+    from hydra_pspec_b200 import pspec
+    nt, nf, nm = 24, 16, 2
+    vis, _, F, Ninv, prior = make_problem(21, nt, nf, nm, 0)
+    rng = np.random.default_rng(77)
+    flags = rng.random((nt, nf)) > 0.15
+    flags[:, 5] = False
+    burn, niter = 100, 3000
+    ps_o = oracle_chain(vis, flags, F, Ninv, prior, 1200, seed=19)[burn:]
+    out = pspec.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, Ninv, prior, Niter=niter, seed=777, verbose=False,
+                                     rng="philox")
+    ps_d = out[2][burn:]
+    assert np.all(np.isfinite(ps_d)) and np.all(ps_d > 0)
+    lo, ld = np.log(ps_o), np.log(ps_d)
+    mo, so = batch_mean_stats(lo)
+    md, sd = batch_mean_stats(ld)
+    z = (md - mo) / np.sqrt(so ** 2 + sd ** 2)
+    assert np.max(np.abs(z)) < 5.0, z
+    vo, svo = batch_mean_stats((lo - mo) ** 2)
+    vd, svd = batch_mean_stats((ld - md) ** 2)
+    zv = (vd - vo) / np.sqrt(svo ** 2 + svd ** 2)
+    assert np.max(np.abs(zv)) < 5.0, zv
+
+
 def test_frozen_omega_semantics():
     """refresh_omega=False reproduces the reference's re-use of the fluctuation draws: with the
     power spectrum held fixed by a tight prior, consecutive GCR solutions are identical."""
