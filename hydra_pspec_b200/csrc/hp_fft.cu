@@ -175,7 +175,7 @@ int postfft_ktp(int n, int m, size_t max_smem) {
 }
 
 template <int kTP>
-__global__ void __launch_bounds__(32 * kTP) k_post_fft(PostFftArgs a) {
+__global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFftArgs a) {
     constexpr int kThreads = 32 * kTP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.plan.n, m = a.m, mk = ((m + 3) / 4) * 4, ldf = mk + 1;
