@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--ntimes", type=int, default=1024)
     ap.add_argument("--nfg", type=int, default=32)
     ap.add_argument("--e2e-baselines", type=int, default=32)
-    ap.add_argument("--e2e-iters", type=int, default=32)
+    ap.add_argument("--e2e-iters", type=int, default=16)
     ap.add_argument("--substreams", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
