@@ -9,7 +9,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -243,6 +245,7 @@ struct hp_engine {
     double *ps_out = nullptr, *lnpost_out = nullptr, *cr_out = nullptr, *fg_out = nullptr, *chisq_out = nullptr;
     double *Gd = nullptr, *stage = nullptr, *vecn = nullptr;  // set-up scratch
     void* arena = nullptr;   // one device allocation holds every buffer below
+    size_t arena_bytes = 0;
     hp::FftPlan plan{};
     bool fft_ok = false;
     int ntilesE = 0, ktp = 8;
@@ -278,6 +281,42 @@ struct hp_engine {
 };
 
 namespace {
+// One cached device arena per GPU.  The drop-in functions create and destroy an engine per call (the reference's
+// driver calls gibbs_sample_with_fg once per baseline), and cudaMalloc / cudaFree of a multi-GB arena cost
+// milliseconds to tens of milliseconds each: the arena of a destroyed engine is kept and handed to the next engine
+// on that device if it is large enough.  hp_release_cached_memory() frees it; HP_NO_ARENA_CACHE=1 disables it.
+constexpr int kMaxDevices = 64;
+struct CachedArena { void* p = nullptr; size_t bytes = 0; };
+CachedArena g_arena_cache[kMaxDevices];
+std::mutex g_arena_mutex;
+bool arena_cache_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("HP_NO_ARENA_CACHE"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
+}
+cudaError_t arena_acquire(void** base, size_t* bytes, int device) {
+    if (arena_cache_enabled() && device >= 0 && device < kMaxDevices) {
+        std::lock_guard<std::mutex> lk(g_arena_mutex);
+        CachedArena& c = g_arena_cache[device];
+        if (c.p && c.bytes >= *bytes) { *base = c.p; *bytes = c.bytes; c.p = nullptr; c.bytes = 0; return cudaSuccess; }
+        if (c.p) { cudaFree(c.p); c.p = nullptr; c.bytes = 0; }   // too small: make room before the larger allocation
+    }
+    return cudaMalloc(base, *bytes);
+}
+void arena_release(void* p, size_t bytes, int device) {
+    if (!p) return;
+    if (arena_cache_enabled() && device >= 0 && device < kMaxDevices) {
+        std::lock_guard<std::mutex> lk(g_arena_mutex);
+        CachedArena& c = g_arena_cache[device];
+        if (!c.p || c.bytes < bytes) {
+            if (c.p) cudaFree(c.p);
+            c.p = p; c.bytes = bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
 // Collects buffer requests, then serves them all from one cudaMalloc (engine creation / teardown is
 // part of the end-to-end path: one allocation and one free instead of ~45).
 struct ArenaPlan {
@@ -285,12 +324,14 @@ struct ArenaPlan {
     std::vector<Req> reqs;
     template <typename T>
     void want(T** p, size_t count) { *p = nullptr; if (count) reqs.push_back({reinterpret_cast<void**>(p), count * sizeof(T)}); }
-    cudaError_t commit(void** base, cudaStream_t st) {
+    cudaError_t commit(void** base, size_t* bytes_out, int device, cudaStream_t st) {
         size_t total = 0;
         for (auto& r : reqs) total += (r.bytes + 255) & ~size_t(255);
-        cudaError_t e = cudaMalloc(base, total ? total : 256);
+        if (!total) total = 256;
+        *bytes_out = total;
+        cudaError_t e = arena_acquire(base, bytes_out, device);
         if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(*base, 0, total ? total : 256, st);
+        e = cudaMemsetAsync(*base, 0, total, st);
         if (e != cudaSuccess) return e;
         size_t off = 0;
         for (auto& r : reqs) { *r.p = static_cast<char*>(*base) + off; off += (r.bytes + 255) & ~size_t(255); }
@@ -311,6 +352,18 @@ extern "C" {
 
 const char* hp_last_error(void) { return g_err.c_str(); }
 const char* hp_version(void) { return "hydra_pspec_b200 0.1 (sm_100a)"; }
+void hp_release_cached_memory(void) {
+    std::lock_guard<std::mutex> lk(g_arena_mutex);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (g_arena_cache[d].p) {
+            cudaSetDevice(d);
+            cudaFree(g_arena_cache[d].p);
+            g_arena_cache[d] = CachedArena();
+        }
+    cudaSetDevice(cur);
+}
 const char* hp_kernel_class_name(int cls) {
     static const char* names[HP_NUM_KERNEL_CLASSES] = {"chol", "solve", "transform", "post", "sample"};
     return (cls >= 0 && cls < HP_NUM_KERNEL_CLASSES) ? names[cls] : "?";
@@ -321,7 +374,7 @@ int hp_engine_destroy(hp_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->st) cudaStreamSynchronize(e->st);
     for (auto& x : e->ev) cudaEventDestroy(x);
-    cudaFree(e->arena);
+    arena_release(e->arena, e->arena_bytes, e->cfg.device);
     if (e->copy_st) cudaStreamDestroy(e->copy_st);
     for (auto x : e->sub_st) cudaStreamDestroy(x);
     if (e->fork_ev) cudaEventDestroy(e->fork_ev);
@@ -416,7 +469,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->tw, 2 * n);
     ap.want(&e->Empart, C * e->ntilesE * n); ap.want(&e->Eupart, C * e->ntilesE * n);
     {
-        cudaError_t ce = ap.commit(&e->arena, e->st);
+        cudaError_t ce = ap.commit(&e->arena, &e->arena_bytes, cfg->device, e->st);
         if (ce != cudaSuccess) {
             std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(ce);
             hp_engine_destroy(e);
@@ -538,7 +591,8 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     CU_TRY(cudaMemcpyAsync(e->ninvd + (size_t)c * n, ninv_diag, n * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(wd, vis, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
     if (pt) CU_TRY(cudaMemcpyAsync(e->wT + (size_t)c * Tp * n, wtv.data(), (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));  // wv / wtv are locals
+    // (wv / wtv are pageable locals: cudaMemcpyAsync has staged them before it returns; `vis` may be page-locked and is
+    //  only guaranteed consumed by the stream synchronisation at the end of this function)
     if (pt) k_mask_elem<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->wT + (size_t)c * Tp * n, (long long)T * n);
     else k_mask_cols<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->w + (size_t)c * n, T, n);
     k_noise_vectors<<<nblocks(n), 256, 0, st>>>(e->w + (size_t)c * n, e->ninvd + (size_t)c * n, e->ni + (size_t)c * n,
@@ -563,12 +617,11 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
         k_basis_fg<<<nblocks((long long)n * m), 256, 0, st>>>(BF, e->Ft + 2 * (size_t)c * m * n, e->stage, n, m, Np);
         if (e->cfg.general_basis0)
             k_basis_fg<<<nblocks((long long)n * m), 256, 0, st>>>(e->b0.Bmat + 2 * (size_t)c * n * Np, nullptr, e->stage, n, m, Np);
-        CU_TRY(cudaStreamSynchronize(st));
+        // e->stage is reused below / by the next chain: stream order is enough, no host synchronisation
     }
     if (e->cfg.general_basis0) {
         CU_TRY(cudaMemcpyAsync(e->stage, basis0, 2 * (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
         k_basis_general<<<nblocks((long long)n * n), 256, 0, st>>>(e->b0.Bmat + 2 * (size_t)c * n * Np, e->stage, n, Np);
-        CU_TRY(cudaStreamSynchronize(st));
     }
     int rc;
     if ((rc = build_basis_products(e, e->bF, c)) != HP_OK) return rc;
@@ -653,6 +706,19 @@ int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
     return HP_OK;
+}
+
+// rows x width bytes, device -> host: one strided copy when the pitches allow it (cudaMemcpy2D limits them to
+// cudaDeviceProp::memPitch, 2^31 - 1), else row by row
+static cudaError_t copy_rows_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                                 cudaStream_t st) {
+    if (rows == 0 || width == 0) return cudaSuccess;
+    if (dpitch < (size_t)0x7fffffff && spitch < (size_t)0x7fffffff)
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    for (size_t r = 0; r < rows && e == cudaSuccess; ++r)
+        e = cudaMemcpyAsync((char*)dst + r * dpitch, (const char*)src + r * spitch, width, cudaMemcpyDeviceToHost, st);
+    return e;
 }
 
 // Output slots of one Gibbs iteration (null = not kept).
@@ -981,18 +1047,18 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
         evs.push_back(ev);
         cudaEventRecord(ev, e->st);
         cudaStreamWaitEvent(e->copy_st, ev, 0);
-        // this iteration's big arrays leave over PCIe while the next iteration computes
-        for (size_t c = 0; c < (size_t)e->C && cerr == cudaSuccess; ++c) {
-            if (sink->signal_cr)
-                cerr = cudaMemcpyAsync(sink->signal_cr + 2 * ((c * HI + it) * T * n), e->cr_out + 2 * ((c * I + it) * T * n),
-                                       T * n * 16, cudaMemcpyDeviceToHost, e->copy_st);
-            if (sink->fg_amps && m && cerr == cudaSuccess)
-                cerr = cudaMemcpyAsync(sink->fg_amps + 2 * ((c * HI + it) * T * m), e->fg_out + 2 * ((c * I + it) * T * m),
-                                       T * m * 16, cudaMemcpyDeviceToHost, e->copy_st);
-            if (sink->chisq && cerr == cudaSuccess)
-                cerr = cudaMemcpyAsync(sink->chisq + (c * HI + it) * T * n, e->chisq_out + (c * I + it) * T * n, T * n * 8,
-                                       cudaMemcpyDeviceToHost, e->copy_st);
-        }
+        // this iteration's big arrays leave over PCIe while the next iteration computes: one strided copy per array
+        // (rows = chains; device pitch = a chain's whole output ring, host pitch = a chain's host array)
+        const size_t C = (size_t)e->C;
+        if (sink->signal_cr)
+            cerr = copy_rows_d2h(sink->signal_cr + 2 * (it * T * n), HI * T * n * 16, e->cr_out + 2 * (it * T * n), I * T * n * 16,
+                                 T * n * 16, C, e->copy_st);
+        if (sink->fg_amps && m && cerr == cudaSuccess)
+            cerr = copy_rows_d2h(sink->fg_amps + 2 * (it * T * m), HI * T * m * 16, e->fg_out + 2 * (it * T * m), I * T * m * 16,
+                                 T * m * 16, C, e->copy_st);
+        if (sink->chisq && cerr == cudaSuccess)
+            cerr = copy_rows_d2h(sink->chisq + it * T * n, HI * T * n * 8, e->chisq_out + it * T * n, I * T * n * 8, T * n * 8, C,
+                                 e->copy_st);
         return false;
     });
     if (cerr != cudaSuccess) return fail(HP_ERR_CUDA, std::string("hp_engine_run_to_host: ") + cudaGetErrorString(cerr));
@@ -1004,14 +1070,12 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
         CU_TRY(cudaStreamWaitEvent(e->copy_st, ev, 0));
     }
     if (niter > 0) {
-        for (size_t c = 0; c < (size_t)e->C; ++c) {
-            if (sink->signal_ps)
-                CU_TRY(cudaMemcpyAsync(sink->signal_ps + (c * HI + first) * n, e->ps_out + (c * I + first) * n,
-                                       (size_t)niter * n * 8, cudaMemcpyDeviceToHost, e->copy_st));
-            if (sink->ln_post)
-                CU_TRY(cudaMemcpyAsync(sink->ln_post + c * HI + first, e->lnpost_out + c * I + first, (size_t)niter * 8,
-                                       cudaMemcpyDeviceToHost, e->copy_st));
-        }
+        if (sink->signal_ps)
+            CU_TRY(copy_rows_d2h(sink->signal_ps + first * n, HI * n * 8, e->ps_out + first * n, I * n * 8, (size_t)niter * n * 8,
+                                 (size_t)e->C, e->copy_st));
+        if (sink->ln_post)
+            CU_TRY(copy_rows_d2h(sink->ln_post + first, HI * 8, e->lnpost_out + first, I * 8, (size_t)niter * 8, (size_t)e->C,
+                                 e->copy_st));
     }
     CU_TRY(cudaStreamSynchronize(e->copy_st));
     for (auto ev : evs) cudaEventDestroy(ev);

@@ -170,6 +170,9 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
 /* FP64 tensor-pipe (DMMA.8x8x4) peak of the device measured with an issue loop for ~`seconds`; TFLOP/s. */
 double hp_fp64_peak_tflops(int device, double seconds);
 /* page-locked host memory for the host<->device copies of the end-to-end path */
+/* A destroyed engine's device arena is kept (one per GPU) for the next hp_engine_create on that device; this frees it.
+ * HP_NO_ARENA_CACHE=1 in the environment disables the cache. */
+void hp_release_cached_memory(void);
 void* hp_pinned_alloc(size_t bytes);
 void hp_pinned_free(void* p);
 
