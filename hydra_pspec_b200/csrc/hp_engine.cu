@@ -235,6 +235,8 @@ struct hp_engine {
     double *Lp = nullptr, *Linvp = nullptr, *Wp = nullptr;
     double *wT = nullptr, *Hpt = nullptr, *niT = nullptr, *Bsel = nullptr, *ptScratch = nullptr;  // per-time flags
     int pt_ctas = 0;
+    int gd_slots = 1;
+    std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
     bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
     double *Wd = nullptr, *Yb = nullptr;
     double *NiD = nullptr, *NihD = nullptr, *Td = nullptr, *Rm = nullptr, *Yd = nullptr;  // dense (non-diagonal) noise
@@ -463,7 +465,8 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     if (cfg->keep & HP_KEEP_CR) ap.want(&e->cr_out, 2 * C * I * T * n);
     if (cfg->keep & HP_KEEP_FG) ap.want(&e->fg_out, 2 * C * I * T * (m ? m : 1));
     if (cfg->keep & HP_KEEP_CHISQ) ap.want(&e->chisq_out, C * I * T * n);
-    ap.want(&e->Gd, 2 * (size_t)e->N * e->N);
+    e->gd_slots = (int)(C < 16 ? C : 16);   // dense Gram scratch for a batch of chains (deferred set-up)
+    ap.want(&e->Gd, 2 * (size_t)e->gd_slots * e->N * e->N);
     ap.want(&e->stage, 2 * (T * n > n * n ? T * n : n * n));
     ap.want(&e->vecn, 4 * n);
     ap.want(&e->tw, 2 * n);
@@ -477,6 +480,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         }
     }
     e->flagged.assign(C, 0);
+    e->pending.assign(C, 0);
     e->have_omega.assign(C, 0);
     {
         int ns = cfg->substreams > 1 ? (cfg->substreams < (int)C ? cfg->substreams : (int)C) : 1;
@@ -560,6 +564,50 @@ static int build_basis_products(hp_engine* e, Basis& b, int c) {
     return HP_OK;
 }
 
+// The same products for `nc` consecutive chains at once (diagonal noise, time-invariant flags): one batched launch
+// fills the GPU where a single chain's 416 x 416 Gram product occupies a third of it.  Chain loading defers its
+// products to the first call that needs them (flush_pending), so a batch of load_chain calls costs one set of launches.
+static int build_basis_products_batch(hp_engine* e, Basis& b, int c0, int nc) {
+    const int n = e->n, N = e->N, Np = e->Np, T = e->T;
+    const size_t tri = hp::tri_blocks(e->nblk);
+    for (int cc0 = c0; cc0 < c0 + nc; cc0 += e->gd_slots) {
+        const int ncc = (c0 + nc - cc0) < e->gd_slots ? (c0 + nc - cc0) : e->gd_slots;
+        double* Bm = b.Bmat + 2 * (size_t)cc0 * n * Np;
+        hp::ZgemmArgs g{};
+        g.A = Bm; g.sAi = 1; g.sAk = Np; g.bsA = (long long)n * Np; g.conjA = 1;
+        g.B = Bm; g.sBk = Np; g.sBj = 1; g.bsB = (long long)n * Np;
+        g.dk = e->ni + (size_t)cc0 * n; g.bsD = n;
+        g.C = e->Gd; g.sCi = N; g.sCj = 1; g.bsC = (long long)N * N;
+        g.M = N; g.N = N; g.K = n; g.accumulate = 0; g.alpha = 1.0; g.batch = ncc;
+        hp::launch_zgemm(g, e->st);
+        hp::launch_pack_lower(e->Gd, N, (long long)N * N, b.Gp + (size_t)cc0 * tri * hp::kBlkDoubles, N, e->nblk, ncc, e->st);
+        hp::ZgemmArgs r{};
+        r.A = e->wd + 2 * (size_t)cc0 * e->Tp * n; r.sAi = n; r.sAk = 1; r.bsA = (long long)e->Tp * n;
+        r.dk = e->ni + (size_t)cc0 * n; r.bsD = n;
+        r.B = Bm; r.sBk = Np; r.sBj = 1; r.bsB = (long long)n * Np; r.conjB = 1;
+        r.C = b.Rfix + 2 * (size_t)cc0 * e->Tp * Np; r.sCi = Np; r.sCj = 1; r.bsC = (long long)e->Tp * Np;
+        r.M = T; r.N = N; r.K = n; r.accumulate = 0; r.alpha = 1.0; r.batch = ncc;
+        hp::launch_zgemm(r, e->st);
+    }
+    CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+static int flush_pending(hp_engine* e) {
+    const int C = e->C;
+    for (int c = 0; c < C;) {
+        if (!e->pending[c]) { ++c; continue; }
+        int c1 = c;
+        while (c1 < C && e->pending[c1]) ++c1;
+        int rc;
+        if ((rc = build_basis_products_batch(e, e->bF, c, c1 - c)) != HP_OK) return rc;
+        if (e->cfg.general_basis0 && (rc = build_basis_products_batch(e, e->b0, c, c1 - c)) != HP_OK) return rc;
+        for (int k = c; k < c1; ++k) e->pending[k] = 0;
+        c = c1;
+    }
+    return HP_OK;
+}
+
 static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t* flags, const double* fgmodes,
                            const double* ninv_diag, const double* ninv_dense, const double* nih_dense, const double* basis0,
                            const double* lam0sq, const double* ps_prior) {
@@ -623,9 +671,13 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
         CU_TRY(cudaMemcpyAsync(e->stage, basis0, 2 * (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
         k_basis_general<<<nblocks((long long)n * n), 256, 0, st>>>(e->b0.Bmat + 2 * (size_t)c * n * Np, e->stage, n, Np);
     }
-    int rc;
-    if ((rc = build_basis_products(e, e->bF, c)) != HP_OK) return rc;
-    if (e->cfg.general_basis0 && (rc = build_basis_products(e, e->b0, c)) != HP_OK) return rc;
+    if (!e->cfg.dense_noise && !e->cfg.time_flags) {
+        e->pending[c] = 1;   // products built in one batched launch by the first call that needs them
+    } else {
+        int rc;
+        if ((rc = build_basis_products(e, e->bF, c)) != HP_OK) return rc;
+        if (e->cfg.general_basis0 && (rc = build_basis_products(e, e->b0, c)) != HP_OK) return rc;
+    }
     // initial spectrum
     CU_TRY(cudaMemcpyAsync(e->vecn, lam0sq, n * sizeof(double), cudaMemcpyHostToDevice, st));
     k_init_lam<<<nblocks(Np), 256, 0, st>>>(e->lam + (size_t)c * Np, e->ps + (size_t)c * n, e->vecn, n, N, Np);
@@ -657,6 +709,7 @@ int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double
     if ((omega_a == nullptr) != (omega_b == nullptr)) return fail(HP_ERR_ARG, "omega_a and omega_b must both be given or both NULL");
     if (n_draw_iters > e->cfg.max_iters) return fail(HP_ERR_ARG, "more draw iterations than max_iters");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    { int rcf = flush_pending(e); if (rcf != HP_OK) return rcf; }
     const int n = e->n, Np = e->Np, T = e->T, Tp = e->Tp;
     cudaStream_t st = e->st;
     if (s_draws && n_draw_iters > 0)
@@ -951,6 +1004,7 @@ static void join_subs(hp_engine* e, const std::vector<Sub>& subs) {
 int hp_engine_gcr(hp_engine* e) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    { int rcf = flush_pending(e); if (rcf != HP_OK) return rcf; }
     Basis& b = (e->cfg.general_basis0 && e->iter == 0) ? e->b0 : e->bF;
     IterOut o{e->Sf, (long long)e->Tp * e->n, nullptr, 0, nullptr, 0};
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
@@ -1022,6 +1076,7 @@ int hp_engine_run(hp_engine* e, int niter) {
     if (niter < 0 || e->out_pos + niter > e->cfg.max_iters)
         return fail(HP_ERR_ARG, "hp_engine_run: would exceed max_iters (use hp_engine_rewind)");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    { int rcf = flush_pending(e); if (rcf != HP_OK) return rcf; }
     enqueue_iterations(e, niter, [](int) { return false; });
     CU_TRY(cudaGetLastError());
     return HP_OK;
@@ -1034,6 +1089,7 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
     if ((sink->signal_cr && !e->cr_out) || (sink->fg_amps && !e->fg_out) || (sink->chisq && !e->chisq_out))
         return fail(HP_ERR_ARG, "hp_engine_run_to_host: sink asks for an output that is not kept (cfg.keep)");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    { int rcf = flush_pending(e); if (rcf != HP_OK) return rcf; }
     if (!e->copy_st) CU_TRY(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
     const size_t n = e->n, m = e->m, T = e->T, I = e->cfg.max_iters, HI = sink->iters;
     const int first = e->out_pos;
