@@ -301,13 +301,43 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        # the same call keeping only what a power-spectrum analysis consumes (signal_ps + ln_post per iteration):
+        # shows how much of the end-to-end time is the reference's full return set crossing PCIe
+        bufs_ps = None
+
+        def one_call_ps():
+            nonlocal bufs_ps
+            e = pspec.GibbsEngine(Be, nt, nf, nm, max_iters=Ke, rng="philox", keep=(), seed=99 + rank, device=local_rank,
+                                  stream=stream)
+            if bufs_ps is None:
+                bufs_ps = e.host_buffers(Ke)
+            for c, (pv, flags, F, nd, l0sq) in enumerate(pin):
+                e.load_chain(c, pv, flags, F, nd, l0sq)
+            e.run_to_host(Ke, bufs_ps)
+            e.close()
+
+        one_call_ps()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one_call_ps()
+        torch.cuda.synchronize()
+        dt_ps = (time.perf_counter() - t0) / reps
+        tt = torch.tensor([dt_ps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_ps = float(tt.item())
         h2d = sum(pv.nbytes + F.nbytes + nd.nbytes + l0sq.nbytes + flags.size for pv, flags, F, nd, l0sq in pin) / Ke
         d2h = sum(v.nbytes for v in bufs.values()) / Ke
         e2e = {"value": world * Be * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "call": f"GibbsEngine(create) + load_chain x{Be} from pinned host arrays + run_to_host({Ke} iterations): "
                        "signal_cr/fg_amps/chisq/signal_ps/ln_post of every iteration (the reference's full return set, "
                        "10.3 MB per baseline-iteration) land in pinned host arrays; PCIe-bound",
-               "pcie_gbs": d2h * Ke / dt * 1e-9, "numa_node": numa_node}
+               "pcie_gbs": d2h * Ke / dt * 1e-9, "numa_node": numa_node,
+               "power_spectrum_only": {"value": world * Be * Ke / dt_ps, "unit": UNIT,
+                                       "d2h_bytes_per_step": int(sum(v.nbytes for v in bufs_ps.values()) / Ke),
+                                       "call": "same call with keep=(): only signal_ps + ln_post are read back"}}
 
     # ---- CPU baseline on this box (rank 0, N=1 only)
     cpu = None
