@@ -404,7 +404,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     e->Tp = e->ntiles * hp::kTT;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    e->big_solve = cfg->force_dense_solve || hp::solve_smem_bytes(e->nblk) > (size_t)max_smem;
+    e->big_solve = cfg->force_dense_solve || !hp::solve_resident_ok(e->nblk, (size_t)max_smem);
     if (e->big_solve && cfg->cg_compat && !cfg->time_flags) {
         delete e;
         return fail(HP_ERR_SIZE, "Nfreqs + Nmodes = " + std::to_string(e->N) + " is too large for the shared-memory resident "

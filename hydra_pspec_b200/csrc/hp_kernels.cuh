@@ -78,6 +78,7 @@ struct SolveArgs {
 };
 void launch_solve(const SolveArgs& a, cudaStream_t st);
 size_t solve_smem_bytes(int nblk);
+bool solve_resident_ok(int nblk, size_t max_smem);   // false: use the dense-product solve (N > 576)
 
 struct PostArgs {
     const double* Sf;      // [nsys][>=T][n] complex: signal in frequency space (rows t < T are read)

@@ -142,6 +142,11 @@ static size_t solve_smem_bytes_stages(int nblk, int stages) {
     return d * sizeof(double);
 }
 size_t solve_smem_bytes(int nblk) { return solve_smem_bytes_stages(nblk, 2); }  // minimum configuration
+// k_solve can take a system: the minimum configuration fits shared memory AND its two ring slots can stage four
+// right-hand-side rows at a time (Np <= 576); larger systems go to the dense-product solve of the engine
+bool solve_resident_ok(int nblk, size_t max_smem) {
+    return solve_smem_bytes(nblk) <= max_smem && (size_t)2 * kLBlkDoubles * 8 >= (size_t)4 * nblk * 32 * 16;
+}
 
 __global__ void __launch_bounds__(544) k_solve(SolveArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -471,7 +476,7 @@ void launch_solve(const SolveArgs& a_in, cudaStream_t st) {
         size_t ring_bytes = (size_t)stages * kLBlkDoubles * 8, row_bytes = (size_t)a.nblk * 32 * 16;
         int rpr = (int)(ring_bytes / row_bytes) / 4 * 4;
         a.rows_per_round = rpr >= kTT ? kTT : (rpr >= 8 ? 8 : 4);
-        if (ring_bytes < 4 * row_bytes) a.rows_per_round = 0;  // cannot happen: 2 stages hold 4 rows up to Np = 576
+        if (ring_bytes < 4 * row_bytes) return;  // excluded by solve_resident_ok (the engine never launches this)
     }
     size_t smem = solve_smem_bytes_stages(a.nblk, stages);
     static size_t attr_smem = 0;
