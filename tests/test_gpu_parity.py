@@ -201,3 +201,50 @@ def test_full_size_linear_system_residual():
         b = np.concatenate([S0 @ z + Sh @ oma[t], F.conj().T @ z])
         worst = max(worst, np.linalg.norm(A @ x[t] - b) / np.linalg.norm(b))
     assert worst < 1e-11
+
+
+@pytest.mark.parametrize("nt,nf,nm,seed", [(2, 4, 1, 1), (3, 8, 2, 2), (5, 6, 0, 3), (17, 64, 40, 4), (33, 31, 3, 5)])
+def test_edge_shapes_match_oracle(nt, nf, nm, seed):
+    """Smallest shapes the API accepts, a system smaller than one 32x32 block, more foreground modes than a block,
+    a prime Nfreqs (dense transforms), Ntimes not a multiple of any tile size."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(100 + seed)
+    F = np.linalg.qr(crandn(rng, nf, max(nm, 1)))[0][:, :nm]
+    fop = ho.fourier_operator(nf)
+    S0 = fop.conj().T @ np.diag((0.5 + rng.random(nf)) / nf ** 2) @ fop
+    sig = 0.3 + rng.random(nf)
+    vis = crandn(rng, nt, nf) * sig + crandn(rng, nt, nf) @ np.linalg.cholesky(S0 + 1e-13 * np.eye(nf)).T
+    if nm:
+        vis = vis + (5 * crandn(rng, nt, nm)) @ F.T
+    flags = np.ones(nf, dtype=bool)
+    flags[rng.integers(nf)] = False
+    prior = np.zeros((2, nf))
+    Ninv = np.diag(1.0 / sig ** 2)
+    want = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=seed, solver="direct")
+    got = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=seed, verbose=False, solver="exact")
+    for o, w, k in zip(got[:6], want, KEYS):
+        assert rel(o, w) < TOL, k
+
+
+def test_prior_on_every_bin_and_wide_dynamic_range():
+    """Every delay bin prior-bounded (inversion sampler everywhere) and an initial spectrum spanning six decades."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(321)
+    nt, nf, nm = 14, 40, 4
+    F = np.linalg.qr(crandn(rng, nf, nm))[0]
+    fop = ho.fourier_operator(nf)
+    p0 = 10.0 ** rng.uniform(-3, 3, nf)
+    S0 = fop.conj().T @ np.diag(p0 / nf ** 2) @ fop
+    vis = crandn(rng, nt, nf) * 0.5 + (5 * crandn(rng, nt, nm)) @ F.T + crandn(rng, nt, nf) @ np.linalg.cholesky(
+        S0 + 1e-12 * np.eye(nf)).T
+    flags = np.ones(nf, dtype=bool)
+    flags[[3, 30]] = False
+    prior = np.zeros((2, nf))
+    prior[0, :] = 1e4
+    prior[1, :] = 1e-4
+    Ninv = np.eye(nf) * 4.0
+    want = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=9, solver="direct")
+    got = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=9, verbose=False, solver="exact")
+    for o, w, k in zip(got[:6], want, KEYS):
+        assert rel(o, w) < 1e-8, k   # cond(A) ~ 1e6 on the oracle's (unwhitened) side
+    assert np.all(got[2] >= 1e-4) and np.all(got[2] <= 1e4)

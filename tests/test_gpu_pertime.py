@@ -132,3 +132,24 @@ def test_per_time_unsupported_combinations_raise():
         pspec.gibbs_sample_with_fg(vis, flags, S0, F, dense, prior, Niter=1, verbose=False)
     with pytest.raises(NotImplementedError):
         pspec.gibbs_sample_with_fg(vis, flags, S0 + 0.01 * np.diag(np.arange(32.0)), F, Ninv, prior, Niter=1, verbose=False)
+
+
+@pytest.mark.parametrize("nt,nf,nm,seed", [(2, 8, 1, 1), (3, 12, 2, 2), (5, 16, 0, 3)])
+def test_per_time_tiny_shapes(nt, nf, nm, seed):
+    from hydra_pspec_b200 import pspec
+    vis, flags, S0, F, Ninv, _ = make_case(nt, nf, nm, 0.2, 50 + seed)
+    prior = np.zeros((2, nf))
+    ref = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=seed, solver="direct")
+    out = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=seed, verbose=False)
+    for o, r, k in zip(out[:6], ref, KEYS):
+        assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
+
+
+def test_per_time_fully_flagged_integration_is_refused():
+    """An integration with every channel flagged leaves the (flat-prior) foreground amplitudes of that time
+    unconstrained: the system is singular and the chain is refused with LinAlgError instead of returning NaNs."""
+    from hydra_pspec_b200 import pspec
+    vis, flags, S0, F, Ninv, prior = make_case(6, 32, 4, 0.1, 1)
+    flags[2, :] = False
+    with pytest.raises(np.linalg.LinAlgError):
+        pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=1, verbose=False)
