@@ -26,48 +26,53 @@ __device__ __forceinline__ bool diag_chol_inverse8(double* Ar, double* Ai, doubl
     const int r = lane & 7;
     const bool act = lane < 8;
     bool bad = false;
-    double ar[8], ai[8], dinv[8];   // dinv[c] = 1 / L[c][c], kept for the inverse (no division on its critical path)
+    {
+        // factor: lane = row, the row lives in 16 registers; 1 / L[c][c] is parked on the diagonal of V
+        double ar[8], ai[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { ar[c] = Ar[r * kLdBlk + c]; ai[c] = Ai[r * kLdBlk + c]; }
+        for (int c = 0; c < 8; ++c) { ar[c] = Ar[r * kLdBlk + c]; ai[c] = Ai[r * kLdBlk + c]; }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const double piv = __shfl_sync(0xffffffffu, ar[c], c);
-        if (!(piv > 0.0)) bad = true;
-        const double inv = rsqrt(piv);
-        dinv[c] = inv;
-        double lr = ar[c] * inv, li = ai[c] * inv;
-        if (r == c) { lr = piv * inv; li = 0.0; }
-        if (r < c) { lr = 0.0; li = 0.0; }
-        ar[c] = lr; ai[c] = li;
+        for (int c = 0; c < 8; ++c) {
+            const double piv = __shfl_sync(0xffffffffu, ar[c], c);
+            if (!(piv > 0.0)) bad = true;
+            const double inv = rsqrt(piv);
+            double lr = ar[c] * inv, li = ai[c] * inv;
+            if (r == c) { lr = piv * inv; li = 0.0; }
+            if (r < c) { lr = 0.0; li = 0.0; }
+            if (act) {
+                Ar[r * kLdBlk + c] = lr; Ai[r * kLdBlk + c] = li;
+                if (r == c) Vr[c * kLdBlk + c] = inv;
+            }
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2) {
-            const double yr = __shfl_sync(0xffffffffu, lr, c2), yi = __shfl_sync(0xffffffffu, li, c2);
-            ar[c2] -= lr * yr + li * yi;     // a[r][c2] -= l[r][c] conj(l[c2][c])
-            ai[c2] -= li * yr - lr * yi;
+            for (int c2 = c + 1; c2 < 8; ++c2) {
+                const double yr = __shfl_sync(0xffffffffu, lr, c2), yi = __shfl_sync(0xffffffffu, li, c2);
+                ar[c2] -= lr * yr + li * yi;     // a[r][c2] -= l[r][c] conj(l[c2][c])
+                ai[c2] -= li * yr - lr * yi;
+            }
         }
-    }
-    if (act) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { Ar[r * kLdBlk + c] = ar[c]; Ai[r * kLdBlk + c] = ai[c]; }
     }
     __syncwarp();
-    // inverse, lane = column c:  V[q][c] = (delta_qc - sum_{p<q} L[q][p] V[p][c]) / L[q][q]   (L: broadcast reads)
-    double vr[8], vi[8];
+    {
+        // inverse, lane = column c:  V[q][c] = (delta_qc - sum_{p<q} L[q][p] V[p][c]) / L[q][q]   (L, 1/L[q][q]: broadcast reads)
+        double vr[8], vi[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        double sr = 0.0, si = 0.0;
+        for (int q = 0; q < 8; ++q) {
+            double sr = 0.0, si = 0.0;
 #pragma unroll
-        for (int p = 0; p < q; ++p) {
-            const double lr = Ar[q * kLdBlk + p], li = Ai[q * kLdBlk + p];
-            sr += lr * vr[p] - li * vi[p];
-            si += lr * vi[p] + li * vr[p];
+            for (int p = 0; p < q; ++p) {
+                const double lr = Ar[q * kLdBlk + p], li = Ai[q * kLdBlk + p];
+                sr += lr * vr[p] - li * vi[p];
+                si += lr * vi[p] + li * vr[p];
+            }
+            const double dinv = Vr[q * kLdBlk + q];
+            vr[q] = r < q ? -sr * dinv : (r == q ? dinv : 0.0);
+            vi[q] = r < q ? -si * dinv : 0.0;
         }
-        vr[q] = r < q ? -sr * dinv[q] : (r == q ? dinv[q] : 0.0);
-        vi[q] = r < q ? -si * dinv[q] : 0.0;
-    }
-    if (act) {
+        __syncwarp();  // every lane has read the parked reciprocals
+        if (act) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { Vr[q * kLdBlk + r] = vr[q]; Vi[q * kLdBlk + r] = vi[q]; }
+            for (int q = 0; q < 8; ++q) { Vr[q * kLdBlk + r] = vr[q]; Vi[q * kLdBlk + r] = vi[q]; }
+        }
     }
     __syncwarp();
     return bad;

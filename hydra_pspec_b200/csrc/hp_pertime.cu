@@ -240,7 +240,23 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
         __syncthreads();
 
         // ---- backward substitution  x_i = V_ii^H (y_i - sum_{j>i} L_ji^H x_j), in place in y
+        // The scratch slots of all CTAs (245 MB at configs[2]) do not stay in L2, so the blocks of a row would be
+        // fetched from DRAM by a chain of dependent loads.  Each row therefore starts by asking L2 for the blocks of
+        // the NEXT row (prefetch.global.L2, one 128-byte line per thread and step): by the time they are needed the
+        // loads hit L2.
+        auto prefetch_row = [&](int i) {   // V_ii and L_ji, j > i
+            const char* vb = reinterpret_cast<const char*>(Vp + (size_t)i * kLBlkDoubles);
+            for (int off = tid * 128; off < (int)(kLBlkDoubles * 8); off += kPT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + off));
+            for (int j = i + 1; j < nblk; ++j) {
+                const char* lb = reinterpret_cast<const char*>(Lp + blk_index(j, i) * kLBlkDoubles);
+                for (int off = tid * 128; off < (int)(kLBlkDoubles * 8); off += kPT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(lb + off));
+            }
+        };
+        prefetch_row(nblk - 1);
         for (int i = nblk - 1; i >= 0; --i) {
+            if (i > 0) prefetch_row(i - 1);
             double pr = 0.0, pi = 0.0;
             for (int j = i + 1 + warp; j < nblk; j += 16) {
                 const double* Lr = Lp + blk_index(j, i) * kLBlkDoubles + lane;
