@@ -14,6 +14,7 @@
 #include "hp_math.h"
 #include "hp_mma.cuh"
 #include "hp_diag.cuh"
+#include <cstdlib>
 
 namespace hp {
 
@@ -283,13 +284,122 @@ __global__ void __launch_bounds__(kCT) k_chol(CholArgs a) {
     if (tid == 0 && a.info) a.info[sys] = bad;
 }
 
+// ------------------------------------------------------------------------------------------
+// k_chol_col: the same factorisation, one block column per launch and one CTA per block.
+//   diag = 1: grid (1, nsys)            block (k, k): update, factorisation + inverse, writes L_kk and V_kk
+//   diag = 0: grid (nblk - k - 1, nsys) block (i, k), i = k + 1 + blockIdx.x: update, L_ik = C V_kk^H
+// Two launches per block column instead of one CTA walking the whole matrix: the blocks of a column are
+// independent, so a column's work spreads over (nblk - k) x nsys CTAs, two per SM.  With few systems resident
+// (32 per GPU at BASELINE.json configs[4], 33 block columns) k_chol leaves 116 of 148 SMs idle for the whole
+// factorisation; the critical path of the column version is one block per column.
+struct CholColSmem {
+    double A[2][kLBlkDoubles];   // L_ij (double buffered); A[0] also holds the block being finished
+    double B[2][kLBlkDoubles];   // L_kj (double buffered)
+    double V[kLBlkDoubles];      // V_kk
+};
+
+__global__ void __launch_bounds__(kCT, 2) k_chol_col(CholArgs a, int k, int diag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CholColSmem& s = *reinterpret_cast<CholColSmem*>(smem_raw);
+    const int sys = blockIdx.y;
+    const int i = diag ? k : k + 1 + (int)blockIdx.x;
+    const int nblk = a.nblk, Np = nblk * 32;
+    const double* Gp = a.Gp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
+    double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    double* Linvp = a.Linvp + (size_t)sys * nblk * kLBlkDoubles;
+    const double* lam = a.lam + (size_t)sys * Np;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int ti = warp >> 2, tj = warp & 3;
+    double* Ar = s.A[0];
+    double* Ai = s.A[0] + kLPlane;
+    double* Vr = s.V;
+    double* Vi = s.V + kLPlane;
+
+    double cr[1][1][2], ci[1][1][2], P3m[3][1][1][2];
+    warp_zero<1, 1>(cr, ci);
+    warp_zero3m<1, 1>(P3m);
+    if (!diag) load_block_async_ct(s.V, Linvp + (size_t)k * kLBlkDoubles);   // rides with the first operand stage
+    if (k > 0) {
+        load_block_async_ct(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
+        if (!diag) load_block_async_ct(s.B[0], Lp + blk_index(k, 0) * kLBlkDoubles);
+    }
+    cp_async_commit();
+    for (int j = 0; j < k; ++j) {
+        const int st = j & 1;
+        if (j + 1 < k) {
+            load_block_async_ct(s.A[st ^ 1], Lp + blk_index(i, j + 1) * kLBlkDoubles);
+            if (!diag) load_block_async_ct(s.B[st ^ 1], Lp + blk_index(k, j + 1) * kLBlkDoubles);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* ar = s.A[st];
+        const double* br = diag ? s.A[st] : s.B[st];
+        warp_zgemm3m<1, 1, false, false, true, true>(P3m, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                     br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk, kLdBlk, 32);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // V_kk landed (k = 0: nothing else waited for it); A[0] is free
+    warp_zgemm3m_finish<1, 1, false, true>(P3m, cr, ci);
+    const double* Gb = Gp + blk_index(i, k) * kBlkDoubles;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+        int gi = 32 * i + r, gj = 32 * k + c;
+        double sc = lam[gi] * lam[gj];
+        double vr = sc * Gb[r * 32 + c], vi = sc * Gb[1024 + r * 32 + c];
+        if (gi == gj && (gi < a.n || gi >= a.N)) vr += 1.0;
+        Ar[r * kLdBlk + c] = vr - cr[0][0][e];
+        Ai[r * kLdBlk + c] = vi - ci[0][0][e];
+    }
+    __syncthreads();
+    if (diag) {
+        const bool bad = diag_chol_inverse_block(Ar, Ai, Vr, Vi, tid, kCT);
+        __syncthreads();
+        double* Lb = Lp + blk_index(k, k) * kLBlkDoubles;
+        double* Vb = Linvp + (size_t)k * kLBlkDoubles;
+        for (int e = tid; e < kLBlkDoubles; e += kCT) {
+            Lb[e] = s.A[0][e];
+            Vb[e] = s.V[e];
+        }
+        if (bad && tid == 0 && a.info) atomicMax(a.info + sys, k + 1);
+    } else {
+        double dr[1][1][2], di[1][1][2], Q3m[3][1][1][2];
+        warp_zero3m<1, 1>(Q3m);
+        warp_zgemm3m<1, 1, false, false, true, true>(Q3m, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk, Vr + 8 * tj * kLdBlk,
+                                                     Vi + 8 * tj * kLdBlk, kLdBlk, 32);
+        warp_zgemm3m_finish<1, 1, false, true>(Q3m, dr, di);
+        double* Lb = Lp + blk_index(i, k) * kLBlkDoubles;
+        int r = 8 * ti + g, c = 8 * tj + 2 * q;
+        *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
+        *reinterpret_cast<double2*>(Lb + kLPlane + r * kLdBlk + c) = make_double2(di[0][0][0], di[0][0][1]);
+    }
+}
+
 void launch_chol(const CholArgs& a, cudaStream_t st) {
     static bool attr_set = false;
+    static int mode = -1;   // HP_CHOL_COLUMNS = 0 (one CTA per system), 1 (one launch pair per block column), unset: auto
     if (!attr_set) {
         cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
+        cudaFuncSetAttribute(k_chol_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholColSmem));
+        const char* ev = getenv("HP_CHOL_COLUMNS");
+        mode = ev ? atoi(ev) : -1;
         attr_set = true;
     }
-    k_chol<<<a.nsys, kCT, sizeof(CholSmem), st>>>(a);
+    const bool columns = mode >= 0 ? mode == 1 : true;
+    if (!columns) {
+        k_chol<<<a.nsys, kCT, sizeof(CholSmem), st>>>(a);
+        return;
+    }
+    if (a.info) cudaMemsetAsync(a.info, 0, sizeof(int) * a.nsys, st);
+    for (int k = 0; k < a.nblk; ++k) {
+        k_chol_col<<<dim3(1, a.nsys), kCT, sizeof(CholColSmem), st>>>(a, k, 1);
+        if (k + 1 < a.nblk) k_chol_col<<<dim3(a.nblk - k - 1, a.nsys), kCT, sizeof(CholColSmem), st>>>(a, k, 0);
+    }
 }
 
 // ==========================================================================================
