@@ -865,6 +865,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         y.B = Wd; y.sBk = 1; y.sBj = e->Np; y.bsB = NN;
         y.C = Yb; y.sCi = e->Np; y.sCj = 1; y.bsC = TN;
         y.M = e->T; y.N = e->Np; y.K = e->Np; y.alpha = 1.0; y.batch = sb.nc;
+        y.tri = 1;           // B[k = j][col = i] = W[i][j] = 0 for j > i
         hp::launch_zgemm(y, sb.st);
         int nl = 4;
         if (philox) {
@@ -877,6 +878,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         x.B = Wd; x.sBk = e->Np; x.sBj = 1; x.bsB = NN; x.conjB = 1;
         x.C = X; x.sCi = e->Np; x.sCj = 1; x.bsC = TN;
         x.M = e->T; x.N = e->Np; x.K = e->Np; x.alpha = 1.0; x.batch = sb.nc;
+        x.tri = 2;           // B[k = j][col = i] = conj(W[j][i]) = 0 for j < i
         hp::launch_zgemm(x, sb.st);
         hp::launch_colsumsq(X, OFFS(e->Ppart, (size_t)e->ntiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
         ++nl;

@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(256) k_zgemm(ZgemmArgs a) {
     const bool a_kfast = a.sAk <= a.sAi;
     const bool b_jfast = a.sBj <= a.sBk;
     const double sgnA = a.conjA ? -1.0 : 1.0, sgnB = a.conjB ? -1.0 : 1.0;
-    for (int k0 = 0; k0 < a.K; k0 += ZG_BK) {
+    // triangular B: skip the K range where this column tile of B is structurally zero
+    //   tri = 1: B[k][j] = 0 for k > j  (k < j0 + BN suffices);   tri = 2: B[k][j] = 0 for k < j  (start at k = j0)
+    const int kbeg = a.tri == 2 ? (j0 / ZG_BK) * ZG_BK : 0;
+    const int kend = a.tri == 1 ? (a.K < j0 + ZG_BN ? a.K : j0 + ZG_BN) : a.K;
+    for (int k0 = kbeg; k0 < kend; k0 += ZG_BK) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             int e = tid + 256 * r;

@@ -35,6 +35,7 @@ struct ZgemmArgs {
     int conjA, conjB, accumulate;
     double alpha;
     int batch;
+    int tri;   // 0: dense B;  1: B[k][j] = 0 for k > j;  2: B[k][j] = 0 for k < j  (the zero K range of a column tile is skipped)
 };
 void launch_zgemm(const ZgemmArgs& a, cudaStream_t st);
 
