@@ -843,9 +843,9 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     ca.Gp = OFFS(b.Gp, tri * hp::kBlkDoubles); ca.lam = OFFS(e->lam, Np); ca.Lp = OFFS(e->Lp, tri * hp::kLBlkDoubles);
     ca.Linvp = OFFS(e->Linvp, (size_t)e->nblk * hp::kLBlkDoubles); ca.info = e->info + sb.c0;
     ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = sb.nc;
-    hp::launch_chol(ca, sb.st);
+    const int nchol = hp::launch_chol(ca, sb.st);
     hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), e->nblk, sb.nc, sb.st);
-    e->prof_end(CLS_CHOL, 2, sb.st);
+    e->prof_end(CLS_CHOL, nchol + 1, sb.st);
 
     if (e->big_solve) {
         // x = W^H (W r + xi) as two dense products (W unpacked to a dense lower-triangular matrix): the path for

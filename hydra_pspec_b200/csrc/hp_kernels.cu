@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kCT, 2) k_chol_col(CholArgs a, int k, int diag
     }
 }
 
-void launch_chol(const CholArgs& a, cudaStream_t st) {
+int launch_chol(const CholArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     static int mode = -1;   // HP_CHOL_COLUMNS = 0 (one CTA per system), 1 (one launch pair per block column), unset: auto
     if (!attr_set) {
@@ -397,13 +397,14 @@ void launch_chol(const CholArgs& a, cudaStream_t st) {
     const bool columns = mode >= 0 ? mode == 1 : true;
     if (!columns) {
         k_chol<<<a.nsys, kCT, sizeof(CholSmem), st>>>(a);
-        return;
+        return 1;
     }
     if (a.info) cudaMemsetAsync(a.info, 0, sizeof(int) * a.nsys, st);
     for (int k = 0; k < a.nblk; ++k) {
         k_chol_col<<<dim3(1, a.nsys), kCT, sizeof(CholColSmem), st>>>(a, k, 1);
         if (k + 1 < a.nblk) k_chol_col<<<dim3(a.nblk - k - 1, a.nsys), kCT, sizeof(CholColSmem), st>>>(a, k, 0);
     }
+    return 2 * a.nblk - 1;
 }
 
 // ==========================================================================================

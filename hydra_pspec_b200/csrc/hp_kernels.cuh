@@ -55,7 +55,7 @@ struct CholArgs {
     int* info;             // [nsys]  0 ok, k+1 = non-positive pivot in block column k
     int nblk, n, N, nsys;
 };
-void launch_chol(const CholArgs& a, cudaStream_t st);
+int launch_chol(const CholArgs& a, cudaStream_t st);   // returns the number of kernel launches (1, or 2 nblk - 1 in column mode)
 // W = L^-1 in the same padded block layout as L ([nsys][tri_blocks][2304])
 void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, int nsys, cudaStream_t st);
 
