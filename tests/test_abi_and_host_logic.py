@@ -123,3 +123,12 @@ def test_noise_model_split():
     assert pspec._noise_model(N, fl, 4, False)[2] is None
     with pytest.raises(NotImplementedError):
         pspec._noise_model(np.zeros((5, 4, 4)), fl, 4, False)
+
+
+def test_numa_binding_is_best_effort():
+    """No GPU / no topology here: the helper must return None and leave the affinity alone."""
+    import os
+    from hydra_pspec_b200 import _lib
+    before = os.sched_getaffinity(0)
+    assert _lib.bind_to_device_numa(0) is None
+    assert os.sched_getaffinity(0) == before

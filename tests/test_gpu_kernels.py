@@ -83,3 +83,34 @@ def test_chol_reports_indefinite():
     info = np.zeros(1, dtype=np.int32)
     L.check(L.lib().hp_test_chol_solve(n, m, T, L.ptr(G), L.ptr(lam), L.ptr(Rfix), None, 0, None, L.ptr(X), L.ptr(info)))
     assert info[0] != 0
+
+
+def test_arena_cache_and_deferred_setup_survive_engine_churn():
+    """Engines of different sizes created and destroyed back to back (the drop-in functions do this once per
+    baseline): the cached device arena must be reused / replaced correctly and results must not depend on it."""
+    import os
+    from hydra_pspec_b200 import _lib, pspec
+    rng = np.random.default_rng(0)
+
+    def run(nt, nf, nm, nch):
+        F = np.linalg.qr(rng.standard_normal((nf, nm)) + 1j * rng.standard_normal((nf, nm)))[0]
+        vis = rng.standard_normal((nt, nf)) + 1j * rng.standard_normal((nt, nf))
+        eng = pspec.GibbsEngine(nch, nt, nf, nm, max_iters=3, rng="philox", keep=(), seed=5)
+        for c in range(nch):
+            eng.load_chain(c, vis * (c + 1), np.ones(nf, bool), F, np.ones(nf), np.ones(nf))
+        eng.run(3)
+        out = np.stack([eng.signal_ps(c) for c in range(nch)])
+        eng.close()
+        return vis, F, out
+
+    np.random.seed(0)
+    sizes = [(16, 32, 2, 3), (40, 96, 6, 5), (8, 16, 1, 1), (40, 96, 6, 5)]
+    outs = []
+    for s in sizes:
+        rng = np.random.default_rng(sum(s))
+        outs.append(run(*s)[2])
+    assert np.array_equal(outs[1], outs[3])          # same problem, arena reused after a smaller engine
+    _lib.lib().hp_release_cached_memory()
+    rng = np.random.default_rng(sum(sizes[1]))
+    assert np.array_equal(run(*sizes[1])[2], outs[1])  # and after the cache has been dropped
+    assert all(np.all(np.isfinite(o)) for o in outs)
