@@ -370,4 +370,20 @@ class UVH5Data:
 
 
 def read_uvh5(path):
+    """One file, or a list of files with the same frequency / polarisation axes concatenated along the
+    baseline-time axis (what ``UVData.read([...])`` does for files that split an observation in time)."""
+    if isinstance(path, (list, tuple)):
+        parts = [UVH5Data(p) for p in path]
+        uv = parts[0]
+        for o in parts[1:]:
+            if o.freq_array.shape != uv.freq_array.shape or not np.allclose(o.freq_array, uv.freq_array) \
+                    or list(o.polarization_array) != list(uv.polarization_array):
+                raise ValueError("uvh5 files to concatenate must share their frequency and polarisation axes")
+        uv.data_array = np.concatenate([o.data_array for o in parts])
+        uv.flag_array = np.concatenate([o.flag_array for o in parts])
+        uv.nsample_array = np.concatenate([o.nsample_array for o in parts])
+        uv.ant_1_array = np.concatenate([o.ant_1_array for o in parts])
+        uv.ant_2_array = np.concatenate([o.ant_2_array for o in parts])
+        uv.time_array = np.concatenate([o.time_array for o in parts])
+        return uv
     return UVH5Data(path)

@@ -91,6 +91,9 @@ int hp_engine_destroy(hp_engine* e);
  *   lam0sq     [Nfreqs] eigenvalues of S_initial in that basis; for a delay-diagonal S_initial
  *              these are diag(U S U^H) with U = fourier_operator(Nfreqs)/sqrt(Nfreqs)
  *   ps_prior   [2][Nfreqs] (pspec.py:84-86; [0] upper, [1] lower; 0 = no prior)
+ * The host arrays may be reused as soon as the call returns.  With diagonal noise and time-invariant flags the Gram
+ * matrix and right-hand-side products of the loaded chains are built lazily, for all pending chains in one batched
+ * launch, by the first hp_engine_run / hp_engine_run_to_host / hp_engine_gcr / hp_engine_set_draws that follows.
  */
 int hp_engine_load_chain(hp_engine* e, int chain, const double* vis, const uint8_t* flags, const double* fgmodes,
                          const double* ninv_diag, const double* basis0, const double* lam0sq,

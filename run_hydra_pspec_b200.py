@@ -146,9 +146,7 @@ def read_visibilities(file_paths, ant_str, freq_range):
         get = lambda ap: (uvd.get_data(ap + ("xx",), force_copy=True), uvd.get_flags(ap + ("xx",)))  # noqa: E731
         return uvd.get_antpairs(), freqs, get
     from hydra_pspec_b200.uvh5 import read_uvh5
-    if len(file_paths) != 1:
-        raise NotImplementedError("the built-in uvh5 reader takes one file; install pyuvdata to concatenate several")
-    uvd = read_uvh5(file_paths[0])
+    uvd = read_uvh5(file_paths[0] if len(file_paths) == 1 else list(file_paths))
     keep = None
     if freq_range:
         keep = utils.filter_freqs(freq_range, uvd.freq_array / 1e6) * 1e6

@@ -76,6 +76,17 @@ def test_uvh5_select_conjugate_and_frequencies(td):
     assert uv.get_antpairs() == []
 
 
+def test_uvh5_concatenates_files_along_time(td):
+    from hydra_pspec_b200.uvh5 import read_uvh5
+    one = read_uvh5(td / "vis-eor-fgs.uvh5")
+    two = read_uvh5([td / "vis-eor-fgs.uvh5", td / "vis-eor-fgs.uvh5"])
+    assert two.data_array.shape == (406, 120, 4) and two.get_antpairs() == [(0, 1)]
+    d1, d2 = one.get_data((0, 1, "xx")), two.get_data((0, 1, "xx"))
+    assert d2.shape == (406, 120)
+    np.testing.assert_array_equal(d2[0::2], d1)    # rows are returned in time order (stable): each time twice
+    np.testing.assert_array_equal(d2[1::2], d1)
+
+
 def test_filter_freqs():
     from hydra_pspec_b200 import utils
     f = np.linspace(100, 120, 21)
