@@ -11,7 +11,8 @@ sys.path.insert(0, str(ROOT / "tests" / "golden"))
 import run_hydra_pspec_b200 as drv  # noqa: E402
 from make_golden_testdata import driver_argv  # noqa: E402
 
-td = ROOT / "tests" / "golden" / "testdata"
+from testdata_fixture import materialize  # noqa: E402
+td = materialize(tempfile.mkdtemp())
 for rng in ("numpy", "philox"):
     for rep in range(2):
         with tempfile.TemporaryDirectory() as out:

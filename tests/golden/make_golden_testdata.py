@@ -5,8 +5,8 @@ its own `test_data` (vis-eor-fgs.uvh5 + 0-1/*.npy, config.yaml parameters), 3 it
 pyuvdata is not installed here, so the visibilities are read with this repo's uvh5 reader and
 assembled by this repo's driver functions (the part of run-hydra-pspec.py that precedes the hot
 path); everything from `gibbs_sample_with_fg` down is the reference's code.  Build container only.
-Output: tests/golden/chain_T_testdata_driver.npz.  The input files under tests/golden/testdata/ are
-copies of the reference's test_data files (data, not source).
+Output: tests/golden/chain_T_testdata_driver.npz.  The inputs under tests/golden/testdata/ are the reference's
+test_data files (data, not source), stored compressed; tests/golden/testdata_fixture.py unpacks them.
 """
 import sys
 import warnings
@@ -33,7 +33,9 @@ def driver_argv(td, out_dir):
 
 
 def main():
-    td = HERE / "testdata"
+    import tempfile
+    from testdata_fixture import materialize
+    td = materialize(tempfile.mkdtemp())
     _, args = drv.parse_args(driver_argv(td, "/tmp/unused"))
     antpairs, freqs, get = drv.read_visibilities([Path(p) for p in args.file_paths], args.ant_str, args.freq_range)
     bls = drv.assemble_baselines(args, antpairs, freqs, get, Path("/tmp/unused"))

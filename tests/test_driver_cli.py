@@ -14,11 +14,13 @@ import run_hydra_pspec_b200 as drv
 
 sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
 from make_golden_testdata import driver_argv, NITER  # noqa: E402
+from testdata_fixture import materialize  # noqa: E402
 
 
 @pytest.fixture(scope="module")
-def td(golden_dir):
-    return golden_dir / "testdata"
+def td(tmp_path_factory):
+    """The reference's test_data layout, unpacked from the compressed fixtures."""
+    return materialize(tmp_path_factory.mktemp("testdata"))
 
 
 def test_config_file_and_cli_precedence(tmp_path, td):
