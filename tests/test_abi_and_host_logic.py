@@ -132,3 +132,29 @@ def test_numa_binding_is_best_effort():
     before = os.sched_getaffinity(0)
     assert _lib.bind_to_device_numa(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_header_compiles_as_c_and_links(tmp_path):
+    """include/hydra_pspec_b200.h is a plain C header: a C translation unit that takes the address of every declared
+    entry point must compile with gcc and link against the shared library (no compute call is made)."""
+    import re
+    import shutil
+    import subprocess
+    from pathlib import Path
+    from hydra_pspec_b200 import _lib
+    if shutil.which("gcc") is None or not _lib.LIB_PATH.exists():
+        import pytest
+        pytest.skip("gcc or the built library is missing")
+    root = Path(__file__).resolve().parent.parent
+    header = (root / "include" / "hydra_pspec_b200.h").read_text()
+    names = sorted(set(re.findall(r"\b(hp_[a-z_0-9]+)\s*\(", header)))
+    assert "hp_engine_create" in names and "hp_release_cached_memory" in names and len(names) >= 20
+    src = tmp_path / "abi.c"
+    src.write_text('#include "hydra_pspec_b200.h"\n#include <stdio.h>\nint main(void) {\n  void* p[] = {' +
+                   ", ".join(f"(void*){n}" for n in names) +
+                   '};\n  printf("%d %s\\n", (int)(sizeof p / sizeof p[0]), hp_version());\n  return 0;\n}\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(root / "include"), str(src), "-o", str(exe),
+                    "-L", str(_lib.LIB_PATH.parent), "-lhydra_pspec_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and "hydra_pspec_b200" in " ".join(out[1:])
