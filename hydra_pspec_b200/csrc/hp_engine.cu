@@ -234,6 +234,7 @@ struct hp_engine {
     double *wd = nullptr, *w = nullptr, *ninvd = nullptr, *ni = nullptr, *nu = nullptr, *Ft = nullptr, *prior = nullptr;
     double *Lp = nullptr, *Linvp = nullptr, *Wp = nullptr;
     double *wT = nullptr, *Hpt = nullptr, *niT = nullptr, *Bsel = nullptr, *ptScratch = nullptr;  // per-time flags
+    int* ptSame = nullptr;   // [C][Tp]: flags of time t equal those of t - 1
     int pt_ctas = 0;
     int gd_slots = 1;
     std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
@@ -450,6 +451,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     if (cfg->time_flags) {
         e->pt_ctas = hp::pt_grid(e->C, e->T);
         ap.want(&e->wT, C * Tp * n);
+        ap.want(&e->ptSame, C * Tp);
         ap.want(&e->Hpt, 2 * C * Tp * (1 + m) * Np);
         ap.want(&e->niT, Tp * n);
         ap.want(&e->Bsel, 2 * n * (1 + m));
@@ -638,7 +640,12 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     CU_TRY(cudaMemcpyAsync(e->w + (size_t)c * n, wv.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(e->ninvd + (size_t)c * n, ninv_diag, n * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(wd, vis, 2 * (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (pt) CU_TRY(cudaMemcpyAsync(e->wT + (size_t)c * Tp * n, wtv.data(), (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (pt) {
+        CU_TRY(cudaMemcpyAsync(e->wT + (size_t)c * Tp * n, wtv.data(), (size_t)T * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        std::vector<int> same(Tp, 0);
+        for (int t = 1; t < T; ++t) same[t] = std::memcmp(flags + (size_t)t * n, flags + (size_t)(t - 1) * n, n) == 0 ? 1 : 0;
+        CU_TRY(cudaMemcpyAsync(e->ptSame + (size_t)c * Tp, same.data(), (size_t)Tp * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
     // (wv / wtv are pageable locals: cudaMemcpyAsync has staged them before it returns; `vis` may be page-locked and is
     //  only guaranteed consumed by the stream synchronisation at the end of this function)
     if (pt) k_mask_elem<<<nblocks((long long)T * n), 256, 0, st>>>(wd, e->wT + (size_t)c * Tp * n, (long long)T * n);
@@ -827,6 +834,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         pa.H = OFFS(e->Hpt, 2 * Tp * (1 + m) * Np); pa.lam = OFFS(e->lam, Np); pa.Rfix = OFFS(b.Rfix, 2 * Tp * Np);
         pa.wa = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
         pa.X = OFFS(e->X, 2 * Tp * Np);
+        pa.same_prev = OFFS(e->ptSame, Tp);
         pa.scratch = e->ptScratch + (size_t)slot0 * hp::pt_scratch_doubles_per_cta(e->nblk);
         pa.info = e->info + sb.c0;
         pa.nblk = e->nblk; pa.n = e->n; pa.m = e->m; pa.N = e->N; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc;

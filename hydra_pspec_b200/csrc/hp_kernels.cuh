@@ -111,6 +111,7 @@ struct PtArgs {
     const double* wa;      // [nsys][Tp][Np] complex or null
     double* X;             // [nsys][Tp][Np] complex: solution [ytilde ; f]
     double* scratch;       // [grid][pt_scratch_doubles_per_cta]: factor L and the inverses of its diagonal blocks
+    const int* same_prev;  // [nsys][Tp] or null: 1 = the flags of time t equal those of t - 1 (the factor is re-used)
     int* info;             // [nsys], zeroed by the caller; atomicMax(k + 1) on a non-positive pivot in block column k
     int nblk, n, m, N, T, Tp, nsys;
     int philox_wa;

@@ -84,8 +84,16 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
 
-    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    // Every CTA walks a contiguous range of (system, time) pairs.  Consecutive times of a baseline often carry the
+    // same flag vector (persistent RFI channels): `same_prev[sys][t]` marks a time whose mask equals that of t - 1,
+    // and such a pair re-uses the factor that is already in the CTA's scratch slot: only the two substitutions
+    // are done (the time-invariant case of the reference, one factorisation for all times, is the limit of this).
+    const long long chunk = (nitems + gridDim.x - 1) / gridDim.x;
+    const long long item_begin = (long long)blockIdx.x * chunk;
+    const long long item_end = item_begin + chunk < nitems ? item_begin + chunk : nitems;
+    for (long long item = item_begin; item < item_end; ++item) {
         const int sys = (int)(item / a.T), t = (int)(item % a.T);
+        const bool reuse = item > item_begin && t > 0 && a.same_prev && a.same_prev[(size_t)sys * a.Tp + t] != 0;
         const double2* H = reinterpret_cast<const double2*>(a.H) + ((size_t)sys * a.Tp + t) * (size_t)(1 + m) * Np;
         const double* lam = a.lam + (size_t)sys * Np;
         const double2* R = reinterpret_cast<const double2*>(a.Rfix) + ((size_t)sys * a.Tp + t) * Np;
@@ -103,6 +111,47 @@ __global__ void __launch_bounds__(kPT, 2) k_pt_cholsolve(PtArgs a) {
         int bad = 0;
         PT_T(0);  // item prologue
 
+        if (reuse) {
+            // ---- forward substitution only, y_k = V_kk (r_k - sum_{j<k} L_kj y_j), with the factor of the previous time
+            {   // start the whole factor on its way from DRAM to L2 (1 MB: 16 lines per thread)
+                const char* base = reinterpret_cast<const char*>(Lp);
+                const size_t bytes = (tri + nblk) * (size_t)kLBlkDoubles * 8;
+                for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)kPT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            }
+            for (int k = 0; k < nblk; ++k) {
+                double f0r = 0.0, f0i = 0.0, f1r = 0.0, f1i = 0.0;
+                for (int j = 0; j < k; ++j) {
+                    const double* Lb = Lp + blk_index(k, j) * kLBlkDoubles + mr * kLdBlk + 2 * ms;
+                    const double lr0 = __ldcg(Lb), lr1 = __ldcg(Lb + 1), li0 = __ldcg(Lb + kLPlane), li1 = __ldcg(Lb + kLPlane + 1);
+                    const double2 vr = *reinterpret_cast<const double2*>(yr + 32 * j + 2 * ms);
+                    const double2 vi = *reinterpret_cast<const double2*>(yi + 32 * j + 2 * ms);
+                    f0r += lr0 * vr.x - li0 * vi.x; f0i += lr0 * vi.x + li0 * vr.x;
+                    f1r += lr1 * vr.y - li1 * vi.y; f1i += lr1 * vi.y + li1 * vr.y;
+                }
+                double fr = f0r + f1r, fi = f0i + f1i;
+                for (int o = 8; o > 0; o >>= 1) {
+                    fr += __shfl_xor_sync(0xffffffffu, fr, o);
+                    fi += __shfl_xor_sync(0xffffffffu, fi, o);
+                }
+                if (ms == 0) { s.tv[mr] = yr[32 * k + mr] - fr; s.tv[32 + mr] = yi[32 * k + mr] - fi; }
+                __syncthreads();
+                {
+                    const double* Vb = Vp + (size_t)k * kLBlkDoubles + mr * kLdBlk + 2 * ms;
+                    const double vr0 = __ldcg(Vb), vr1 = __ldcg(Vb + 1), vi0 = __ldcg(Vb + kLPlane), vi1 = __ldcg(Vb + kLPlane + 1);
+                    const double2 xr = *reinterpret_cast<const double2*>(s.tv + 2 * ms);
+                    const double2 xi = *reinterpret_cast<const double2*>(s.tv + 32 + 2 * ms);
+                    double pr = vr0 * xr.x - vi0 * xi.x + vr1 * xr.y - vi1 * xi.y;
+                    double pi = vr0 * xi.x + vi0 * xr.x + vr1 * xi.y + vi1 * xr.y;
+                    for (int o = 8; o > 0; o >>= 1) {
+                        pr += __shfl_xor_sync(0xffffffffu, pr, o);
+                        pi += __shfl_xor_sync(0xffffffffu, pi, o);
+                    }
+                    if (ms == 0) { yr[32 * k + mr] = pr; yi[32 * k + mr] = pi; }
+                }
+                __syncthreads();
+            }
+        } else
         for (int k = 0; k < nblk; ++k) {
             double fr = 0.0, fi = 0.0;  // partial of sum_{j<k} L_kj y_j for row mr (columns 2 ms, 2 ms + 1)
             for (int i = k; i < nblk; ++i) {

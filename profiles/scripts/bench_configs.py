@@ -1,6 +1,7 @@
 """Throughput of the BASELINE.json configurations that are not the bench.py headline.
 
-    python profiles/scripts/bench_configs.py 2 [baselines]   configs[2]: Nfreq=256 Ntimes=512 Nfg=16, per-time RFI flags
+    python profiles/scripts/bench_configs.py 2 [baselines] [hold]   configs[2]: Nfreq=256 Ntimes=512 Nfg=16, per-time RFI flags
+                                                              (hold > 1: every random mask is kept for `hold` consecutive times)
     python profiles/scripts/bench_configs.py 4 [baselines]   configs[4]: Nfreq=1024 Nfg=64 Ntimes=1024, dense noise covariance
 
 Device Philox draws, exact solves, signal_ps + ln_post kept (like bench.py's `value`).  Prints one JSON line."""
@@ -37,7 +38,9 @@ for c in range(B):
     vis, flags, F, ninv_diag, lam0sq = make_baseline(c, nt, nf, nm)
     if cfg == 2:
         fl = np.broadcast_to(flags, (nt, nf)).copy()
-        fl &= np.random.default_rng(1000 + c).random((nt, nf)) > 0.05
+        hold = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+        rnd = np.random.default_rng(1000 + c).random(((nt + hold - 1) // hold, nf)) > 0.05
+        fl &= np.repeat(rnd, hold, axis=0)[:nt]
         eng.load_chain(c, vis, fl, F, ninv_diag, lam0sq)
     else:
         eng.load_chain(c, vis, flags, F, np.real(np.diagonal(Ninv)).copy(), lam0sq, ninv_dense=Ninv)

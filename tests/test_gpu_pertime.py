@@ -153,3 +153,23 @@ def test_per_time_fully_flagged_integration_is_refused():
     flags[2, :] = False
     with pytest.raises(np.linalg.LinAlgError):
         pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=1, verbose=False)
+
+
+@pytest.mark.parametrize("hold", [2, 5, 100])
+def test_per_time_repeated_masks_reuse_the_factor(hold):
+    """Consecutive times with identical flag vectors re-use the factorisation held in the CTA's scratch slot
+    (forward + backward substitution only): results must not depend on it."""
+    from hydra_pspec_b200 import pspec
+    nt = 23
+    vis, flags, S0, F, Ninv, prior = make_case(nt, 64, 6, 0.15, 40 + hold)
+    flags = np.repeat(flags[::hold], hold, axis=0)[:nt]     # every mask held for `hold` times (100: one mask for all)
+    ref = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=7, solver="direct")
+    out = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=7, verbose=False)
+    for o, r, k in zip(out[:6], ref, KEYS):
+        assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
+    # many chains in one engine: ranges of (chain, time) pairs per CTA straddle chain boundaries
+    bls = [dict(vis=vis * (1 + 0.1 * c), flags=flags, S_initial=S0, fgmodes=F, Ninv=Ninv, ps_prior=prior) for c in range(7)]
+    outs = pspec.gibbs_sample_batch(bls, Niter=2, seed=7, rng="numpy", solver="exact")
+    one = pspec.gibbs_sample_with_fg(bls[3]["vis"], flags, S0, F, Ninv, prior, Niter=2, seed=7, verbose=False)
+    for o, r, k in zip(outs[3][:6], one[:6], KEYS):
+        assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
