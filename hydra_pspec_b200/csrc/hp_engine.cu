@@ -800,7 +800,9 @@ static void enqueue_dense_lnp1(hp_engine* e, const Sub& sb) {
     e->prof_begin(CLS_TRANSFORM, sb.st);
     hp::ZgemmArgs y{};
     y.A = OFFS(e->Rm, 2 * Tp * n); y.sAi = e->n; y.sAk = 1; y.bsA = (long long)e->Tp * e->n;
-    y.B = OFFS(e->NiD, 2 * n * n); y.sBk = 1; y.sBj = e->n; y.bsB = (long long)e->n * e->n;
+    // Y = R conj(Ni) (row-major operand, coalesced) instead of R Ni^T: identical for a Hermitian Ni, and only the real part
+    // of sum_j conj(R_j) Y_j is used, which is Re(r^H Ni r) either way
+    y.B = OFFS(e->NiD, 2 * n * n); y.sBk = e->n; y.sBj = 1; y.conjB = 1; y.bsB = (long long)e->n * e->n;
     y.C = OFFS(e->Yd, 2 * Tp * n); y.sCi = e->n; y.sCj = 1; y.bsC = (long long)e->Tp * e->n;
     y.M = e->T; y.N = e->n; y.K = e->n; y.alpha = 1.0; y.batch = sb.nc;
     hp::launch_zgemm(y, sb.st);

@@ -41,7 +41,7 @@ constexpr int ZG_BM = 64, ZG_BN = 64, ZG_BK = 16;
 constexpr int ZG_LDA = 20;  // 16 + 4
 constexpr int ZG_LDB = 68;  // 64 + 4
 
-__global__ void __launch_bounds__(256) k_zgemm(ZgemmArgs a) {
+__global__ void __launch_bounds__(256, 2) k_zgemm(ZgemmArgs a) {
     __shared__ double Asr[ZG_BM * ZG_LDA], Asi[ZG_BM * ZG_LDA];
     __shared__ double Bsr[ZG_BK * ZG_LDB], Bsi[ZG_BK * ZG_LDB];
     const int b = blockIdx.z;
@@ -61,33 +61,56 @@ __global__ void __launch_bounds__(256) k_zgemm(ZgemmArgs a) {
     //   tri = 1: B[k][j] = 0 for k > j  (k < j0 + BN suffices);   tri = 2: B[k][j] = 0 for k < j  (start at k = j0)
     const int kbeg = a.tri == 2 ? (j0 / ZG_BK) * ZG_BK : 0;
     const int kend = a.tri == 1 ? (a.K < j0 + ZG_BN ? a.K : j0 + ZG_BN) : a.K;
-    for (int k0 = kbeg; k0 < kend; k0 += ZG_BK) {
+    // register double buffer: the global loads of k-tile t + 1 are in flight while tile t is multiplied
+    double2 ra[4], rb[4];
+    auto load_tile = [&](int k0) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            int e = tid + 256 * r;
+            const int e = tid + 256 * r;
             int i, k;
             if (a_kfast) { i = e >> 4; k = e & 15; } else { i = e & 63; k = e >> 6; }
-            double xr = 0.0, xi = 0.0;
-            if (i0 + i < a.M && k0 + k < a.K) {
-                const double* p = A + 2 * ((long long)(i0 + i) * a.sAi + (long long)(k0 + k) * a.sAk);
-                xr = p[0]; xi = sgnA * p[1];
-                if (dk) { double d = dk[k0 + k]; xr *= d; xi *= d; }
+            double2 x = make_double2(0.0, 0.0);
+            if (i0 + i < a.M && k0 + k < kend) {
+                x = *reinterpret_cast<const double2*>(A + 2 * ((long long)(i0 + i) * a.sAi + (long long)(k0 + k) * a.sAk));
+                x.y *= sgnA;
+                if (dk) { const double d = dk[k0 + k]; x.x *= d; x.y *= d; }
             }
-            Asr[i * ZG_LDA + k] = xr; Asi[i * ZG_LDA + k] = xi;
+            ra[r] = x;
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            int e = tid + 256 * r;
+            const int e = tid + 256 * r;
             int k, j;
             if (b_jfast) { k = e >> 6; j = e & 63; } else { k = e & 15; j = e >> 4; }
-            double xr = 0.0, xi = 0.0;
-            if (k0 + k < a.K && j0 + j < a.N) {
-                const double* p = B + 2 * ((long long)(k0 + k) * a.sBk + (long long)(j0 + j) * a.sBj);
-                xr = p[0]; xi = sgnB * p[1];
+            double2 x = make_double2(0.0, 0.0);
+            if (k0 + k < kend && j0 + j < a.N) {
+                x = *reinterpret_cast<const double2*>(B + 2 * ((long long)(k0 + k) * a.sBk + (long long)(j0 + j) * a.sBj));
+                x.y *= sgnB;
             }
-            Bsr[k * ZG_LDB + j] = xr; Bsi[k * ZG_LDB + j] = xi;
+            rb[r] = x;
         }
+    };
+    auto store_tile = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid + 256 * r;
+            int i, k;
+            if (a_kfast) { i = e >> 4; k = e & 15; } else { i = e & 63; k = e >> 6; }
+            Asr[i * ZG_LDA + k] = ra[r].x; Asi[i * ZG_LDA + k] = ra[r].y;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = tid + 256 * r;
+            int k, j;
+            if (b_jfast) { k = e >> 6; j = e & 63; } else { k = e & 15; j = e >> 4; }
+            Bsr[k * ZG_LDB + j] = rb[r].x; Bsi[k * ZG_LDB + j] = rb[r].y;
+        }
+    };
+    if (kbeg < kend) load_tile(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += ZG_BK) {
+        store_tile();
         __syncthreads();
+        if (k0 + ZG_BK < kend) load_tile(k0 + ZG_BK);
         warp_zgemm<4, 2, false, false, false, false>(cr, ci, Asr + 32 * wr * ZG_LDA, Asi + 32 * wr * ZG_LDA, ZG_LDA,
                                                      Bsr + 16 * wc, Bsi + 16 * wc, ZG_LDB, ZG_BK);
         __syncthreads();
