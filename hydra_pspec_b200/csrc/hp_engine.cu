@@ -186,8 +186,23 @@ __global__ void k_mask_dense(double* NiD, const double* Ninv, const double* w, i
     NiD[2 * e] = s * Ninv[2 * e];
     NiD[2 * e + 1] = s * Ninv[2 * e + 1];
 }
-// out[t] = Re sum_x conj(A[t][x]) B[t][x]
-__global__ void k_rowdot(const double* A, const double* B, double* out, int T, int Tp, int n) {
+// NiL = lower triangle of the Hermitian part of NiD with half its diagonal:  r^H Ni r = 2 Re(r^H NiL r)
+__global__ void k_lower_half(double* NiL, const double* NiD, int n) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    int x = (int)(e / n), y = (int)(e % n);
+    double re = 0.0, im = 0.0;
+    if (y < x) {
+        const long long f = (long long)y * n + x;
+        re = 0.5 * (NiD[2 * e] + NiD[2 * f]);
+        im = 0.5 * (NiD[2 * e + 1] - NiD[2 * f + 1]);
+    } else if (y == x) {
+        re = 0.5 * NiD[2 * e];
+    }
+    NiL[2 * e] = re; NiL[2 * e + 1] = im;
+}
+// out[t] = scale * Re sum_x conj(A[t][x]) B[t][x]
+__global__ void k_rowdot(const double* A, const double* B, double* out, int T, int Tp, int n, double scale) {
     const int sys = blockIdx.y, t = blockIdx.x;
     const double* a = A + 2 * (((size_t)sys * Tp + t) * n);
     const double* b = B + 2 * (((size_t)sys * Tp + t) * n);
@@ -201,7 +216,7 @@ __global__ void k_rowdot(const double* A, const double* B, double* out, int T, i
     if (threadIdx.x == 0) {
         double s2 = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s2 += red[i];
-        out[(size_t)sys * Tp + t] = s2;
+        out[(size_t)sys * Tp + t] = scale * s2;
     }
 }
 
@@ -240,6 +255,7 @@ struct hp_engine {
     std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
     bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
     double *Wd = nullptr, *Yb = nullptr;
+    double *NiL = nullptr;   // dense noise: lower half of the Hermitian part of NiD (ln_post term as a triangular product)
     double *NiD = nullptr, *NihD = nullptr, *Td = nullptr, *Rm = nullptr, *Yd = nullptr;  // dense (non-diagonal) noise
     int* info = nullptr;
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
@@ -459,6 +475,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     }
     if (cfg->dense_noise) {
         ap.want(&e->NiD, 2 * C * n * n);
+        ap.want(&e->NiL, 2 * C * n * n);
         if (cfg->rng_mode == HP_RNG_INJECTED) ap.want(&e->NihD, 2 * C * n * n);
         ap.want(&e->Td, 2 * n * Np); ap.want(&e->Rm, 2 * C * Tp * n); ap.want(&e->Yd, 2 * C * Tp * n);
     }
@@ -657,6 +674,7 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     if (ninv_dense) {
         CU_TRY(cudaMemcpyAsync(e->stage, ninv_dense, 2 * (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
         k_mask_dense<<<nblocks((long long)n * n), 256, 0, st>>>(e->NiD + 2 * (size_t)c * n * n, e->stage, e->w + (size_t)c * n, n);
+        k_lower_half<<<nblocks((long long)n * n), 256, 0, st>>>(e->NiL + 2 * (size_t)c * n * n, e->NiD + 2 * (size_t)c * n * n, n);
         CU_TRY(cudaStreamSynchronize(st));
         if (e->NihD) {
             if (!nih_dense) return fail(HP_ERR_ARG, "injected-draw mode with dense noise needs the square root of the flagged N^-1");
@@ -800,14 +818,15 @@ static void enqueue_dense_lnp1(hp_engine* e, const Sub& sb) {
     e->prof_begin(CLS_TRANSFORM, sb.st);
     hp::ZgemmArgs y{};
     y.A = OFFS(e->Rm, 2 * Tp * n); y.sAi = e->n; y.sAk = 1; y.bsA = (long long)e->Tp * e->n;
-    // Y = R conj(Ni) (row-major operand, coalesced) instead of R Ni^T: identical for a Hermitian Ni, and only the real part
-    // of sum_j conj(R_j) Y_j is used, which is Re(r^H Ni r) either way
-    y.B = OFFS(e->NiD, 2 * n * n); y.sBk = e->n; y.sBj = 1; y.conjB = 1; y.bsB = (long long)e->n * e->n;
+    // r^H Ni r = 2 Re(r^H NiL r) with NiL the lower half of the Hermitian part of Ni (k_lower_half): Y = R conj(NiL) is a
+    // triangular product (B[k][j] = conj(NiL[k][j]) = 0 for k < j: k_zgemm skips that K range), half the flops of R Ni^T
+    y.B = OFFS(e->NiL, 2 * n * n); y.sBk = e->n; y.sBj = 1; y.conjB = 1; y.bsB = (long long)e->n * e->n;
     y.C = OFFS(e->Yd, 2 * Tp * n); y.sCi = e->n; y.sCj = 1; y.bsC = (long long)e->Tp * e->n;
     y.M = e->T; y.N = e->n; y.K = e->n; y.alpha = 1.0; y.batch = sb.nc;
+    y.tri = 2;
     hp::launch_zgemm(y, sb.st);
     k_rowdot<<<dim3(e->Tp, sb.nc), 128, 0, sb.st>>>(OFFS(e->Rm, 2 * Tp * n), OFFS(e->Yd, 2 * Tp * n), OFFS(e->lnp1, Tp), e->T,
-                                                   e->Tp, e->n);
+                                                   e->Tp, e->n, 2.0);
     e->prof_end(CLS_TRANSFORM, 2, sb.st);
 }
 
