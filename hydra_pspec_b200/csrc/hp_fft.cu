@@ -379,7 +379,9 @@ int postfft_tiles(int T, int ktp) { return (T + ktp - 1) / ktp; }
 
 void launch_post_fft(const PostFftArgs& a, cudaStream_t st) {
     const size_t smem = postfft_smem_bytes(a.plan.n, a.m, a.ktp);
-    static size_t attr8 = 0, attr4 = 0;
+    static size_t attr8_dev[kMaxDev] = {0}, attr4_dev[kMaxDev] = {0};
+    size_t& attr8 = attr8_dev[current_device_slot()];
+    size_t& attr4 = attr4_dev[current_device_slot()];
     if (a.ktp == 8) {
         if (smem > attr8) { cudaFuncSetAttribute(k_post_fft<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr8 = smem; }
         k_post_fft<8><<<dim3(postfft_tiles(a.T, 8), a.nsys), 256, smem, st>>>(a);

@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(kCT, 2) k_chol_col(CholArgs a, int k, int diag
 }
 
 int launch_chol(const CholArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
+    static bool attr_dev[kMaxDev] = {false};
+    bool& attr_set = attr_dev[current_device_slot()];
     static int mode = -1;   // HP_CHOL_COLUMNS = 0 (one CTA per system), 1 (one launch pair per block column), unset: auto
     if (!attr_set) {
         cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
@@ -505,7 +506,8 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
 }
 
 void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, int nsys, cudaStream_t st) {
-    static bool attr_set = false;
+    static bool attr_dev[kMaxDev] = {false};
+    bool& attr_set = attr_dev[current_device_slot()];
     if (!attr_set) {
         cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrinvSmem));
         attr_set = true;

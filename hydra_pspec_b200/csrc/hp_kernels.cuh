@@ -22,6 +22,14 @@ constexpr int kLBlkDoubles = 2 * kLPlane;  // L / L^-1 blocks are stored in the 
 constexpr int kTT = 16;                 // right-hand sides (times) per solve CTA
 constexpr int kInvGrid = 1000;          // pspec.py:11 ngrid default
 
+// cudaFuncSetAttribute is per device: the launch wrappers cache what they have set per device ordinal
+constexpr int kMaxDev = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= kMaxDev) ? 0 : d;
+}
+
 __host__ __device__ inline size_t tri_blocks(int nblk) { return (size_t)nblk * (nblk + 1) / 2; }
 __host__ __device__ inline size_t blk_index(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
 

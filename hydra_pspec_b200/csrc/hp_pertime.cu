@@ -387,7 +387,8 @@ extern "C" void hp_pt_timers(unsigned long long* out, int reset) {
 #endif
 void launch_pt_cholsolve(const PtArgs& a, int grid, cudaStream_t st) {
     const size_t smem = pt_smem_bytes(a.nblk, a.n);
-    static size_t attr_set = 0;
+    static size_t attr_dev[kMaxDev] = {0};
+    size_t& attr_set = attr_dev[current_device_slot()];
     if (attr_set < smem) {
         cudaFuncSetAttribute(k_pt_cholsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = smem;

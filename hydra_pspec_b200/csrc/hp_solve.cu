@@ -479,7 +479,8 @@ void launch_solve(const SolveArgs& a_in, cudaStream_t st) {
         if (ring_bytes < 4 * row_bytes) return;  // excluded by solve_resident_ok (the engine never launches this)
     }
     size_t smem = solve_smem_bytes_stages(a.nblk, stages);
-    static size_t attr_smem = 0;
+    static size_t attr_dev[kMaxDev] = {0};
+    size_t& attr_smem = attr_dev[current_device_slot()];
     if (smem > attr_smem) {
         cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_smem = smem;

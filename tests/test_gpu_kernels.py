@@ -114,3 +114,27 @@ def test_arena_cache_and_deferred_setup_survive_engine_churn():
     rng = np.random.default_rng(sum(sizes[1]))
     assert np.array_equal(run(*sizes[1])[2], outs[1])  # and after the cache has been dropped
     assert all(np.all(np.isfinite(o)) for o in outs)
+
+
+def test_two_devices_in_one_process():
+    """The drop-in functions take `device=`: kernels with > 48 KB of dynamic shared memory need their attribute set on
+    every device they run on (the launch wrappers cache it per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(3)
+    nt, nf, nm = 24, 96, 6
+    F = np.linalg.qr(rng.standard_normal((nf, nm)) + 1j * rng.standard_normal((nf, nm)))[0]
+    vis = rng.standard_normal((nt, nf)) + 1j * rng.standard_normal((nt, nf))
+    flags = np.ones(nf, bool)
+    flags[[5, 50]] = False
+    prior = np.zeros((2, nf))
+    a = pspec.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, np.eye(nf) * 2.0, prior, Niter=3, seed=4, verbose=False, device=0)
+    b = pspec.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, np.eye(nf) * 2.0, prior, Niter=3, seed=4, verbose=False, device=1)
+    fl2 = np.broadcast_to(flags, (nt, nf)).copy()
+    fl2[3, 7] = False
+    c = pspec.gibbs_sample_with_fg(vis, fl2, np.eye(nf), F, np.eye(nf) * 2.0, prior, Niter=2, seed=4, verbose=False, device=1)
+    for x, y in zip(a[:6], b[:6]):
+        assert np.array_equal(x, y)
+    assert np.all(np.isfinite(c[2]))
