@@ -257,8 +257,25 @@ def run_b200(args):
     step_flops = (4.0 * N ** 3 / 3 + 8.0 * N * N * nt) * B
     roofline["step_tflops"] = step_flops * K / (ms_max * 1e-3) * 1e-12
     roofline["step_frac_of_peak"] = roofline["step_tflops"] / peak if peak > 0 else None
+    # the other kernels of the step against their own rooflines (CUDA-event times of the same untimed steps)
+    post_ms = kms["post"][0] / KP
+    chol_ms = kms["chol"][0] / KP
+    post_bytes = 16.0 * nt * (N + 2 * nf) * B          # X in, flags*vis in, frequency-space signal out
+    roofline["other_kernels"] = {
+        "k_post_fft": {"bound": "hbm", "achieved": post_bytes / (post_ms * 1e-3) * 1e-9 if post_ms > 0 else None, "unit": "GB/s",
+                       "algorithmic_bytes_per_launch": post_bytes},
+        "k_chol_col + k_trinv": {"bound": "tensor", "unit": "TFLOP/s",
+                                 "achieved": (8.0 * N ** 3 / 3) * B / (chol_ms * 1e-3) * 1e-12 if chol_ms > 0 else None,
+                                 "flops_per_step": (8.0 * N ** 3 / 3) * B,
+                                 "peak": peak, "note": "4 N^3/3 (Cholesky) + 4 N^3/3 (explicit inverse of the factor)"},
+    }
+    _ck = roofline["other_kernels"]["k_chol_col + k_trinv"]
+    _ck["frac"] = _ck["achieved"] / peak if (_ck["achieved"] and peak > 0) else None
     try:
         peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        if roofline["other_kernels"]["k_post_fft"]["achieved"]:
+            roofline["other_kernels"]["k_post_fft"]["peak"] = peaks["hbm_gbs"]
+            roofline["other_kernels"]["k_post_fft"]["frac"] = roofline["other_kernels"]["k_post_fft"]["achieved"] / peaks["hbm_gbs"]
         hbm_bytes = 16.0 * (3 * nt * N + 3 * nt * nf) * B  # Rfix, eta, X + Ssc, Sf, z per baseline-iteration
         roofline["hbm"] = {"algorithmic_gbs": hbm_bytes * K / (ms_max * 1e-3) * 1e-9, "peak_gbs": peaks["hbm_gbs"]}
     except Exception:
