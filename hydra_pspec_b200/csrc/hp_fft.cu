@@ -277,19 +277,19 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
             load_b(warp, bcur);
             for (int ct = warp; ct < nct; ct += kTP) {
                 load_b(ct + kTP, bnxt);
-                double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0}, dr[2] = {0.0, 0.0}, di[2] = {0.0, 0.0};
+                // three real DMMAs per complex MAC (3M):  P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi)
+                double p1[2] = {0.0, 0.0}, p2[2] = {0.0, 0.0}, p3[2] = {0.0, 0.0};
 #pragma unroll
                 for (int s8 = 0; s8 < 8; ++s8) {
-                    dmma884(cr[0], cr[1], af[s8].x, bcur[s8].x);
-                    dmma884(ci[0], ci[1], af[s8].x, bcur[s8].y);
-                    dmma884(dr[0], dr[1], af[s8].y, bcur[s8].y);
-                    dmma884(di[0], di[1], af[s8].y, bcur[s8].x);
+                    dmma884(p1[0], p1[1], af[s8].x, bcur[s8].x);
+                    dmma884(p2[0], p2[1], af[s8].y, bcur[s8].y);
+                    dmma884(p3[0], p3[1], af[s8].x + af[s8].y, bcur[s8].x + bcur[s8].y);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     int x = 8 * ct + 2 * q + e;
                     if (x < n && g < kTP) {
-                        double2 v = make_double2(cr[e] - dr[e], ci[e] + di[e]);
+                        double2 v = make_double2(p1[e] - p2[e], p3[e] - p1[e] - p2[e]);
                         if (kc) { double2 o = obuf[(size_t)g * n + x]; v.x += o.x; v.y += o.y; }
                         obuf[(size_t)g * n + x] = v;
                     }
