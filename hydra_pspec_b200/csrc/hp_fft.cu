@@ -19,6 +19,15 @@
 
 namespace hp {
 
+// Phase timers of k_post_fft (build with -DHP_POST_TIMERS; profiles/scripts/post_timers.py): clock64 deltas of thread 0
+// of every CTA.  [0] tables + f + X load  [1] FFT 1  [2] post-twiddle + Sf store  [3] F f (DMMA)  [4] residual  [5] FFT 2 + E
+#ifdef HP_POST_TIMERS
+__device__ unsigned long long g_post_cycles[8];
+#define PO_T(idx) do { if (tid == 0) { long long _n = clock64(); tacc[idx] += _n - tlast; tlast = _n; } } while (0)
+#else
+#define PO_T(idx) do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
@@ -201,6 +210,9 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
         for (size_t off = (size_t)tid * 128; off < bytes; off += kThreads * 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(wdp + off));
     }
+#ifdef HP_POST_TIMERS
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     for (int j = tid; j < n; j += kThreads) tw[j] = twg[j];
     for (int e = tid; e < kTP * ldf; e += kThreads) {
         int t = e / ldf, j = e - t * ldf;
@@ -217,17 +229,32 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
         {
             const int t = warp;
             const bool live = t0 + t < a.T;
-            for (int k = lane; k < n; k += 32) {
-                double2 v = make_double2(0.0, 0.0);
-                if (live) {
-                    v = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + k));
-                    const double l = lam[k];
-                    v = mul_shift_pre(make_double2(l * v.x, -l * v.y), tw, n, k);
+            // batches of four independent 16-byte loads per lane (the one-at-a-time loop exposed a full DRAM / L2
+            // latency per element: 12 serialised round trips at Nfreqs = 384)
+            for (int k0 = lane; k0 < n; k0 += 128) {
+                double2 v[4];
+                double l[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + 32 * u;
+                    v[u] = make_double2(0.0, 0.0);
+                    l[u] = 0.0;
+                    if (live && k < n) {
+                        v[u] = *reinterpret_cast<const double2*>(X + 2 * ((size_t)t * a.Np + k));
+                        l[u] = lam[k];
+                    }
                 }
-                buf0[(size_t)t * n + k] = v;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + 32 * u;
+                    if (k < n) buf0[(size_t)t * n + k] = mul_shift_pre(make_double2(l[u] * v[u].x, -l[u] * v[u].y), tw, n, k);
+                }
             }
         }
+        __syncthreads();
+        PO_T(0);
         double2* res = fft_forward(buf0, buf1, kTP, a.plan, tw);
+        PO_T(1);
         {
             const int t = warp;
             const bool live = t0 + t < a.T;
@@ -250,6 +277,7 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
     }
     double2* obuf = sbuf == buf0 ? buf1 : buf0;
     __syncthreads();
+    PO_T(2);
     // foreground model F f on the tensor pipe:  obuf[t][x] = sum_j f[t][j] Ft[j][x]
     // A = f tile (8 x m) stays in registers for all column tiles; the B fragments of a tile come
     // straight from global (L2-resident Ft) as one 16-byte load per k-step, issued as a batch and
@@ -302,6 +330,7 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
             for (int e = tid; e < kTP * n; e += kThreads) obuf[e] = make_double2(0.0, 0.0);
     }
     __syncthreads();
+    PO_T(3);
     // residual, chi^2, ln-posterior partial, masked signal
     {
         const double* wd = a.wd + 2 * ((size_t)sys * a.Tp + t0) * n;
@@ -309,14 +338,23 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
 #pragma unroll
         for (int t = 0; t < kTP; ++t) part[t] = 0.0;
         for (int x = tid; x < n; x += kThreads) {
+            // all global loads of this channel first: the optional global stores below (chi^2, masked residual) would
+            // otherwise keep the compiler from moving the next time's load above them (one exposed latency per time)
+            double2 dv[kTP];
+            double wv[kTP];
+#pragma unroll
+            for (int t = 0; t < kTP; ++t) {
+                dv[t] = make_double2(0.0, 0.0);
+                if (t0 + t < a.T) dv[t] = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)t * n + x));
+                wv[t] = (a.w_ts == 0 || t0 + t < a.T) ? w[(size_t)t * a.w_ts + x] : 0.0;
+            }
             const double ndx = nd[x];
 #pragma unroll
             for (int t = 0; t < kTP; ++t) {
-                const double wx = (a.w_ts == 0 || t0 + t < a.T) ? w[(size_t)t * a.w_ts + x] : 0.0;
+                const double wx = wv[t];
                 double2 s = sbuf[(size_t)t * n + x];
                 double2 mf = obuf[(size_t)t * n + x];
-                double2 d = make_double2(0.0, 0.0);
-                if (t0 + t < a.T) d = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)t * n + x));
+                const double2 d = dv[t];
                 double rr = d.x - s.x - mf.x, ri = d.y - s.y - mf.y;
                 double r2 = rr * rr + ri * ri;
                 if (t0 + t < a.T) {
@@ -341,6 +379,8 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
             if (t0 + tid < a.Tp) a.lnp1[(size_t)sys * a.Tp + t0 + tid] = t0 + tid < a.T ? s : 0.0;
         }
     }
+    __syncthreads();
+    PO_T(4);
     // |U (w s)|^2 summed over the tile's times (second term of ln_post, pspec.py:479-483)
     if (a.Empart) {
         double2* res = fft_forward(obuf, sbuf, kTP, a.plan, tw);
@@ -352,6 +392,11 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
             Ep[k] = acc / (double)n;
         }
     }
+    __syncthreads();
+    PO_T(5);
+#ifdef HP_POST_TIMERS
+    if (tid == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_post_cycles[i], (unsigned long long)tacc[i]);
+#endif
     // |U s|^2 (unmasked) for the general-basis iteration: reload s from global
     if (a.Eupart) {
         __syncthreads();
@@ -374,6 +419,14 @@ __global__ void __launch_bounds__(32 * kTP, kTP == 8 ? 2 : 1) k_post_fft(PostFft
         }
     }
 }
+
+#ifdef HP_POST_TIMERS
+extern "C" void hp_post_timers(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_post_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_post_cycles, z, sizeof(z)); }
+}
+#endif
 
 int postfft_tiles(int T, int ktp) { return (T + ktp - 1) / ktp; }
 
