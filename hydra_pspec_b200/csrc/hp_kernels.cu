@@ -346,6 +346,21 @@ __global__ void __launch_bounds__(kCT, 2) k_chol_col(CholArgs a, int k, int diag
     double cr[1][1][2], ci[1][1][2], P3m[3][1][1][2];
     warp_zero<1, 1>(cr, ci);
     warp_zero3m<1, 1>(P3m);
+    // this thread's two elements of M_ik = J + lam_i G_ik lam_k do not depend on the update: fetch them now, so that
+    // their global-load latency runs under the operand stream instead of after it
+    double mr_[2], mi_[2];
+    {
+        const double* Gb = Gp + blk_index(i, k) * kBlkDoubles;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+            const int gi = 32 * i + r, gj = 32 * k + c;
+            const double sc = lam[gi] * lam[gj];
+            mr_[e] = sc * Gb[r * 32 + c];
+            mi_[e] = sc * Gb[1024 + r * 32 + c];
+            if (gi == gj && (gi < a.n || gi >= a.N)) mr_[e] += 1.0;
+        }
+    }
     if (!diag) load_block_async_ct(s.V, Linvp + (size_t)k * kLBlkDoubles);   // rides with the first operand stage
     if (k > 0) {
         load_block_async_ct(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
@@ -372,16 +387,11 @@ __global__ void __launch_bounds__(kCT, 2) k_chol_col(CholArgs a, int k, int diag
     cp_async_wait<0>();
     __syncthreads();   // V_kk landed (k = 0: nothing else waited for it); A[0] is free
     warp_zgemm3m_finish<1, 1, false, true>(P3m, cr, ci);
-    const double* Gb = Gp + blk_index(i, k) * kBlkDoubles;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
-        int gi = 32 * i + r, gj = 32 * k + c;
-        double sc = lam[gi] * lam[gj];
-        double vr = sc * Gb[r * 32 + c], vi = sc * Gb[1024 + r * 32 + c];
-        if (gi == gj && (gi < a.n || gi >= a.N)) vr += 1.0;
-        Ar[r * kLdBlk + c] = vr - cr[0][0][e];
-        Ai[r * kLdBlk + c] = vi - ci[0][0][e];
+        Ar[r * kLdBlk + c] = mr_[e] - cr[0][0][e];
+        Ai[r * kLdBlk + c] = mi_[e] - ci[0][0][e];
     }
     __syncthreads();
     if (diag) {
