@@ -241,7 +241,7 @@ def run_b200(args):
         "bound": "tensor", "kernel": "k_solve", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak if peak > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_solve launch of this exact workload, from the
-        # `ncu --set full` capture summarised in profiles/r1_v8_summary.md (1.090 GB + 0.857 GB); the algorithmic
+        # `ncu --set full` capture summarised in profiles/r1_v9_summary.md (1.090 GB + 0.857 GB); the algorithmic
         # bytes of a launch are Rfix in + X out + W once = 16 B * (2 T N + N^2 / 2) * B = 1.94 GB
         "traffic": 1.947e9 if (nt, nf, nm, B) == (1024, 384, 32, 128) else None,
         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
