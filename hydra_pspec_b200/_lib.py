@@ -21,13 +21,13 @@ class HPConfig(C.Structure):
         ("nmodes", C.c_int), ("rng_mode", C.c_int), ("cg_compat", C.c_int), ("refresh_omega", C.c_int),
         ("keep", C.c_int), ("max_iters", C.c_int), ("general_basis0", C.c_int), ("profile", C.c_int), ("substreams", C.c_int), ("dense_noise", C.c_int),
         ("force_dense_transforms", C.c_int), ("force_dense_solve", C.c_int), ("time_flags", C.c_int),
-        ("seed", C.c_uint64), ("stream", C.c_void_p),
+        ("ring_iters", C.c_int), ("seed", C.c_uint64), ("stream", C.c_void_p),
     ]
 
 
 class HPHostSink(C.Structure):
     _fields_ = [("signal_ps", C.c_void_p), ("ln_post", C.c_void_p), ("signal_cr", C.c_void_p),
-                ("fg_amps", C.c_void_p), ("chisq", C.c_void_p), ("iters", C.c_int)]
+                ("fg_amps", C.c_void_p), ("chisq", C.c_void_p), ("iters", C.c_int), ("first_iter", C.c_int)]
 
 
 class HydraLibError(RuntimeError):
@@ -55,6 +55,7 @@ _SIGNATURES = {
     "hp_engine_info": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_engine_kernel_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hp_engine_set_substreams": (C.c_int, [C.c_void_p, C.c_int]),
+    "hp_engine_set_chain_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_engine_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_engine_launch_count": (C.c_longlong, [C.c_void_p]),
     "hp_kernel_class_name": (C.c_char_p, [C.c_int]),
@@ -64,6 +65,8 @@ _SIGNATURES = {
                                 C.c_int, C.c_void_p, C.c_void_p]),
     "hp_test_chol_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hp_test_solve2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hp_fp64_peak_tflops": (C.c_double, [C.c_int, C.c_double]),
     "hp_release_cached_memory": (None, []),
     "hp_pinned_alloc": (C.c_void_p, [C.c_size_t]),

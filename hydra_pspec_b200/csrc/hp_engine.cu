@@ -103,13 +103,14 @@ __global__ void k_build_rhs(double* R, const double* Rfix, const double* wa, con
     R[off] = vr; R[off + 1] = vi;
 }
 // y += xi, xi ~ CN(0, I): same Philox counter layout as k_solve
-__global__ void k_add_noise(double* Y, int N, int Np, int T, int Tp, uint32_t key0, uint32_t key1, uint32_t iter, int chain0) {
+__global__ void k_add_noise(double* Y, int N, int Np, int T, int Tp, uint32_t key0, uint32_t key1, uint32_t iter,
+                            const int* __restrict__ chain_ids) {
     const size_t sys = blockIdx.y;
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= (long long)T * Np) return;
     const int t = (int)(e / Np), row = (int)(e % Np);
     if (row >= N) return;
-    hp::u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)t; ctr.z = iter; ctr.w = (uint32_t)(chain0 + (int)sys);
+    hp::u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)t; ctr.z = iter; ctr.w = (uint32_t)chain_ids[sys];
     double n0, n1;
     hp::normal_pair_fast(hp::philox4x32_10(ctr, key0, key1 ^ 0xA5A5A5A5u), n0, n1);
     double* y = Y + 2 * (sys * (size_t)Tp * Np + (size_t)e);
@@ -227,6 +228,7 @@ struct Basis {
     double* Gp = nullptr;    // [C][tri][2048]
     double* Rfix = nullptr;  // [C][Tp][Np]
     double* wa = nullptr;    // [C][Tp][Np]   injected mode: Q^H omega_a
+    double* Rt = nullptr;    // [C][ntiles][nblk][2][32][16]  right-hand sides in k_solve2's tile layout (k_rhs_tile)
 };
 
 enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4 };
@@ -254,10 +256,14 @@ struct hp_engine {
     int gd_slots = 1;
     std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
     bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
+    bool solve2 = false;                  // k_solve2 (persistent, register-blocked) takes the solve
+    int pp_tiles = 0;                     // partial |ytilde|^2 sums per chain in Ppart: ntiles (k_solve), 2 ntiles (k_solve2)
+    double* Wp1 = nullptr;                // W diag(lam): pass-1 operand of k_solve2 when Rt holds the unscaled Rfix (Philox mode)
     double *Wd = nullptr, *Yb = nullptr;
     double *NiL = nullptr;   // dense noise: lower half of the Hermitian part of NiD (ln_post term as a triangular product)
     double *NiD = nullptr, *NihD = nullptr, *Td = nullptr, *Rm = nullptr, *Yd = nullptr;  // dense (non-diagonal) noise
     int* info = nullptr;
+    int* chain_ids = nullptr;   // [C] Philox chain id of every chain (default: its index; hp_engine_set_chain_ids)
     double *X = nullptr, *Ssc = nullptr, *Ppart = nullptr, *Sf = nullptr, *Wm = nullptr, *Tmp = nullptr;
     double *Em = nullptr, *Eu = nullptr, *lnp1 = nullptr;
     double* sdraws = nullptr;
@@ -272,6 +278,9 @@ struct hp_engine {
     std::vector<uint8_t> flagged;  // per chain: any channel flagged
     std::vector<uint8_t> have_omega;
     bool any_flagged = false;
+    int ring = 1;     // device slots of the big per-iteration outputs (cfg.ring_iters, or max_iters)
+    std::vector<cudaEvent_t> copy_done;   // run_to_host: the device-to-host copies out of ring slot s have completed
+    std::vector<cudaEvent_t> sub_done;    // run_to_host: sub-batch i has finished the iteration being copied
     int iter = 0;     // Gibbs iterations since the chains were loaded (RNG counter, basis choice)
     int out_pos = 0;  // cursor in the per-iteration output buffers
     uint32_t draw_counter = 0;  // Philox counter of the GCR fluctuation draws (advances per GCR step)
@@ -364,6 +373,7 @@ void want_basis(hp_engine* e, ArenaPlan& ap, Basis& b) {
     ap.want(&b.Gp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles);
     ap.want(&b.Rfix, 2 * C * e->Tp * e->Np);
     if (e->cfg.rng_mode == HP_RNG_INJECTED) ap.want(&b.wa, 2 * C * e->Tp * e->Np);
+    if (e->solve2) ap.want(&b.Rt, 2 * C * e->Tp * e->Np);
 }
 }  // namespace
 
@@ -398,6 +408,8 @@ int hp_engine_destroy(hp_engine* e) {
     for (auto x : e->sub_st) cudaStreamDestroy(x);
     if (e->fork_ev) cudaEventDestroy(e->fork_ev);
     for (auto x : e->join_ev) cudaEventDestroy(x);
+    for (auto x : e->copy_done) cudaEventDestroy(x);
+    for (auto x : e->sub_done) cudaEventDestroy(x);
     if (e->own_stream) cudaStreamDestroy(e->st);
     delete e;
     return HP_OK;
@@ -422,10 +434,9 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     e->big_solve = cfg->force_dense_solve || !hp::solve_resident_ok(e->nblk, (size_t)max_smem);
-    if (e->big_solve && cfg->cg_compat && !cfg->time_flags) {
-        delete e;
-        return fail(HP_ERR_SIZE, "Nfreqs + Nmodes = " + std::to_string(e->N) + " is too large for the shared-memory resident "
-                                 "solve tile; the dense-product solve has no cg_compat mode (use the exact solver)");
+    {
+        const char* v1 = getenv("HP_SOLVE_V1");   // experiments: keep the round-1 kernel
+        e->solve2 = !e->big_solve && !cfg->time_flags && hp::solve2_stages(e->nblk, (size_t)max_smem) >= 2 && !(v1 && v1[0] == '1');
     }
     if (cfg->time_flags && (cfg->general_basis0 || cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms)) {
         delete e;
@@ -440,6 +451,8 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     if (cfg->stream) e->st = (cudaStream_t)cfg->stream;
     else { CU_TRY(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking)); e->own_stream = true; }
     const size_t C = e->C, n = e->n, m = e->m, Np = e->Np, Tp = e->Tp, T = e->T, I = cfg->max_iters;
+    e->ring = (cfg->ring_iters > 0 && cfg->ring_iters < cfg->max_iters) ? cfg->ring_iters : cfg->max_iters;
+    const size_t R = e->ring;
     e->ktp = hp::postfft_ktp(e->n, e->m, (size_t)max_smem);
     e->fft_ok = hp::make_fft_plan(e->n, &e->plan) && e->ktp > 0 &&
                 !cfg->force_dense_transforms;
@@ -457,10 +470,13 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->Lp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
     ap.want(&e->Linvp, C * e->nblk * hp::kLBlkDoubles);
     ap.want(&e->Wp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
+    if (e->solve2 && cfg->rng_mode == HP_RNG_PHILOX) ap.want(&e->Wp1, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
     ap.want(&e->info, C);
+    ap.want(&e->chain_ids, C);
     ap.want(&e->X, 2 * C * Tp * Np);
-    if (need_ssc) ap.want(&e->Ssc, 2 * C * Tp * n);
-    ap.want(&e->Ppart, C * e->ntiles * n); ap.want(&e->Sf, 2 * C * Tp * n);
+    if (need_ssc) ap.want(&e->Ssc, 2 * C * Tp * n);   // (dense transforms / general first basis)
+    e->pp_tiles = (e->solve2 ? 2 : 1) * e->ntiles;
+    ap.want(&e->Ppart, C * e->pp_tiles * n); ap.want(&e->Sf, 2 * C * Tp * n);
     if (dense) { ap.want(&e->Wm, 2 * C * Tp * n); ap.want(&e->Tmp, 2 * C * Tp * n); ap.want(&e->Em, C * n); ap.want(&e->Eu, C * n); }
     ap.want(&e->lnp1, C * Tp);
     if (e->big_solve && !cfg->time_flags) { ap.want(&e->Wd, 2 * C * Np * Np); ap.want(&e->Yb, 2 * C * Tp * Np); }
@@ -481,9 +497,9 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     }
     if (cfg->rng_mode != HP_RNG_PHILOX) ap.want(&e->sdraws, C * I * n);
     ap.want(&e->ps_out, C * I * n); ap.want(&e->lnpost_out, C * I);
-    if (cfg->keep & HP_KEEP_CR) ap.want(&e->cr_out, 2 * C * I * T * n);
-    if (cfg->keep & HP_KEEP_FG) ap.want(&e->fg_out, 2 * C * I * T * (m ? m : 1));
-    if (cfg->keep & HP_KEEP_CHISQ) ap.want(&e->chisq_out, C * I * T * n);
+    if (cfg->keep & HP_KEEP_CR) ap.want(&e->cr_out, 2 * C * R * T * n);
+    if (cfg->keep & HP_KEEP_FG) ap.want(&e->fg_out, 2 * C * R * T * (m ? m : 1));
+    if (cfg->keep & HP_KEEP_CHISQ) ap.want(&e->chisq_out, C * R * T * n);
     e->gd_slots = (int)(C < 16 ? C : 16);   // dense Gram scratch for a batch of chains (deferred set-up)
     ap.want(&e->Gd, 2 * (size_t)e->gd_slots * e->N * e->N);
     ap.want(&e->stage, 2 * (T * n > n * n ? T * n : n * n));
@@ -511,6 +527,11 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
             }
             cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming);
         }
+    }
+    {
+        std::vector<int> ids(C);
+        for (size_t c = 0; c < C; ++c) ids[c] = (int)c;
+        cudaMemcpyAsync(e->chain_ids, ids.data(), C * sizeof(int), cudaMemcpyHostToDevice, e->st);   // pageable: staged before return
     }
     hp::launch_fourier_operator(e->Fop, e->n, 1.0, e->st);
     hp::launch_fourier_operator(e->U, e->n, 1.0 / std::sqrt((double)e->n), e->st);
@@ -565,6 +586,9 @@ static int build_basis_products(hp_engine* e, Basis& b, int c) {
         r.dk = e->cfg.time_flags ? e->ninvd + (size_t)c * n : e->ni + (size_t)c * n;
     }
     hp::launch_zgemm(r, e->st);
+    if (b.Rt && e->cfg.rng_mode == HP_RNG_PHILOX)
+        hp::launch_rhs_tile(b.Rt + 2 * (size_t)c * e->Tp * Np, b.Rfix + 2 * (size_t)c * e->Tp * Np, nullptr, nullptr, e->nblk, e->n, e->N,
+                            e->T, e->Tp, e->ntiles, 1, e->st);
     if (e->cfg.time_flags) {
         // H_t = [Q|F]^H (w_t N^-1) [q_0 | F]  for every time: column 0 is the generator chat_t of the circulant
         // signal block, the rest are the foreground columns of G_t (hp_pertime.cu)
@@ -607,6 +631,9 @@ static int build_basis_products_batch(hp_engine* e, Basis& b, int c0, int nc) {
         r.C = b.Rfix + 2 * (size_t)cc0 * e->Tp * Np; r.sCi = Np; r.sCj = 1; r.bsC = (long long)e->Tp * Np;
         r.M = T; r.N = N; r.K = n; r.accumulate = 0; r.alpha = 1.0; r.batch = ncc;
         hp::launch_zgemm(r, e->st);
+        if (b.Rt && e->cfg.rng_mode == HP_RNG_PHILOX)
+            hp::launch_rhs_tile(b.Rt + 2 * (size_t)cc0 * e->Tp * Np, b.Rfix + 2 * (size_t)cc0 * e->Tp * Np, nullptr, nullptr, e->nblk,
+                                e->n, e->N, e->T, e->Tp, e->ntiles, ncc, e->st);
     }
     CU_TRY(cudaGetLastError());
     return HP_OK;
@@ -861,10 +888,10 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         pa.nblk = e->nblk; pa.n = e->n; pa.m = e->m; pa.N = e->N; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc;
         pa.philox_wa = philox ? 1 : 0;
         pa.key0 = (uint32_t)e->cfg.seed; pa.key1 = (uint32_t)(e->cfg.seed >> 32); pa.iter = draw_iter;
-        pa.chain_ids = nullptr; pa.chain0 = sb.c0;
+        pa.chain_ids = OFFS(e->chain_ids, 1); pa.chain0 = sb.c0;
         hp::launch_pt_cholsolve(pa, grid, sb.st);
         // beta partial sums: Ppart[sys][0][k] = sum_t |ytilde_k|^2
-        hp::launch_colsumsq(OFFS(e->X, 2 * Tp * Np), OFFS(e->Ppart, (size_t)e->ntiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+        hp::launch_colsumsq(OFFS(e->X, 2 * Tp * Np), OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
         e->prof_end(CLS_SOLVE, 2, sb.st);
     } else {
     e->prof_begin(CLS_CHOL, sb.st);
@@ -873,7 +900,8 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     ca.Linvp = OFFS(e->Linvp, (size_t)e->nblk * hp::kLBlkDoubles); ca.info = e->info + sb.c0;
     ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = sb.nc;
     const int nchol = hp::launch_chol(ca, sb.st);
-    hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), e->nblk, sb.nc, sb.st);
+    hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), OFFS(e->Wp1, tri * hp::kLBlkDoubles), OFFS(e->lam, Np),
+                     e->nblk, sb.nc, sb.st);
     e->prof_end(CLS_CHOL, nchol + 1, sb.st);
 
     if (e->big_solve) {
@@ -899,7 +927,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         int nl = 4;
         if (philox) {
             k_add_noise<<<dim3(nblocks((long long)e->T * e->Np), sb.nc), 256, 0, sb.st>>>(
-                Yb, e->N, e->Np, e->T, e->Tp, (uint32_t)e->cfg.seed, (uint32_t)(e->cfg.seed >> 32), draw_iter, sb.c0);
+                Yb, e->N, e->Np, e->T, e->Tp, (uint32_t)e->cfg.seed, (uint32_t)(e->cfg.seed >> 32), draw_iter, OFFS(e->chain_ids, 1));
             ++nl;
         }
         hp::ZgemmArgs x{};   // X[t][i] = sum_j y[t][j] conj(W[j][i])
@@ -909,10 +937,48 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         x.M = e->T; x.N = e->Np; x.K = e->Np; x.alpha = 1.0; x.batch = sb.nc;
         x.tri = 2;           // B[k = j][col = i] = conj(W[j][i]) = 0 for j < i
         hp::launch_zgemm(x, sb.st);
-        hp::launch_colsumsq(X, OFFS(e->Ppart, (size_t)e->ntiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+        if (e->cfg.cg_compat) {
+            hp::launch_cg_scale(X, OFFS(b.Rfix, 2 * Tp * Np), (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr, OFFS(e->lam, Np),
+                                e->n, e->N, e->Np, e->T, e->Tp, sb.nc, sb.st);
+            ++nl;
+        }
+        hp::launch_colsumsq(X, OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
         ++nl;
         if (!fused_inverse) {
             k_make_ssc<<<dim3(nblocks((long long)e->T * e->n), sb.nc), 256, 0, sb.st>>>(OFFS(e->Ssc, 2 * Tp * n), X, OFFS(e->lam, Np),
+                                                                                       e->n, e->Np, e->T, e->Tp);
+            ++nl;
+        }
+        e->prof_end(CLS_SOLVE, nl, sb.st);
+    } else if (e->solve2) {
+        // k_solve2: right-hand sides in tile layout.  Philox mode: the unscaled Rfix tiles built at load time and
+        // W1 = W diag(lam) from k_trinv; injected draws: r = lam * Rfix + wa rebuilt per solve, W1 = W.
+        e->prof_begin(CLS_SOLVE, sb.st);
+        int nl = 1;
+        const double* wa_sb = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
+        if (!philox) {
+            hp::launch_rhs_tile(OFFS(b.Rt, 2 * Tp * Np), OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->nblk, e->n, e->N, e->T,
+                                e->Tp, e->ntiles, sb.nc, sb.st);
+            ++nl;
+        }
+        hp::Solve2Args sa{};
+        sa.W1 = philox ? OFFS(e->Wp1, tri * hp::kLBlkDoubles) : OFFS(e->Wp, tri * hp::kLBlkDoubles);
+        sa.W2 = OFFS(e->Wp, tri * hp::kLBlkDoubles);
+        sa.Rt = OFFS(b.Rt, 2 * Tp * Np);
+        sa.X = OFFS(e->X, 2 * Tp * Np);
+        sa.Ppart = OFFS(e->Ppart, (size_t)e->pp_tiles * n);
+        sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = sb.nc; sa.T = e->T;
+        sa.philox = philox ? 1 : 0;
+        sa.key0 = (uint32_t)e->cfg.seed; sa.key1 = (uint32_t)(e->cfg.seed >> 32); sa.iter = draw_iter;
+        sa.chain_ids = OFFS(e->chain_ids, 1); sa.chain0 = sb.c0;
+        hp::launch_solve2(sa, sb.st);
+        if (e->cfg.cg_compat) {
+            hp::launch_cg_scale(sa.X, OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->n, e->N, e->Np, e->T, e->Tp, sb.nc, sb.st);
+            hp::launch_colsumsq(sa.X, OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+            nl += 2;
+        }
+        if (!fused_inverse) {
+            k_make_ssc<<<dim3(nblocks((long long)e->T * e->n), sb.nc), 256, 0, sb.st>>>(OFFS(e->Ssc, 2 * Tp * n), sa.X, OFFS(e->lam, Np),
                                                                                        e->n, e->Np, e->T, e->Tp);
             ++nl;
         }
@@ -924,12 +990,12 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     sa.Rfix = OFFS(b.Rfix, 2 * Tp * Np);
     sa.wa = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
     sa.X = OFFS(e->X, 2 * Tp * Np); sa.Ssc = fused_inverse ? nullptr : OFFS(e->Ssc, 2 * Tp * n);
-    sa.Ppart = OFFS(e->Ppart, (size_t)e->ntiles * n);
+    sa.Ppart = OFFS(e->Ppart, (size_t)e->pp_tiles * n);
     sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = sb.nc; sa.T = e->T;
     sa.philox_wa = philox ? 1 : 0;
     sa.cg_compat = e->cfg.cg_compat;
     sa.key0 = (uint32_t)e->cfg.seed; sa.key1 = (uint32_t)(e->cfg.seed >> 32); sa.iter = draw_iter;
-    sa.chain_ids = nullptr; sa.chain0 = sb.c0;
+    sa.chain_ids = OFFS(e->chain_ids, 1); sa.chain0 = sb.c0;
     hp::launch_solve(sa, sb.st);
     e->prof_end(CLS_SOLVE, 1, sb.st);
     }
@@ -1055,15 +1121,16 @@ static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t 
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
     Basis& b = general ? e->b0 : e->bF;
     IterOut o{};
-    o.sf = e->cr_out ? e->cr_out + 2 * (size_t)it * T * n : e->Sf;
-    o.sf_bs = e->cr_out ? (long long)(I * T * n) : (long long)(Tp * n);
-    o.fg = e->fg_out ? e->fg_out + 2 * (size_t)it * T * m : nullptr; o.fg_bs = 2 * (long long)(I * T * m);
-    o.chisq = e->chisq_out ? e->chisq_out + (size_t)it * T * n : nullptr; o.chisq_bs = (long long)(I * T * n);
+    const size_t R = e->ring, slot = (size_t)it % R;   // big outputs: ring slot; signal_ps / ln_post: one entry per iteration
+    o.sf = e->cr_out ? e->cr_out + 2 * slot * T * n : e->Sf;
+    o.sf_bs = e->cr_out ? (long long)(R * T * n) : (long long)(Tp * n);
+    o.fg = e->fg_out ? e->fg_out + 2 * slot * T * m : nullptr; o.fg_bs = 2 * (long long)(R * T * m);
+    o.chisq = e->chisq_out ? e->chisq_out + slot * T * n : nullptr; o.chisq_bs = (long long)(R * T * n);
     enqueue_gcr(e, b, o, sb, draw_iter);
 
     e->prof_begin(CLS_SAMPLE, sb.st);
     hp::SampleArgs sp{};
-    sp.Ppart = OFFS(e->Ppart, (size_t)e->ntiles * n);
+    sp.Ppart = OFFS(e->Ppart, (size_t)e->pp_tiles * n);
     sp.ntilesE = e->fft_ok ? e->ntilesE : 0;
     sp.Eu = e->fft_ok ? OFFS(e->Eupart, (size_t)e->ntilesE * n) : OFFS(e->Eu, n);
     sp.Em = e->any_flagged ? (e->fft_ok ? OFFS(e->Empart, (size_t)e->ntilesE * n) : OFFS(e->Em, n)) : nullptr;
@@ -1073,10 +1140,11 @@ static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t 
     sp.ps_out = OFFS(e->ps_out, I * n) + (size_t)it * n; sp.ps_bs = (long long)(I * n);
     sp.lnpost_out = OFFS(e->lnpost_out, I) + it; sp.lnpost_bs = (long long)I;
     sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = sb.nc;
-    if (e->cfg.time_flags || e->big_solve) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
+    sp.ntiles = e->pp_tiles;
+    if (e->cfg.time_flags || e->big_solve || (e->solve2 && e->cfg.cg_compat)) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
     sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
     sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = iter;
-    sp.chain_ids = nullptr; sp.chain0 = sb.c0;
+    sp.chain_ids = OFFS(e->chain_ids, 1); sp.chain0 = sb.c0;
     hp::launch_sample(sp, sb.st);
     e->prof_end(CLS_SAMPLE, 1, sb.st);
 }
@@ -1115,58 +1183,91 @@ int hp_engine_run(hp_engine* e, int niter) {
 
 int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
     if (!e || !sink) return fail(HP_ERR_ARG, "null argument");
-    if (niter < 0 || e->out_pos + niter > e->cfg.max_iters || e->out_pos + niter > sink->iters)
+    if (niter < 0 || e->out_pos + niter > e->cfg.max_iters || sink->first_iter < 0 || e->out_pos < sink->first_iter ||
+        e->out_pos + niter - sink->first_iter > sink->iters)
         return fail(HP_ERR_ARG, "hp_engine_run_to_host: would exceed max_iters / sink capacity");
     if ((sink->signal_cr && !e->cr_out) || (sink->fg_amps && !e->fg_out) || (sink->chisq && !e->chisq_out))
         return fail(HP_ERR_ARG, "hp_engine_run_to_host: sink asks for an output that is not kept (cfg.keep)");
     CU_TRY(cudaSetDevice(e->cfg.device));
     { int rcf = flush_pending(e); if (rcf != HP_OK) return rcf; }
     if (!e->copy_st) CU_TRY(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
-    const size_t n = e->n, m = e->m, T = e->T, I = e->cfg.max_iters, HI = sink->iters;
+    const size_t n = e->n, m = e->m, T = e->T, I = e->cfg.max_iters, HI = sink->iters, R = e->ring, C = (size_t)e->C;
     const int first = e->out_pos;
-    std::vector<cudaEvent_t> evs;
+    const bool big = sink->signal_cr || (sink->fg_amps && m) || sink->chisq;
+    const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
+    auto subs = make_subs(e);
+    if (big) {
+        while (e->copy_done.size() < R) {
+            cudaEvent_t ev;
+            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->copy_done.push_back(ev);
+        }
+        while (e->sub_done.size() < subs.size()) {
+            cudaEvent_t ev;
+            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->sub_done.push_back(ev);
+        }
+    }
+    // Sub-batches never join between iterations: each records an event after its part of an iteration, the copy stream
+    // waits for all of them and streams the iteration's ring slot to the host while the next iterations compute; a
+    // sub-batch only waits (for the copies out of the slot it is about to overwrite) when it is R iterations ahead.
+    fork_subs(e, subs);
     cudaError_t cerr = cudaSuccess;
-    enqueue_iterations(e, niter, [&](int k) -> bool {
-        if (k >= 0) return true;  // ask for a join after every iteration, then get called back with -1 - k
-        const size_t it = (size_t)e->out_pos - 1;
-        cudaEvent_t ev;
-        if ((cerr = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return false;
-        evs.push_back(ev);
-        cudaEventRecord(ev, e->st);
-        cudaStreamWaitEvent(e->copy_st, ev, 0);
-        // this iteration's big arrays leave over PCIe while the next iteration computes: one strided copy per array
-        // (rows = chains; device pitch = a chain's whole output ring, host pitch = a chain's host array)
-        const size_t C = (size_t)e->C;
+    for (int k = 0; k < niter && cerr == cudaSuccess; ++k) {
+        const size_t it = (size_t)e->out_pos, slot = it % R, hs = it - (size_t)sink->first_iter;
+        const bool general = e->cfg.general_basis0 && e->iter == 0;
+        const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
+        for (auto& sb : subs) {
+            if (big && it >= R + (size_t)first) cudaStreamWaitEvent(sb.st, e->copy_done[slot], 0);
+            enqueue_iteration_sub(e, sb, (int)it, (uint32_t)e->iter, draw_iter, general);
+        }
+        e->iter++;
+        e->out_pos++;
+        if (!big) continue;
+        for (size_t i = 0; i < subs.size(); ++i) {
+            cudaEventRecord(e->sub_done[i], subs[i].st);
+            cudaStreamWaitEvent(e->copy_st, e->sub_done[i], 0);
+        }
+        // one strided copy per array (rows = chains; device pitch = a chain's ring, host pitch = a chain's host array)
         if (sink->signal_cr)
-            cerr = copy_rows_d2h(sink->signal_cr + 2 * (it * T * n), HI * T * n * 16, e->cr_out + 2 * (it * T * n), I * T * n * 16,
+            cerr = copy_rows_d2h(sink->signal_cr + 2 * (hs * T * n), HI * T * n * 16, e->cr_out + 2 * (slot * T * n), R * T * n * 16,
                                  T * n * 16, C, e->copy_st);
         if (sink->fg_amps && m && cerr == cudaSuccess)
-            cerr = copy_rows_d2h(sink->fg_amps + 2 * (it * T * m), HI * T * m * 16, e->fg_out + 2 * (it * T * m), I * T * m * 16,
+            cerr = copy_rows_d2h(sink->fg_amps + 2 * (hs * T * m), HI * T * m * 16, e->fg_out + 2 * (slot * T * m), R * T * m * 16,
                                  T * m * 16, C, e->copy_st);
         if (sink->chisq && cerr == cudaSuccess)
-            cerr = copy_rows_d2h(sink->chisq + it * T * n, HI * T * n * 8, e->chisq_out + it * T * n, I * T * n * 8, T * n * 8, C,
+            cerr = copy_rows_d2h(sink->chisq + hs * T * n, HI * T * n * 8, e->chisq_out + slot * T * n, R * T * n * 8, T * n * 8, C,
                                  e->copy_st);
-        return false;
-    });
+        cudaEventRecord(e->copy_done[slot], e->copy_st);
+    }
+    join_subs(e, subs);
     if (cerr != cudaSuccess) return fail(HP_ERR_CUDA, std::string("hp_engine_run_to_host: ") + cudaGetErrorString(cerr));
     {
         cudaEvent_t ev;
         CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        evs.push_back(ev);
         CU_TRY(cudaEventRecord(ev, e->st));
         CU_TRY(cudaStreamWaitEvent(e->copy_st, ev, 0));
+        cudaEventDestroy(ev);   // released once the wait has consumed it
     }
     if (niter > 0) {
+        const size_t h0 = (size_t)(first - sink->first_iter);
         if (sink->signal_ps)
-            CU_TRY(copy_rows_d2h(sink->signal_ps + first * n, HI * n * 8, e->ps_out + first * n, I * n * 8, (size_t)niter * n * 8,
-                                 (size_t)e->C, e->copy_st));
-        if (sink->ln_post)
-            CU_TRY(copy_rows_d2h(sink->ln_post + first, HI * 8, e->lnpost_out + first, I * 8, (size_t)niter * 8, (size_t)e->C,
+            CU_TRY(copy_rows_d2h(sink->signal_ps + h0 * n, HI * n * 8, e->ps_out + first * n, I * n * 8, (size_t)niter * n * 8, C,
                                  e->copy_st));
+        if (sink->ln_post)
+            CU_TRY(copy_rows_d2h(sink->ln_post + h0, HI * 8, e->lnpost_out + first, I * 8, (size_t)niter * 8, C, e->copy_st));
     }
     CU_TRY(cudaStreamSynchronize(e->copy_st));
-    for (auto ev : evs) cudaEventDestroy(ev);
+    CU_TRY(cudaStreamSynchronize(e->st));
     CU_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_engine_set_chain_ids(hp_engine* e, const int* ids) {
+    if (!e || !ids) return fail(HP_ERR_ARG, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaMemcpyAsync(e->chain_ids, ids, (size_t)e->C * sizeof(int), cudaMemcpyHostToDevice, e->st));
+    CU_TRY(cudaStreamSynchronize(e->st));
     return HP_OK;
 }
 
@@ -1211,14 +1312,23 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
         case HP_BUF_PS: src = e->ps_out + ((size_t)c * I + iter0) * n; bytes = (size_t)niter * n * 8; break;
         case HP_BUF_LNPOST: src = e->lnpost_out + (size_t)c * I + iter0; bytes = (size_t)niter * 8; break;
         case HP_BUF_CR:
-            if (!e->cr_out) return fail(HP_ERR_ARG, "signal_cr was not kept (cfg.keep)");
-            src = e->cr_out + 2 * ((size_t)c * I + iter0) * T * n; bytes = (size_t)niter * T * n * 16; break;
         case HP_BUF_FG:
-            if (!e->fg_out) return fail(HP_ERR_ARG, "fg_amps was not kept (cfg.keep)");
-            src = e->fg_out + 2 * ((size_t)c * I + iter0) * T * m; bytes = (size_t)niter * T * m * 16; break;
-        case HP_BUF_CHISQ:
-            if (!e->chisq_out) return fail(HP_ERR_ARG, "chisq was not kept (cfg.keep)");
-            src = e->chisq_out + ((size_t)c * I + iter0) * T * n; bytes = (size_t)niter * T * n * 8; break;
+        case HP_BUF_CHISQ: {
+            // ring of e->ring slots per chain: iteration i lives in slot i % ring until iteration i + ring overwrites it
+            const double* base = buffer == HP_BUF_CR ? e->cr_out : (buffer == HP_BUF_FG ? e->fg_out : e->chisq_out);
+            if (!base) return fail(HP_ERR_ARG, "this output was not kept (cfg.keep)");
+            const size_t R = e->ring;
+            const size_t per = buffer == HP_BUF_CR ? 2 * T * n : (buffer == HP_BUF_FG ? 2 * T * m : T * n);   // doubles per iteration
+            bytes = (size_t)niter * per * 8;
+            if (dst_bytes < bytes) return fail(HP_ERR_ARG, "destination too small");
+            if (niter > 0 && (size_t)iter0 + R < (size_t)e->out_pos)
+                return fail(HP_ERR_ARG, "iteration no longer in the device ring (cfg.ring_iters): stream it with hp_engine_run_to_host");
+            for (int k = 0; k < niter; ++k) {
+                const size_t slot = (size_t)(iter0 + k) % R;
+                if (per) CU_TRY(cudaMemcpy((char*)dst + (size_t)k * per * 8, base + ((size_t)c * R + slot) * per, per * 8, cudaMemcpyDeviceToHost));
+            }
+            return HP_OK;
+        }
         case HP_BUF_LAST_CR:
             if (!e->last_sf) return fail(HP_ERR_ARG, "no GCR solve has run yet");
             src = e->last_sf + 2 * (size_t)c * e->last_sf_bs; bytes = T * n * 16; break;

@@ -454,18 +454,28 @@ struct TrinvSmem {
 };
 
 __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all, const double* __restrict__ Linvp_all,
-                                               double* Wp_all, int nblk) {
+                                               double* Wp_all, double* Wp1_all, const double* __restrict__ lam_all, int nblk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrinvSmem& s = *reinterpret_cast<TrinvSmem*>(smem_raw);
     const int j = blockIdx.x, sys = blockIdx.y;
     const double* Lp = Lp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
     const double* Vp = Linvp_all + (size_t)sys * nblk * kLBlkDoubles;
     double* Wp = Wp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    // W1 = W diag(lam): columns of block column j scaled by lam[32 j ..]
+    double* Wp1 = Wp1_all ? Wp1_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles : nullptr;
+    const double* lamj = lam_all ? lam_all + (size_t)sys * nblk * 32 + 32 * j : nullptr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     const int ti = warp >> 2, tj = warp & 3;
     // W_jj = V_jj
-    for (int e = tid; e < kLBlkDoubles; e += kCT) Wp[blk_index(j, j) * kLBlkDoubles + e] = Vp[(size_t)j * kLBlkDoubles + e];
+    for (int e = tid; e < kLBlkDoubles; e += kCT) {
+        const double v = Vp[(size_t)j * kLBlkDoubles + e];
+        Wp[blk_index(j, j) * kLBlkDoubles + e] = v;
+        if (Wp1) {
+            const int c = (e % kLPlane) % kLdBlk;
+            Wp1[blk_index(j, j) * kLBlkDoubles + e] = c < 32 ? v * lamj[c] : 0.0;
+        }
+    }
     for (int i = j + 1; i < nblk; ++i) {
         double cr[1][1][2], ci[1][1][2];
         warp_zero<1, 1>(cr, ci);
@@ -512,17 +522,24 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
         int r = 8 * ti + g, c = 8 * tj + 2 * q;
         *reinterpret_cast<double2*>(Wb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
         *reinterpret_cast<double2*>(Wb + kLPlane + r * kLdBlk + c) = make_double2(di[0][0][0], di[0][0][1]);
+        if (Wp1) {
+            double* Wb1 = Wp1 + blk_index(i, j) * kLBlkDoubles;
+            const double l0 = lamj[c], l1 = lamj[c + 1];
+            *reinterpret_cast<double2*>(Wb1 + r * kLdBlk + c) = make_double2(l0 * dr[0][0][0], l1 * dr[0][0][1]);
+            *reinterpret_cast<double2*>(Wb1 + kLPlane + r * kLdBlk + c) = make_double2(l0 * di[0][0][0], l1 * di[0][0][1]);
+        }
     }
 }
 
-void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, int nsys, cudaStream_t st) {
+void launch_trinv(const double* Lp, const double* Linvp, double* Wp, double* Wp1, const double* lam, int nblk, int nsys,
+                  cudaStream_t st) {
     static bool attr_dev[kMaxDev] = {false};
     bool& attr_set = attr_dev[current_device_slot()];
     if (!attr_set) {
         cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrinvSmem));
         attr_set = true;
     }
-    k_trinv<<<dim3(nblk, nsys), kCT, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, nblk);
+    k_trinv<<<dim3(nblk, nsys), kCT, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, Wp1, lam, nblk);
 }
 
 // ==========================================================================================

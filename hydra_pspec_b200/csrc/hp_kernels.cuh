@@ -64,8 +64,10 @@ struct CholArgs {
     int nblk, n, N, nsys;
 };
 int launch_chol(const CholArgs& a, cudaStream_t st);   // returns the number of kernel launches (1, or 2 nblk - 1 in column mode)
-// W = L^-1 in the same padded block layout as L ([nsys][tri_blocks][2304])
-void launch_trinv(const double* Lp, const double* Linvp, double* Wp, int nblk, int nsys, cudaStream_t st);
+// W = L^-1 in the same padded block layout as L ([nsys][tri_blocks][2304]); Wp1 (optional) receives W diag(lam), the
+// pass-1 operand of k_solve2 when the stored right-hand sides are unscaled (lam: [nsys][Np])
+void launch_trinv(const double* Lp, const double* Linvp, double* Wp, double* Wp1, const double* lam, int nblk, int nsys,
+                  cudaStream_t st);
 
 struct SolveArgs {
     const double* Wp;      // [nsys][tri_blocks][2304]  W = L^-1 (k_trinv)
@@ -88,6 +90,29 @@ struct SolveArgs {
 void launch_solve(const SolveArgs& a, cudaStream_t st);
 size_t solve_smem_bytes(int nblk);
 bool solve_resident_ok(int nblk, size_t max_smem);   // false: use the dense-product solve (N > 576)
+
+// ---- k_solve2 (hp_solve2.cu): persistent register-blocked solve, right-hand sides in tile layout -------------------
+struct Solve2Args {
+    const double* W1;      // [nsys][tri_blocks][2304] pass-1 operand: W, or W diag(lam) when Rt holds unscaled Rfix
+    const double* W2;      // [nsys][tri_blocks][2304] pass-2 operand: W (applied as W^H)
+    const double* Rt;      // [nsys][ntiles][nblk][2][32][16] right-hand sides in the tile's shared-memory layout (k_rhs_tile)
+    double* X;             // [nsys][Tp][Np] complex: solution [ytilde ; f]
+    double* Ppart;         // [nsys][2 ntiles][n]: sum over eight of the tile's times of |ytilde|^2
+    int nblk, n, N, Tp, ntiles, nsys, T;
+    int philox;            // 1: add xi ~ CN(0, I) (Philox, same counter layout as k_solve) to y = W1 r
+    uint32_t key0, key1, iter;
+    const int* chain_ids;
+    int chain0;
+    int stages;            // set by launch_solve2
+    int grid_limit;        // > 0: cap on the persistent grid (sub-batches sharing the GPU); 0 = one CTA per SM
+};
+void launch_solve2(const Solve2Args& a, cudaStream_t st);
+int solve2_stages(int nblk, size_t max_smem);   // W-ring depth that fits shared memory; 0 = k_solve2 cannot take this size
+void launch_rhs_tile(double* Rt, const double* Rfix, const double* wa, const double* lam, int nblk, int n, int N, int T, int Tp,
+                     int ntiles, int nsys, cudaStream_t st);
+// scalar model of the reference's truncated CG applied to the global solution X (every solve path)
+void launch_cg_scale(double* X, const double* Rfix, const double* wa, const double* lam, int n, int N, int Np, int T, int Tp,
+                     int nsys, cudaStream_t st);
 
 struct PostArgs {
     const double* Sf;      // [nsys][>=T][n] complex: signal in frequency space (rows t < T are read)

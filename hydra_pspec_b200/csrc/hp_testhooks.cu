@@ -53,7 +53,7 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
     hp::CholArgs ca{};
     ca.Gp = dGp; ca.lam = dlam; ca.Lp = dLp; ca.Linvp = dLinv; ca.info = dinfo; ca.nblk = nblk; ca.n = n; ca.N = N; ca.nsys = 1;
     hp::launch_chol(ca, 0);
-    hp::launch_trinv(dLp, dLinv, dWp, nblk, 1, 0);
+    hp::launch_trinv(dLp, dLinv, dWp, nullptr, nullptr, nblk, 1, 0);
     hp::SolveArgs sa{};
     sa.Wp = dWp; sa.lam = dlam; sa.Rfix = dR; sa.wa = dW; sa.X = dX; sa.Ssc = dS; sa.Ppart = dP;
     sa.nblk = nblk; sa.n = n; sa.N = N; sa.Tp = Tp; sa.ntiles = ntiles; sa.nsys = 1; sa.T = T; sa.cg_compat = cg_compat;
@@ -78,6 +78,84 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
     }
     cudaFree(dG); cudaFree(dGp); cudaFree(dlam); cudaFree(dLp); cudaFree(dLinv); cudaFree(dWp); cudaFree(dR); cudaFree(dW); cudaFree(dX);
     cudaFree(dS); cudaFree(dP); cudaFree(dinfo);
+    return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
+}
+
+
+// The same factorisation followed by k_solve2 (hp_solve2.cu) for `nsys` systems that share G and lam but have their own
+// right-hand sides Rfix[nsys][T][N] (and wa[nsys][T][n]).  wa == NULL: unscaled right-hand sides in tile layout and
+// W1 = W diag(lam) (the Philox-mode data flow, without the noise); wa != NULL: r = lam * Rfix + wa built by k_rhs_tile
+// and W1 = W.  grid_limit > 0 caps the persistent grid (several tiles per CTA at test sizes).
+// X [nsys][T][N]; psum [nsys][n] = sum_t |x_k|^2 from the kernel's partial sums (or NULL).
+int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double* lam, const double* Rfix, const double* wa,
+                   int cg_compat, int grid_limit, double* X, double* psum) {
+    const int N = n + m, nblk = (N + 31) / 32, Np = nblk * 32, ntiles = (T + 15) / 16, Tp = ntiles * 16;
+    int max_smem = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (hp::solve2_stages(nblk, (size_t)max_smem) == 0) return HP_ERR_SIZE;
+    double *dG, *dGp, *dlam, *dLp, *dLinv, *dWp, *dWp1, *dR, *dW = nullptr, *dX, *dP, *dRt;
+    int* dinfo;
+    const size_t tri = hp::tri_blocks(nblk) * hp::kLBlkDoubles, trig = hp::tri_blocks(nblk) * hp::kBlkDoubles;
+    const size_t rt_doubles = (size_t)nsys * ntiles * nblk * 2 * 32 * hp::kTT;
+    cudaMalloc(&dG, 16ull * N * N); cudaMalloc(&dGp, 8 * trig); cudaMalloc(&dlam, 8ull * Np); cudaMalloc(&dLp, 8 * tri);
+    cudaMalloc(&dLinv, 8ull * nblk * hp::kLBlkDoubles); cudaMalloc(&dWp, 8 * tri); cudaMalloc(&dWp1, 8 * tri);
+    cudaMalloc(&dR, 16ull * nsys * Tp * Np); cudaMalloc(&dX, 16ull * nsys * Tp * Np);
+    cudaMalloc(&dP, 8ull * nsys * 2 * ntiles * n); cudaMalloc(&dinfo, 4); cudaMalloc(&dRt, 8 * rt_doubles);
+    cudaMemset(dR, 0, 16ull * nsys * Tp * Np); cudaMemset(dlam, 0, 8ull * Np); cudaMemset(dX, 0xff, 16ull * nsys * Tp * Np);
+    cudaMemcpy(dG, G, 16ull * N * N, cudaMemcpyHostToDevice);
+    cudaMemcpy(dlam, lam, 8ull * N, cudaMemcpyHostToDevice);
+    for (int s = 0; s < nsys; ++s)
+        cudaMemcpy2D(dR + 2ull * s * Tp * Np, 16ull * Np, Rfix + 2ull * s * T * N, 16ull * N, 16ull * N, T, cudaMemcpyHostToDevice);
+    if (wa) {
+        cudaMalloc(&dW, 16ull * nsys * Tp * Np); cudaMemset(dW, 0, 16ull * nsys * Tp * Np);
+        for (int s = 0; s < nsys; ++s)
+            cudaMemcpy2D(dW + 2ull * s * Tp * Np, 16ull * Np, wa + 2ull * s * T * n, 16ull * n, 16ull * n, T, cudaMemcpyHostToDevice);
+    }
+    hp::launch_pack_lower(dG, N, 0, dGp, N, nblk, 1, 0);
+    hp::CholArgs ca{};
+    ca.Gp = dGp; ca.lam = dlam; ca.Lp = dLp; ca.Linvp = dLinv; ca.info = dinfo; ca.nblk = nblk; ca.n = n; ca.N = N; ca.nsys = 1;
+    hp::launch_chol(ca, 0);
+    hp::launch_trinv(dLp, dLinv, dWp, dWp1, dlam, nblk, 1, 0);
+    // every system uses the one factor: replicate the per-system strides by giving k_solve2 nsys = 1 per launch
+    for (int s = 0; s < nsys; ++s) {
+        // lam is shared: k_rhs_tile indexes lam by system, so build one system at a time
+        hp::launch_rhs_tile(dRt + (size_t)s * ntiles * nblk * 2 * 32 * hp::kTT, dR + 2ull * s * Tp * Np,
+                            dW ? dW + 2ull * s * Tp * Np : nullptr, wa ? dlam : nullptr, nblk, n, N, T, Tp, ntiles, 1, 0);
+    }
+    // one launch over all systems needs per-system W: replicate the factor
+    double *dWall, *dW1all;
+    cudaMalloc(&dWall, 8 * tri * nsys); cudaMalloc(&dW1all, 8 * tri * nsys);
+    for (int s = 0; s < nsys; ++s) {
+        cudaMemcpy(dWall + tri * s, dWp, 8 * tri, cudaMemcpyDeviceToDevice);
+        cudaMemcpy(dW1all + tri * s, wa ? dWp : dWp1, 8 * tri, cudaMemcpyDeviceToDevice);
+    }
+    hp::Solve2Args sa{};
+    sa.W1 = dW1all; sa.W2 = dWall; sa.Rt = dRt; sa.X = dX; sa.Ppart = dP;
+    sa.nblk = nblk; sa.n = n; sa.N = N; sa.Tp = Tp; sa.ntiles = ntiles; sa.nsys = nsys; sa.T = T;
+    sa.philox = 0; sa.grid_limit = grid_limit;
+    hp::launch_solve2(sa, 0);
+    if (cg_compat)
+        for (int s = 0; s < nsys; ++s)
+            hp::launch_cg_scale(dX + 2ull * s * Tp * Np, dR + 2ull * s * Tp * Np, dW ? dW + 2ull * s * Tp * Np : nullptr, dlam, n, N,
+                                Np, T, Tp, 1, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) {
+        for (int s = 0; s < nsys; ++s)
+            cudaMemcpy2D(X + 2ull * s * T * N, 16ull * N, dX + 2ull * s * Tp * Np, 16ull * Np, 16ull * N, T, cudaMemcpyDeviceToHost);
+        if (psum) {
+            std::vector<double> pp((size_t)nsys * 2 * ntiles * n);
+            cudaMemcpy(pp.data(), dP, 8 * pp.size(), cudaMemcpyDeviceToHost);
+            for (int s = 0; s < nsys; ++s)
+                for (int k = 0; k < n; ++k) {
+                    double acc = 0.0;
+                    for (int tl = 0; tl < 2 * ntiles; ++tl) acc += pp[((size_t)s * 2 * ntiles + tl) * n + k];
+                    psum[(size_t)s * n + k] = acc;
+                }
+        }
+    }
+    cudaFree(dG); cudaFree(dGp); cudaFree(dlam); cudaFree(dLp); cudaFree(dLinv); cudaFree(dWp); cudaFree(dWp1); cudaFree(dR);
+    cudaFree(dW); cudaFree(dX); cudaFree(dP); cudaFree(dinfo); cudaFree(dRt); cudaFree(dWall); cudaFree(dW1all);
     return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
 }
 

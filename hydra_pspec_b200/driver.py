@@ -70,9 +70,12 @@ def run_baselines(baselines, Niter, seed=0, rng="philox", keep=(), device=None, 
     if device is None:
         device = rank
     make = engine_factory or pspec.GibbsEngine
-    # chain c of an engine draws from Philox stream (key = seed, chain id = c): give every rank its own key
-    rank_seed = (int(seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
-    eng = make(len(mine), ntimes, nfreqs, nmodes, max_iters=Niter, rng=rng, keep=keep, seed=rank_seed, device=device)
+    # The device draws of a chain depend on (seed, chain id, iteration) only: every rank uses the same key and the
+    # global baseline index as chain id, so the samples do not depend on how the baselines are sharded over GPUs.
+    eng = make(len(mine), ntimes, nfreqs, nmodes, max_iters=Niter, rng=rng, keep=keep,
+               seed=int(seed) & 0xFFFFFFFFFFFFFFFF, device=device)
+    if hasattr(eng, "set_chain_ids"):
+        eng.set_chain_ids(np.asarray(mine, dtype=np.int32))
     try:
         for c, gi in enumerate(mine):
             b = baselines[gi]

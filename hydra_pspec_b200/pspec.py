@@ -146,11 +146,14 @@ def _analyse_signal_cov(S):
     d = np.real(np.diagonal(D)).copy()
     off = D - np.diag(np.diagonal(D))
     scale = max(np.max(np.abs(d)), 1e-300)
+    # eigenvalues are clipped at zero: a rank-deficient or barely positive semi-definite S (e.g. a sample covariance
+    # passed as --sigcov0) has eigenvalues ~ -1e-17, whose square root would turn the whole chain into NaN
+    # (the reference's sqrtm tolerates them, pspec.py:355)
     if np.max(np.abs(off)) <= 1e-13 * scale and np.max(np.abs(np.imag(np.diagonal(D)))) <= 1e-13 * scale:
-        return None, d
+        return None, np.clip(d, 0.0, None)
     Sh = 0.5 * (S + S.conj().T)
     w, V = np.linalg.eigh(Sh)
-    return np.ascontiguousarray(V, dtype=np.complex128), np.ascontiguousarray(w, dtype=np.float64)
+    return np.ascontiguousarray(V, dtype=np.complex128), np.ascontiguousarray(np.clip(w, 0.0, None), dtype=np.float64)
 
 
 def _noise_model(Ninv, flags, nfreqs, need_sqrt):
@@ -320,6 +323,13 @@ class GibbsEngine:
     @property
     def launch_count(self):
         return _lib.lib().hp_engine_launch_count(self._h)
+
+    def set_chain_ids(self, ids):
+        """Philox chain id of every chain (default: its index).  Passing the global baseline indices (and the same
+        seed on every rank) makes the device draws independent of how baselines are sharded over GPUs."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        assert ids.shape == (self.nchains,)
+        _lib.check(_lib.lib().hp_engine_set_chain_ids(self._h, _lib.ptr(ids)))
 
     def set_substreams(self, n):
         _lib.check(_lib.lib().hp_engine_set_substreams(self._h, int(n)))
@@ -586,7 +596,7 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
 
 
 def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=None, keep=("cr", "fg", "chisq"),
-                       write_Niter=100, map_estimate=False, device=0, verbose=False):
+                       write_Niter=100, map_estimate=False, device=0, verbose=False, substreams=1, chain_ids=None):
     """Advance the Gibbs chains of several baselines of identical shape together on one GPU.
 
     This is the batched form of the reference's per-rank loop over baselines
@@ -636,7 +646,10 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
     eng = GibbsEngine(nb, ntimes, nfreqs, nmodes, Niter, rng=rng, cg_compat=(solver == "reference-cg"),
                       refresh_omega=(rng == "philox"), keep=keep, general_basis0=general,
                       seed=0 if seed is None else seed, device=device,
-                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=dense, time_flags=per_time)
+                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=dense, time_flags=per_time,
+                      substreams=substreams)
+    if chain_ids is not None:
+        eng.set_chain_ids(chain_ids)
     write_times = [0.0] * nb
     try:
         if rng == "numpy":

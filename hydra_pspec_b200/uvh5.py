@@ -215,9 +215,14 @@ class _H5File:
         cshape = cdims[:-1]
         out = np.zeros(shape, dtype)
         if bt != UNDEF:
-            for offs, caddr, csize in self._walk_chunk_btree(bt, len(cdims)):
+            for offs, caddr, csize, fmask in self._walk_chunk_btree(bt, len(cdims)):
                 raw = b[caddr:caddr + csize]
-                for fid, cd in reversed(filters):
+                # bit i of the chunk's filter mask set = filter i of the pipeline was skipped for this chunk
+                # (optional filters such as LZF leave incompressible chunks unfiltered)
+                for fidx in range(len(filters) - 1, -1, -1):
+                    if (fmask >> fidx) & 1:
+                        continue
+                    fid, cd = filters[fidx]
                     if fid == 1:
                         raw = zlib.decompress(raw)
                     elif fid == 32000:
@@ -244,11 +249,11 @@ class _H5File:
         keysize = 8 + 8 * nd
         for i in range(nent):
             k = pos + i * (keysize + 8)
-            csize, _mask = struct.unpack_from("<II", b, k)
+            csize, fmask = struct.unpack_from("<II", b, k)
             offs = struct.unpack_from("<" + "Q" * nd, b, k + 8)[:-1]
             child = struct.unpack_from("<Q", b, k + keysize)[0]
             if level == 0:
-                yield offs, child + self.base, csize
+                yield offs, child + self.base, csize, fmask
             else:
                 yield from self._walk_chunk_btree(child, nd)
 
@@ -323,6 +328,15 @@ class UVH5Data:
     def conjugate_bls(self):
         sw = self.ant_1_array > self.ant_2_array
         self.data_array[sw] = np.conj(self.data_array[sw])
+        # conjugating a baseline swaps its cross-hand polarisations (xy <-> yx, rl <-> lr), as pyuvdata does
+        pols = list(self.polarization_array)
+        for pa, pb in ((-7, -8), (-3, -4)):
+            if pa in pols and pb in pols:
+                ia, ib = pols.index(pa), pols.index(pb)
+                for arr in (self.data_array, self.flag_array, self.nsample_array):
+                    tmp = arr[sw][..., ia].copy()
+                    arr[sw, ..., ia] = arr[sw][..., ib]
+                    arr[sw, ..., ib] = tmp
         a1 = self.ant_1_array.copy()
         self.ant_1_array[sw] = self.ant_2_array[sw]
         self.ant_2_array[sw] = a1[sw]

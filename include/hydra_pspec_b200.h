@@ -70,6 +70,12 @@ typedef struct hp_config {
                             "flagged at any time", run-hydra-pspec.py:520-526).  Every (baseline, time) pair is then
                             factored and solved on its own (csrc/hp_pertime.cu).  Needs a delay-diagonal S_initial,
                             diagonal noise, cg_compat = 0 */
+    int ring_iters;      /* device slots of the big per-iteration outputs (signal_cr, fg_amps, chisq): 0 = max_iters
+                            (every iteration stays readable with hp_engine_read); R > 0: a ring of R slots, iteration i
+                            lives in slot i % R until iteration i + R overwrites it.  hp_engine_run_to_host streams
+                            every iteration out before its slot is reused, so the device footprint does not grow with
+                            the chain length (the reference holds one baseline's Niter samples in host RAM,
+                            pspec.py:590-596, 625-636) */
     uint64_t seed;       /* Philox key */
     void* stream;        /* cudaStream_t to launch on, or NULL for an engine-owned stream */
 } hp_config;
@@ -126,6 +132,8 @@ int hp_engine_run(hp_engine* e, int niter);
 typedef struct hp_host_sink {
     double* signal_ps; double* ln_post; double* signal_cr; double* fg_amps; double* chisq;
     int iters;           /* capacity (second dimension) of the host arrays */
+    int first_iter;      /* iteration index stored in host slot 0: iteration i lands in slot i - first_iter.  A bounded
+                            staging area is re-used chunk after chunk by advancing first_iter (0 = whole chain) */
 } hp_host_sink;
 /* hp_engine_run + copy-out: every iteration's arrays are streamed to the host on a second stream
  * while the next iteration computes.  Returns when everything has landed. */
@@ -148,6 +156,11 @@ int hp_engine_info(hp_engine* e, int* info_host);
 
 /* Accumulated device time per kernel class since creation or the last call with reset=1 (needs cfg.profile). */
 int hp_engine_kernel_ms(hp_engine* e, double* ms, int* launches, int reset);
+/* Philox chain id of every chain, ids[nchains] (default: the chain's index in the engine).  The device draws of a chain
+ * depend on (cfg.seed, id, iteration) only: a driver that shards baselines over GPUs passes the global baseline indices
+ * and the same seed on every rank, and the samples do not depend on the number of GPUs
+ * (reference: one numpy stream per baseline, run-hydra-pspec.py:487-557). */
+int hp_engine_set_chain_ids(hp_engine* e, const int* ids);
 /* Use at most n of the cfg.substreams sub-batches from now on (1 = everything on the engine stream). */
 int hp_engine_set_substreams(hp_engine* e, int n);
 /* Switch the per-kernel event timing on or off at run time. */
@@ -168,6 +181,10 @@ int hp_test_zgemm(int M, int N, int K, const double* A, int transA, int conjA, c
                   const double* dk, double* C);
 int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, const double* Rfix, const double* wa,
                        int cg_compat, double* Ldense, double* X, int* info);
+/* chol + trinv + k_solve2 (hp_solve2.cu) for nsys systems sharing G and lam: Rfix [nsys][T][N], wa [nsys][T][n] or NULL,
+ * X [nsys][T][N], psum [nsys][n] = sum_t |x_k|^2 or NULL; grid_limit > 0 caps the persistent grid */
+int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double* lam, const double* Rfix, const double* wa,
+                   int cg_compat, int grid_limit, double* X, double* psum);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* FP64 tensor-pipe (DMMA.8x8x4) peak of the device measured with an issue loop for ~`seconds`; TFLOP/s. */

@@ -226,6 +226,12 @@ def gcr_fgmodes(vis, w, mats, fgmodes, oma=None, omb=None, map_estimate=False, s
         omb = np.zeros((ntimes, nfreqs), dtype=complex)
     per_time = isinstance(mats, (list, tuple))
     out = np.zeros((ntimes, nfreqs + fgmodes.shape[1]), dtype=complex)
+    if solver == "direct" and not per_time:
+        # the same LAPACK LU solve as np.linalg.solve, factored once instead of once per time (all times share A)
+        lu = scipy.linalg.lu_factor(mats["A"])
+        for t in range(ntimes):
+            out[t] = scipy.linalg.lu_solve(lu, gcr_rhs(vis[t], w, mats, fgmodes, oma[t], omb[t]))
+        return out
     for t in range(ntimes):
         m = mats[t] if per_time else mats
         wt = w[t] if per_time else w

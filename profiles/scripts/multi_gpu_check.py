@@ -4,7 +4,8 @@
         profiles/scripts/multi_gpu_check.py
 
 Every rank runs its share of 5 small baselines (numpy-stream draws, so chains are deterministic), the
-sample arrays are gathered over NCCL, and rank 0 compares them with a single-GPU run of all baselines."""
+sample arrays are gathered over NCCL, and rank 0 compares them bit for bit with a single-GPU run of all baselines
+(Philox draws depend on (seed, global baseline index, iteration) only)."""
 import os
 import sys
 from pathlib import Path
@@ -27,30 +28,19 @@ for i in range(nbl):
     bls.append(dict(vis=vis, flags=flags, fgmodes=F, ninv_diag=nd, lam0sq=l0))
 
 
-def factory(*a, **kw):  # same Philox key on every rank and chain ids = global baseline index would be needed for
-    kw["seed"] = 1234   # bit-identical device draws; here: identical keys, and the comparison below re-runs per shard
-    return pspec.GibbsEngine(*a, **kw)
-
-
-ps, lp = driver.run_baselines(bls, Niter=niter, seed=7, rng="philox", device=local, engine_factory=factory)
+ps, lp = driver.run_baselines(bls, Niter=niter, seed=7, rng="philox", device=local)
 assert ps.shape == (nbl, niter, nf) and lp.shape == (nbl, niter), (ps.shape, lp.shape)
 ok = True
 if rank == 0:
-    # single-GPU reference: each rank's shard run as its own engine (chain ids restart at 0 per engine)
-    shards = driver.split_data_for_scatter(list(range(nbl)), world)
-    ref_ps = []
-    for sh in shards:
-        eng = pspec.GibbsEngine(len(sh), nt, nf, nm, max_iters=niter, rng="philox", keep=(), seed=1234, device=local)
-        for c, gi in enumerate(sh):
-            b = bls[gi]
-            eng.load_chain(c, b["vis"], b["flags"], b["fgmodes"], b["ninv_diag"], b["lam0sq"])
-        eng.run(niter)
-        ref_ps += [eng.signal_ps(c) for c in range(len(sh))]
-        eng.close()
-    ref_ps = np.stack(ref_ps)
-    err = np.max(np.abs(ps - ref_ps) / np.abs(ref_ps))
-    ok = bool(err < 1e-12) and bool(np.all(np.isfinite(lp)))
-    print(f"multi_gpu_check: world={world} gathered {ps.shape}, max rel diff vs single-GPU shards = {err:.2e} -> {'OK' if ok else 'FAIL'}")
+    # single-GPU run of ALL baselines in one engine: same key, chain id = global baseline index -> bit-identical
+    eng = pspec.GibbsEngine(nbl, nt, nf, nm, max_iters=niter, rng="philox", keep=(), seed=7, device=local)
+    for c, b in enumerate(bls):
+        eng.load_chain(c, b["vis"], b["flags"], b["fgmodes"], b["ninv_diag"], b["lam0sq"])
+    eng.run(niter)
+    ref_ps = np.stack([eng.signal_ps(c) for c in range(nbl)])
+    eng.close()
+    ok = bool(np.array_equal(ps, ref_ps)) and bool(np.all(np.isfinite(lp)))
+    print(f"multi_gpu_check: world={world} gathered {ps.shape}, bit-identical to the single-GPU run: {ok}")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -282,6 +282,7 @@ def main(argv=None):
         dist.barrier()
     all_data_weights = assemble_baselines(args, antpairs, freqs, get, out_dir)
     list_of_baselines = driver.split_data_for_scatter(all_data_weights, size)[rank]
+    global_ids = driver.split_data_for_scatter(list(range(len(all_data_weights))), size)[rank]
     time_load_end = time.perf_counter()
 
     verbose = args.verbose and rank == 0
@@ -309,11 +310,12 @@ def main(argv=None):
             ant_pairs.append(f"{job['antpair'][0]}_{job['antpair'][1]}")
             write_times.append(res[-1])
     else:
+        # one Philox key for the whole job, chain id = global baseline index: the samples of a baseline do not
+        # depend on the number of ranks / GPUs
         seed = 0 if args.seed is None else args.seed
-        rank_seed = (int(seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
-        res = pspec.gibbs_sample_batch(jobs, Niter=args.Niter, seed=rank_seed, rng="philox", solver=args.solver,
-                                       write_Niter=args.write_Niter, map_estimate=args.map_estimate,
-                                       device=local_rank, verbose=verbose)
+        res = pspec.gibbs_sample_batch(jobs, Niter=args.Niter, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, rng="philox",
+                                       solver=args.solver, write_Niter=args.write_Niter, map_estimate=args.map_estimate,
+                                       device=local_rank, verbose=verbose, chain_ids=global_ids)
         for job, r in zip(jobs, res):
             ant_pairs.append(f"{job['antpair'][0]}_{job['antpair'][1]}")
             write_times.append(r[-1])

@@ -138,3 +138,47 @@ def test_two_devices_in_one_process():
     for x, y in zip(a[:6], b[:6]):
         assert np.array_equal(x, y)
     assert np.all(np.isfinite(c[2]))
+
+
+@pytest.mark.parametrize("n,m,T,nsys,grid,use_wa,cg", [
+    (32, 0, 16, 1, 0, False, 0),      # one block, one tile
+    (20, 4, 5, 2, 1, True, 0),        # padded rows and times, two tiles on one persistent CTA
+    (64, 8, 33, 3, 2, False, 0),      # 3 block rows, 9 tiles on 2 CTAs (ring and exchange parities wrap)
+    (120, 12, 24, 2, 1, True, 1),     # cg_compat through k_cg_scale
+    (96, 8, 48, 4, 3, False, 0),      # 4 block rows, uneven tile split
+    (384, 32, 48, 2, 4, False, 0),    # the headline system: 13 block rows, 4-stage ring
+    (384, 32, 40, 1, 0, True, 1),
+    (500, 44, 20, 1, 0, False, 0),    # Np = 544: the largest k_solve2 takes (2-stage ring)
+])
+def test_solve2(n, m, T, nsys, grid, use_wa, cg):
+    """k_solve2 (persistent register-blocked solve) against numpy: X, and the sum_t |x|^2 partial sums."""
+    from oracle import hydra_oracle as ho  # checker only
+    L = _lib()
+    rng = np.random.default_rng(7 * n + m + T + nsys)
+    N = n + m
+    Bm = crandn(rng, n + 8, N)
+    G = Bm.conj().T @ Bm / (n + 8)
+    G = np.ascontiguousarray((G + G.conj().T) / 2)
+    lam = np.concatenate([0.3 + rng.random(n), np.ones(m)])
+    J = np.concatenate([np.ones(n), np.zeros(m)])
+    Mmat = np.diag(J) + lam[:, None] * G * lam[None, :]
+    Rfix = crandn(rng, nsys, T, N)
+    wa = crandn(rng, nsys, T, n) if use_wa else None
+    R = Rfix * lam[None, None, :]
+    if use_wa:
+        R[:, :, :n] += wa
+    Xw = np.linalg.solve(Mmat, R.reshape(-1, N).T).T.reshape(nsys, T, N)
+    if cg:
+        wgt = np.concatenate([lam[:n] ** 2, np.ones(m)])
+        for s in range(nsys):
+            for t in range(T):
+                c = np.sum(wgt * R[s, t].conj() * Xw[s, t])
+                b = np.sqrt(np.sum(wgt * np.abs(R[s, t]) ** 2))
+                Xw[s, t] *= ho.cg_theta(c, b)
+    X = np.empty((nsys, T, N), dtype=np.complex128)
+    psum = np.empty((nsys, n))
+    L.check(L.lib().hp_test_solve2(n, m, T, nsys, L.ptr(G), L.ptr(lam), L.ptr(np.ascontiguousarray(Rfix)),
+                                   L.ptr(None if wa is None else np.ascontiguousarray(wa)), cg, grid, L.ptr(X), L.ptr(psum)))
+    assert rel(X, Xw) < 1e-11
+    if not cg:  # (with cg_compat the engine recomputes the sums after the scaling)
+        assert rel(psum, np.sum(np.abs(Xw[:, :, :n]) ** 2, axis=1)) < 1e-11

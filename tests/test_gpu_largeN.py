@@ -67,13 +67,17 @@ def test_stress_shape_1024_64_dense_noise_matches_oracle():
         assert rel(o, w) < 1e-9, k
 
 
-def test_large_n_philox_chain_and_cg_compat_refusal():
+def test_large_n_philox_chain_and_reference_cg():
+    """N = 656 > 576 (dense-product solve): a Philox chain runs, and the drop-in default (numpy draws + the scalar model
+    of the reference's truncated CG, k_cg_scale) matches the oracle's theta-scaled solves (pspec.py:228)."""
     from hydra_pspec_b200 import pspec
     vis, flags, S0, F, Ninv, prior = make_case(24, 640, 16, 5, 9, False)
     out = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=4, seed=2, verbose=False, rng="philox")
     assert np.all(np.isfinite(out[2])) and np.all(out[2] > 0) and np.all(np.isfinite(out[5]))
-    with pytest.raises(RuntimeError):
-        pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=1, seed=2, verbose=False)  # default: reference-cg
+    want = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=2, solver="theta")
+    got = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=2, verbose=False)  # default: reference-cg
+    for o, w, k in zip(got[:6], want, KEYS):
+        assert rel(o, w) < 1e-9, k
 
 
 @pytest.mark.parametrize("nf,nm", [(544, 32), (560, 32)])

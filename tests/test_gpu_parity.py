@@ -248,3 +248,38 @@ def test_prior_on_every_bin_and_wide_dynamic_range():
     for o, w, k in zip(got[:6], want, KEYS):
         assert rel(o, w) < 1e-8, k   # cond(A) ~ 1e6 on the oracle's (unwhitened) side
     assert np.all(got[2] >= 1e-4) and np.all(got[2] <= 1e4)
+
+
+def _headline_baseline(seed):
+    import bench  # the synthetic HERA-like baseline of the benchmark (repo root is on sys.path via conftest)
+    return bench.make_baseline(seed, 1024, 384, 32)
+
+
+def test_headline_shape_chain_matches_oracle():
+    """BASELINE.json configs[3] shape (Ntimes=1024, Nfreq=384, Nfg=32: 13 block rows, 64 time tiles): two Gibbs
+    iterations with the reference's numpy draws injected and exact solves, every output against the oracle."""
+    from hydra_pspec_b200 import pspec
+    nf = 384
+    vis, flags, F, nd, _ = _headline_baseline(3)
+    Ninv, prior = np.diag(nd), np.zeros((2, nf))
+    want = ho.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, Ninv, prior, Niter=2, seed=5, solver="direct")
+    got = pspec.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, Ninv, prior, Niter=2, seed=5, verbose=False, solver="exact")
+    for o, w, k in zip(got[:6], want, KEYS):
+        assert rel(o, w) < TOL, k
+
+
+def test_headline_shape_batch_substreams_matches_oracle():
+    """The same shape through gibbs_sample_batch: 8 chains on 4 sub-streams (two distinct baselines, each loaded four
+    times), numpy draws, exact solves."""
+    from hydra_pspec_b200 import pspec
+    nf = 384
+    data = [_headline_baseline(11), _headline_baseline(12)]
+    prior = np.zeros((2, nf))
+    want = [ho.gibbs_sample_with_fg(v, fl, np.eye(nf), F, np.diag(nd), prior, Niter=2, seed=8, solver="direct")
+            for v, fl, F, nd, _ in data]
+    bls = [dict(vis=data[c % 2][0], flags=data[c % 2][1], S_initial=np.eye(nf), fgmodes=data[c % 2][2],
+                Ninv=np.diag(data[c % 2][3]), ps_prior=prior) for c in range(8)]
+    got = pspec.gibbs_sample_batch(bls, Niter=2, seed=8, rng="numpy", solver="exact", substreams=4)
+    for c in range(8):
+        for o, w, k in zip(got[c][:6], want[c % 2], KEYS):
+            assert rel(o, w) < TOL, (c, k)
