@@ -256,7 +256,10 @@ struct hp_engine {
     int gd_slots = 1;
     std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
     bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
-    bool solve2 = false;                  // k_solve2 (persistent, register-blocked) takes the solve
+    bool solve2 = false;                  // k_solve2 (persistent, register-blocked, shared W ring) takes the solve
+    bool solve3 = false;                  // k_solve3 (independent warps, W fragments streamed into registers) takes the solve
+    double *Wf1 = nullptr, *Wf2 = nullptr;   // fragment-major W for k_solve3 (k_trinv writes them)
+    hp::Solve3Sched sched3{};
     int pp_tiles = 0;                     // partial |ytilde|^2 sums per chain in Ppart: ntiles (k_solve), 2 ntiles (k_solve2)
     double* Wp1 = nullptr;                // W diag(lam): pass-1 operand of k_solve2 when Rt holds the unscaled Rfix (Philox mode)
     double *Wd = nullptr, *Yb = nullptr;
@@ -373,7 +376,7 @@ void want_basis(hp_engine* e, ArenaPlan& ap, Basis& b) {
     ap.want(&b.Gp, C * hp::tri_blocks(e->nblk) * hp::kBlkDoubles);
     ap.want(&b.Rfix, 2 * C * e->Tp * e->Np);
     if (e->cfg.rng_mode == HP_RNG_INJECTED) ap.want(&b.wa, 2 * C * e->Tp * e->Np);
-    if (e->solve2) ap.want(&b.Rt, 2 * C * e->Tp * e->Np);
+    if (e->solve2 || e->solve3) ap.want(&b.Rt, 2 * C * e->Tp * e->Np);
 }
 }  // namespace
 
@@ -435,8 +438,13 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     e->big_solve = cfg->force_dense_solve || !hp::solve_resident_ok(e->nblk, (size_t)max_smem);
     {
-        const char* v1 = getenv("HP_SOLVE_V1");   // experiments: keep the round-1 kernel
-        e->solve2 = !e->big_solve && !cfg->time_flags && hp::solve2_stages(e->nblk, (size_t)max_smem) >= 2 && !(v1 && v1[0] == '1');
+        // HP_SOLVE_KERNEL = 1 | 2 | 3 (experiments): round-1 k_solve, k_solve2, k_solve3; default: the newest that fits
+        const char* kv = getenv("HP_SOLVE_KERNEL");
+        const int want = kv ? atoi(kv) : 3;
+        const bool resident = !e->big_solve && !cfg->time_flags;
+        e->solve3 = resident && want >= 3 && hp::solve3_ok(e->nblk, (size_t)max_smem);
+        e->solve2 = resident && !e->solve3 && want >= 2 && hp::solve2_stages(e->nblk, (size_t)max_smem) >= 2;
+        if (e->solve3) hp::solve3_make_schedule(e->nblk, &e->sched3);
     }
     if (cfg->time_flags && (cfg->general_basis0 || cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms)) {
         delete e;
@@ -471,6 +479,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->Linvp, C * e->nblk * hp::kLBlkDoubles);
     ap.want(&e->Wp, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
     if (e->solve2 && cfg->rng_mode == HP_RNG_PHILOX) ap.want(&e->Wp1, C * hp::tri_blocks(e->nblk) * hp::kLBlkDoubles);
+    if (e->solve3) { ap.want(&e->Wf1, C * hp::solve3_frag_doubles(e->nblk)); ap.want(&e->Wf2, C * hp::solve3_frag_doubles(e->nblk)); }
     ap.want(&e->info, C);
     ap.want(&e->chain_ids, C);
     ap.want(&e->X, 2 * C * Tp * Np);
@@ -900,8 +909,12 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     ca.Linvp = OFFS(e->Linvp, (size_t)e->nblk * hp::kLBlkDoubles); ca.info = e->info + sb.c0;
     ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = sb.nc;
     const int nchol = hp::launch_chol(ca, sb.st);
-    hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), OFFS(e->Wp1, tri * hp::kLBlkDoubles), OFFS(e->lam, Np),
-                     e->nblk, sb.nc, sb.st);
+    {
+        // Philox mode: the stored right-hand-side tiles are the unscaled Rfix, so pass 1 multiplies by W diag(lam)
+        hp::TrinvExtra ex{OFFS(e->Wp1, tri * hp::kLBlkDoubles), OFFS(e->Wf1, hp::solve3_frag_doubles(e->nblk)),
+                          OFFS(e->Wf2, hp::solve3_frag_doubles(e->nblk)), philox ? OFFS(e->lam, Np) : nullptr};
+        hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), ex, e->nblk, sb.nc, sb.st);
+    }
     e->prof_end(CLS_CHOL, nchol + 1, sb.st);
 
     if (e->big_solve) {
@@ -946,6 +959,39 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         ++nl;
         if (!fused_inverse) {
             k_make_ssc<<<dim3(nblocks((long long)e->T * e->n), sb.nc), 256, 0, sb.st>>>(OFFS(e->Ssc, 2 * Tp * n), X, OFFS(e->lam, Np),
+                                                                                       e->n, e->Np, e->T, e->Tp);
+            ++nl;
+        }
+        e->prof_end(CLS_SOLVE, nl, sb.st);
+    } else if (e->solve3) {
+        // k_solve3: right-hand sides in tile layout (Philox: the unscaled tiles built at load time, Wf1 = W diag(lam);
+        // injected draws: r = lam * Rfix + wa rebuilt per solve, Wf1 = W)
+        e->prof_begin(CLS_SOLVE, sb.st);
+        int nl = 1;
+        const double* wa_sb = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
+        if (!philox) {
+            hp::launch_rhs_tile(OFFS(b.Rt, 2 * Tp * Np), OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->nblk, e->n, e->N, e->T,
+                                e->Tp, e->ntiles, sb.nc, sb.st);
+            ++nl;
+        }
+        hp::Solve3Args sa{};
+        sa.Wf1 = OFFS(e->Wf1, hp::solve3_frag_doubles(e->nblk)); sa.Wf2 = OFFS(e->Wf2, hp::solve3_frag_doubles(e->nblk));
+        sa.Rt = OFFS(b.Rt, 2 * Tp * Np);
+        sa.X = OFFS(e->X, 2 * Tp * Np);
+        sa.Ppart = OFFS(e->Ppart, (size_t)e->pp_tiles * n);
+        sa.nblk = e->nblk; sa.n = e->n; sa.N = e->N; sa.Tp = e->Tp; sa.ntiles = e->ntiles; sa.nsys = sb.nc; sa.T = e->T;
+        sa.philox = philox ? 1 : 0;
+        sa.key0 = (uint32_t)e->cfg.seed; sa.key1 = (uint32_t)(e->cfg.seed >> 32); sa.iter = draw_iter;
+        sa.chain_ids = OFFS(e->chain_ids, 1); sa.chain0 = sb.c0;
+        sa.sched = e->sched3;
+        hp::launch_solve3(sa, sb.st);
+        if (e->cfg.cg_compat) {
+            hp::launch_cg_scale(sa.X, OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->n, e->N, e->Np, e->T, e->Tp, sb.nc, sb.st);
+            hp::launch_colsumsq(sa.X, OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+            nl += 2;
+        }
+        if (!fused_inverse) {
+            k_make_ssc<<<dim3(nblocks((long long)e->T * e->n), sb.nc), 256, 0, sb.st>>>(OFFS(e->Ssc, 2 * Tp * n), sa.X, OFFS(e->lam, Np),
                                                                                        e->n, e->Np, e->T, e->Tp);
             ++nl;
         }
@@ -1141,7 +1187,7 @@ static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t 
     sp.lnpost_out = OFFS(e->lnpost_out, I) + it; sp.lnpost_bs = (long long)I;
     sp.n = e->n; sp.Np = e->Np; sp.T = e->T; sp.Tp = e->Tp; sp.ntiles = e->ntiles; sp.nsys = sb.nc;
     sp.ntiles = e->pp_tiles;
-    if (e->cfg.time_flags || e->big_solve || (e->solve2 && e->cfg.cg_compat)) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
+    if (e->cfg.time_flags || e->big_solve || ((e->solve2 || e->solve3) && e->cfg.cg_compat)) sp.ntiles = 1;  // one partial sum per chain (k_colsumsq)
     sp.beta_mode = general ? 1 : 0; sp.philox = philox ? 1 : 0;
     sp.key0 = (uint32_t)e->cfg.seed; sp.key1 = (uint32_t)(e->cfg.seed >> 32); sp.iter = iter;
     sp.chain_ids = OFFS(e->chain_ids, 1); sp.chain0 = sb.c0;

@@ -453,8 +453,25 @@ struct TrinvSmem {
     double V[kLBlkDoubles];      // V_ii
 };
 
+// Fragment-major copies of W for k_solve3 (hp_solve3.cu).  One k-step (4 values of k) of one 16-row strip is 32 lanes x
+// [re, im] x 2 row groups = 128 doubles: lane 4 g + q holds A[8 wi + g][4 t + q] for wi = 0, 1.
+//   pass 1: A = W1 (rows R, k = column C);  strip R / 16 stores k-steps t < 4 (strip + 1) from offset 2 s (s + 1)
+//   pass 2: A = W^H (rows = columns C of W, k = row R);  strip C / 16 stores k-steps t >= 4 strip from offset 8 nblk s - 2 s (s - 1)
+__device__ __forceinline__ void store_frag1(double* Wf1, int R, int C, double re, double im) {
+    const int s = R >> 4, t = C >> 2;
+    double* d = Wf1 + ((size_t)(2 * s * (s + 1) + t) * 128 + (4 * (R & 7) + (C & 3)) * 4 + 2 * ((R >> 3) & 1));
+    *reinterpret_cast<double2*>(d) = make_double2(re, im);
+}
+__device__ __forceinline__ void store_frag2(double* Wf2, int nblk, int R, int C, double re, double im) {
+    const int s = C >> 4, t = R >> 2;
+    double* d = Wf2 + ((size_t)(8 * nblk * s - 2 * s * (s - 1) + t - 4 * s) * 128 + (4 * (C & 7) + (R & 3)) * 4 + 2 * ((C >> 3) & 1));
+    *reinterpret_cast<double2*>(d) = make_double2(re, im);
+}
+
 __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all, const double* __restrict__ Linvp_all,
-                                               double* Wp_all, double* Wp1_all, const double* __restrict__ lam_all, int nblk) {
+                                               double* Wp_all, TrinvExtra ex, int nblk) {
+    double* Wp1_all = ex.Wp1;
+    const double* lam_all = ex.lam;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrinvSmem& s = *reinterpret_cast<TrinvSmem*>(smem_raw);
     const int j = blockIdx.x, sys = blockIdx.y;
@@ -462,8 +479,11 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
     const double* Vp = Linvp_all + (size_t)sys * nblk * kLBlkDoubles;
     double* Wp = Wp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
     // W1 = W diag(lam): columns of block column j scaled by lam[32 j ..]
-    double* Wp1 = Wp1_all ? Wp1_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles : nullptr;
+    double* Wp1 = (Wp1_all && lam_all) ? Wp1_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles : nullptr;
     const double* lamj = lam_all ? lam_all + (size_t)sys * nblk * 32 + 32 * j : nullptr;
+    const size_t wf = (size_t)4 * nblk * (2 * nblk + 1) * 128;
+    double* Wf1 = ex.Wf1 ? ex.Wf1 + (size_t)sys * wf : nullptr;
+    double* Wf2 = ex.Wf2 ? ex.Wf2 + (size_t)sys * wf : nullptr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q = lane & 3;
     const int ti = warp >> 2, tj = warp & 3;
@@ -474,6 +494,19 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
         if (Wp1) {
             const int c = (e % kLPlane) % kLdBlk;
             Wp1[blk_index(j, j) * kLBlkDoubles + e] = c < 32 ? v * lamj[c] : 0.0;
+        }
+    }
+    if (Wf1 || Wf2) {
+        // diagonal block (lower triangular, zeros above the diagonal are part of the 16-row strips' k range)
+        const double* Vb = Vp + (size_t)j * kLBlkDoubles;
+        for (int e = tid; e < 1024; e += kCT) {
+            const int r = e >> 5, c = e & 31;
+            const double re = Vb[r * kLdBlk + c], im = Vb[kLPlane + r * kLdBlk + c];
+            if (Wf1 && c < 16 * ((r >> 4) + 1)) {
+                const double l = lamj ? lamj[c] : 1.0;
+                store_frag1(Wf1, 32 * j + r, 32 * j + c, l * re, l * im);
+            }
+            if (Wf2 && r >= 16 * (c >> 4)) store_frag2(Wf2, nblk, 32 * j + r, 32 * j + c, re, im);
         }
     }
     for (int i = j + 1; i < nblk; ++i) {
@@ -528,18 +561,28 @@ __global__ void __launch_bounds__(kCT) k_trinv(const double* __restrict__ Lp_all
             *reinterpret_cast<double2*>(Wb1 + r * kLdBlk + c) = make_double2(l0 * dr[0][0][0], l1 * dr[0][0][1]);
             *reinterpret_cast<double2*>(Wb1 + kLPlane + r * kLdBlk + c) = make_double2(l0 * di[0][0][0], l1 * di[0][0][1]);
         }
+        if (Wf1 || Wf2) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int R = 32 * i + r, C = 32 * j + c + e;
+                if (Wf1) {
+                    const double l = lamj ? lamj[c + e] : 1.0;
+                    store_frag1(Wf1, R, C, l * dr[0][0][e], l * di[0][0][e]);
+                }
+                if (Wf2) store_frag2(Wf2, nblk, R, C, dr[0][0][e], di[0][0][e]);
+            }
+        }
     }
 }
 
-void launch_trinv(const double* Lp, const double* Linvp, double* Wp, double* Wp1, const double* lam, int nblk, int nsys,
-                  cudaStream_t st) {
+void launch_trinv(const double* Lp, const double* Linvp, double* Wp, const TrinvExtra& ex, int nblk, int nsys, cudaStream_t st) {
     static bool attr_dev[kMaxDev] = {false};
     bool& attr_set = attr_dev[current_device_slot()];
     if (!attr_set) {
         cudaFuncSetAttribute(k_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrinvSmem));
         attr_set = true;
     }
-    k_trinv<<<dim3(nblk, nsys), kCT, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, Wp1, lam, nblk);
+    k_trinv<<<dim3(nblk, nsys), kCT, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, ex, nblk);
 }
 
 // ==========================================================================================

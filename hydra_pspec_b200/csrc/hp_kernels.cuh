@@ -66,8 +66,10 @@ struct CholArgs {
 int launch_chol(const CholArgs& a, cudaStream_t st);   // returns the number of kernel launches (1, or 2 nblk - 1 in column mode)
 // W = L^-1 in the same padded block layout as L ([nsys][tri_blocks][2304]); Wp1 (optional) receives W diag(lam), the
 // pass-1 operand of k_solve2 when the stored right-hand sides are unscaled (lam: [nsys][Np])
-void launch_trinv(const double* Lp, const double* Linvp, double* Wp, double* Wp1, const double* lam, int nblk, int nsys,
-                  cudaStream_t st);
+//   ex.Wp1: W diag(lam) in block layout (k_solve2 pass 1);  ex.Wf1 / ex.Wf2: fragment-major copies for k_solve3
+//   (hp_solve3.cu: Wf1 = pass-1 operand, scaled by lam when ex.lam is given; Wf2 = W in pass-2 (transposed) fragment order)
+struct TrinvExtra { double* Wp1; double* Wf1; double* Wf2; const double* lam; };
+void launch_trinv(const double* Lp, const double* Linvp, double* Wp, const TrinvExtra& ex, int nblk, int nsys, cudaStream_t st);
 
 struct SolveArgs {
     const double* Wp;      // [nsys][tri_blocks][2304]  W = L^-1 (k_trinv)
@@ -113,6 +115,33 @@ void launch_rhs_tile(double* Rt, const double* Rfix, const double* wa, const dou
 // scalar model of the reference's truncated CG applied to the global solution X (every solve path)
 void launch_cg_scale(double* X, const double* Rfix, const double* wa, const double* lam, int n, int N, int Np, int T, int Tp,
                      int nsys, cudaStream_t st);
+
+// ---- k_solve3 (hp_solve3.cu): independent warps, W fragments streamed from L2 into registers ------------------------
+constexpr int kS3Warps = 8;          // warps of a k_solve3 CTA (all of them compute)
+constexpr int kS3MaxStrips = 28;     // 16-row strips of the system (Np <= 448: two shared-memory tiles)
+constexpr int kS3MaxPerWarp = 8;
+struct Solve3Sched {                 // per pass and warp: the strips it owns, longest first (solve3_make_schedule)
+    uint8_t n[2][kS3Warps];
+    uint8_t strip[2][kS3Warps][kS3MaxPerWarp];
+};
+struct Solve3Args {
+    const double* Wf1;     // [nsys][solve3_frag_doubles] pass-1 operand in fragment-major order (W, or W diag(lam))
+    const double* Wf2;     // [nsys][solve3_frag_doubles] pass-2 operand (W, transposed fragment order)
+    const double* Rt;      // [nsys][ntiles][nblk][2][32][16] right-hand sides in tile layout (k_rhs_tile)
+    double* X;             // [nsys][Tp][Np] complex
+    double* Ppart;         // [nsys][ntiles][n]
+    int nblk, n, N, Tp, ntiles, nsys, T;
+    int philox;
+    uint32_t key0, key1, iter;
+    const int* chain_ids;
+    int chain0;
+    int grid_limit;
+    Solve3Sched sched;
+};
+void launch_solve3(const Solve3Args& a, cudaStream_t st);
+bool solve3_ok(int nblk, size_t max_smem);
+size_t solve3_frag_doubles(int nblk);               // doubles per system of Wf1 (and of Wf2)
+void solve3_make_schedule(int nblk, Solve3Sched* sc);
 
 struct PostArgs {
     const double* Sf;      // [nsys][>=T][n] complex: signal in frequency space (rows t < T are read)

@@ -53,7 +53,7 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
     hp::CholArgs ca{};
     ca.Gp = dGp; ca.lam = dlam; ca.Lp = dLp; ca.Linvp = dLinv; ca.info = dinfo; ca.nblk = nblk; ca.n = n; ca.N = N; ca.nsys = 1;
     hp::launch_chol(ca, 0);
-    hp::launch_trinv(dLp, dLinv, dWp, nullptr, nullptr, nblk, 1, 0);
+    hp::launch_trinv(dLp, dLinv, dWp, hp::TrinvExtra{nullptr, nullptr, nullptr, nullptr}, nblk, 1, 0);
     hp::SolveArgs sa{};
     sa.Wp = dWp; sa.lam = dlam; sa.Rfix = dR; sa.wa = dW; sa.X = dX; sa.Ssc = dS; sa.Ppart = dP;
     sa.nblk = nblk; sa.n = n; sa.N = N; sa.Tp = Tp; sa.ntiles = ntiles; sa.nsys = 1; sa.T = T; sa.cg_compat = cg_compat;
@@ -88,12 +88,15 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
 // and W1 = W.  grid_limit > 0 caps the persistent grid (several tiles per CTA at test sizes).
 // X [nsys][T][N]; psum [nsys][n] = sum_t |x_k|^2 from the kernel's partial sums (or NULL).
 int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double* lam, const double* Rfix, const double* wa,
-                   int cg_compat, int grid_limit, double* X, double* psum) {
+                   int cg_compat, int grid_limit, int variant, double* X, double* psum) {
     const int N = n + m, nblk = (N + 31) / 32, Np = nblk * 32, ntiles = (T + 15) / 16, Tp = ntiles * 16;
     int max_smem = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (hp::solve2_stages(nblk, (size_t)max_smem) == 0) return HP_ERR_SIZE;
+    if (variant == 3 ? !hp::solve3_ok(nblk, (size_t)max_smem) : hp::solve2_stages(nblk, (size_t)max_smem) == 0) return HP_ERR_SIZE;
+    const int ppt = variant == 3 ? ntiles : 2 * ntiles;   // partial sums per system
+    const size_t wf = hp::solve3_frag_doubles(nblk);
+    double *dWf1 = nullptr, *dWf2 = nullptr;
     double *dG, *dGp, *dlam, *dLp, *dLinv, *dWp, *dWp1, *dR, *dW = nullptr, *dX, *dP, *dRt;
     int* dinfo;
     const size_t tri = hp::tri_blocks(nblk) * hp::kLBlkDoubles, trig = hp::tri_blocks(nblk) * hp::kBlkDoubles;
@@ -116,8 +119,13 @@ int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double*
     hp::CholArgs ca{};
     ca.Gp = dGp; ca.lam = dlam; ca.Lp = dLp; ca.Linvp = dLinv; ca.info = dinfo; ca.nblk = nblk; ca.n = n; ca.N = N; ca.nsys = 1;
     hp::launch_chol(ca, 0);
-    hp::launch_trinv(dLp, dLinv, dWp, dWp1, dlam, nblk, 1, 0);
-    // every system uses the one factor: replicate the per-system strides by giving k_solve2 nsys = 1 per launch
+    if (variant == 3) {
+        cudaMalloc(&dWf1, 8 * wf * nsys); cudaMalloc(&dWf2, 8 * wf * nsys);
+        cudaMemset(dWf1, 0xff, 8 * wf * nsys); cudaMemset(dWf2, 0xff, 8 * wf * nsys);   // NaN: every fragment must be written
+    }
+    // wa given: r = lam * Rfix + wa is built by k_rhs_tile and pass 1 uses the unscaled W
+    hp::launch_trinv(dLp, dLinv, dWp, hp::TrinvExtra{dWp1, dWf1, dWf2, wa ? nullptr : dlam}, nblk, 1, 0);
+    if (variant != 3 && wa) cudaMemcpy(dWp1, dWp, 8 * tri, cudaMemcpyDeviceToDevice);
     for (int s = 0; s < nsys; ++s) {
         // lam is shared: k_rhs_tile indexes lam by system, so build one system at a time
         hp::launch_rhs_tile(dRt + (size_t)s * ntiles * nblk * 2 * 32 * hp::kTT, dR + 2ull * s * Tp * Np,
@@ -128,13 +136,26 @@ int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double*
     cudaMalloc(&dWall, 8 * tri * nsys); cudaMalloc(&dW1all, 8 * tri * nsys);
     for (int s = 0; s < nsys; ++s) {
         cudaMemcpy(dWall + tri * s, dWp, 8 * tri, cudaMemcpyDeviceToDevice);
-        cudaMemcpy(dW1all + tri * s, wa ? dWp : dWp1, 8 * tri, cudaMemcpyDeviceToDevice);
+        cudaMemcpy(dW1all + tri * s, dWp1, 8 * tri, cudaMemcpyDeviceToDevice);
+        if (variant == 3 && s > 0) {
+            cudaMemcpy(dWf1 + wf * s, dWf1, 8 * wf, cudaMemcpyDeviceToDevice);
+            cudaMemcpy(dWf2 + wf * s, dWf2, 8 * wf, cudaMemcpyDeviceToDevice);
+        }
     }
+    if (variant == 3) {
+        hp::Solve3Args s3{};
+        s3.Wf1 = dWf1; s3.Wf2 = dWf2; s3.Rt = dRt; s3.X = dX; s3.Ppart = dP;
+        s3.nblk = nblk; s3.n = n; s3.N = N; s3.Tp = Tp; s3.ntiles = ntiles; s3.nsys = nsys; s3.T = T;
+        s3.philox = 0; s3.grid_limit = grid_limit;
+        hp::solve3_make_schedule(nblk, &s3.sched);
+        hp::launch_solve3(s3, 0);
+    } else {
     hp::Solve2Args sa{};
     sa.W1 = dW1all; sa.W2 = dWall; sa.Rt = dRt; sa.X = dX; sa.Ppart = dP;
     sa.nblk = nblk; sa.n = n; sa.N = N; sa.Tp = Tp; sa.ntiles = ntiles; sa.nsys = nsys; sa.T = T;
     sa.philox = 0; sa.grid_limit = grid_limit;
     hp::launch_solve2(sa, 0);
+    }
     if (cg_compat)
         for (int s = 0; s < nsys; ++s)
             hp::launch_cg_scale(dX + 2ull * s * Tp * Np, dR + 2ull * s * Tp * Np, dW ? dW + 2ull * s * Tp * Np : nullptr, dlam, n, N,
@@ -144,18 +165,18 @@ int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double*
         for (int s = 0; s < nsys; ++s)
             cudaMemcpy2D(X + 2ull * s * T * N, 16ull * N, dX + 2ull * s * Tp * Np, 16ull * Np, 16ull * N, T, cudaMemcpyDeviceToHost);
         if (psum) {
-            std::vector<double> pp((size_t)nsys * 2 * ntiles * n);
+            std::vector<double> pp((size_t)nsys * ppt * n);
             cudaMemcpy(pp.data(), dP, 8 * pp.size(), cudaMemcpyDeviceToHost);
             for (int s = 0; s < nsys; ++s)
                 for (int k = 0; k < n; ++k) {
                     double acc = 0.0;
-                    for (int tl = 0; tl < 2 * ntiles; ++tl) acc += pp[((size_t)s * 2 * ntiles + tl) * n + k];
+                    for (int tl = 0; tl < ppt; ++tl) acc += pp[((size_t)s * ppt + tl) * n + k];
                     psum[(size_t)s * n + k] = acc;
                 }
         }
     }
     cudaFree(dG); cudaFree(dGp); cudaFree(dlam); cudaFree(dLp); cudaFree(dLinv); cudaFree(dWp); cudaFree(dWp1); cudaFree(dR);
-    cudaFree(dW); cudaFree(dX); cudaFree(dP); cudaFree(dinfo); cudaFree(dRt); cudaFree(dWall); cudaFree(dW1all);
+    cudaFree(dW); cudaFree(dX); cudaFree(dP); cudaFree(dinfo); cudaFree(dRt); cudaFree(dWall); cudaFree(dW1all); cudaFree(dWf1); cudaFree(dWf2);
     return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
 }
 

@@ -19,6 +19,7 @@ Two fidelity modes
     Device Philox4x32-10 draws, exact solves, new fluctuation terms every iteration
     (``refresh_omega=True``) -- the production mode used by :class:`GibbsEngine` and ``bench.py``.
 """
+import os
 import time
 
 import numpy as np
@@ -198,7 +199,7 @@ class GibbsEngine:
     def __init__(self, nchains, ntimes, nfreqs, nmodes, max_iters, rng="philox", cg_compat=False,
                  refresh_omega=True, keep=("cr", "fg", "chisq"), general_basis0=False, seed=0, device=0,
                  stream=None, profile=False, force_dense_transforms=False, dense_noise=False, substreams=1,
-                 time_flags=False, force_dense_solve=False):
+                 time_flags=False, force_dense_solve=False, ring_iters=0):
         self._h = None
         L = _lib.lib()
         cfg = _lib.HPConfig()
@@ -220,6 +221,7 @@ class GibbsEngine:
         cfg.substreams = int(substreams)
         cfg.time_flags = int(bool(time_flags))
         cfg.force_dense_solve = int(bool(force_dense_solve or _FORCE_DENSE_SOLVE))
+        cfg.ring_iters = int(ring_iters)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.stream = stream
         h = _lib.C.c_void_p()
@@ -295,9 +297,11 @@ class GibbsEngine:
             out["chisq"] = mk((C, iters, T, n), np.float64)
         return out
 
-    def run_to_host(self, niter, bufs):
+    def run_to_host(self, niter, bufs, first_iter=0):
         """Run ``niter`` iterations and stream every iteration's arrays into ``bufs`` (from
-        :meth:`host_buffers`) while the next iteration computes; returns when all data has landed."""
+        :meth:`host_buffers`) while the next iteration computes; returns when all data has landed.
+        Iteration ``i`` of the chain lands in slot ``i - first_iter`` of the host arrays: a bounded staging area is
+        re-used chunk after chunk by passing the index of the chunk's first iteration."""
         sink = _lib.HPHostSink()
         for k in ("signal_ps", "ln_post", "signal_cr", "fg_amps", "chisq"):
             a = bufs.get(k)
@@ -305,6 +309,7 @@ class GibbsEngine:
                 assert a.flags["C_CONTIGUOUS"] and a.shape[0] == self.nchains
                 setattr(sink, k, a.ctypes.data)
         sink.iters = int(bufs["signal_ps"].shape[1])
+        sink.first_iter = int(first_iter)
         _lib.check(_lib.lib().hp_engine_run_to_host(self._h, int(niter), _lib.C.byref(sink)))
 
     def gcr(self):
@@ -391,6 +396,48 @@ class GibbsEngine:
         return out
 
 
+
+# Device slots of the big per-iteration outputs when they are streamed to the host (cfg.ring_iters): the device footprint
+# of a chain does not grow with Niter (the reference keeps one baseline's samples in host RAM, pspec.py:590-596).
+_RING_ITERS = 3
+_STAGING_BYTES = int(float(os.environ.get("HP_STAGING_GB", "2")) * 2 ** 30)   # page-locked staging area
+
+
+def _big_bytes_per_iter(nchains, ntimes, nfreqs, nmodes, keep):
+    per = 0
+    if "cr" in keep:
+        per += ntimes * nfreqs * 16
+    if "fg" in keep:
+        per += ntimes * nmodes * 16
+    if "chisq" in keep:
+        per += ntimes * nfreqs * 8
+    return nchains * (per + nfreqs * 8 + 8)
+
+
+def _staged_run(eng, Niter, dest, write_Niter=None, after_chunk=None):
+    """Run ``Niter`` iterations of ``eng`` through a bounded page-locked staging area.
+
+    ``dest``: dict of host arrays ``[nchains][Niter][...]`` (numpy arrays or ``np.memmap``) that receive the samples;
+    ``after_chunk(done)`` is called whenever ``done`` is a multiple of ``write_Niter`` (and at the end).
+    """
+    per_iter = _big_bytes_per_iter(eng.nchains, eng.ntimes, eng.nfreqs, eng.nmodes, eng.keep)
+    chunk = max(1, min(Niter, _STAGING_BYTES // max(per_iter, 1)))
+    if write_Niter:
+        chunk = min(chunk, write_Niter)
+    stage = eng.host_buffers(chunk)
+    done = 0
+    while done < Niter:
+        c = min(chunk, Niter - done)
+        if write_Niter:   # never run past a write boundary (pspec.py:625: files every write_Niter iterations)
+            c = min(c, write_Niter - done % write_Niter)
+        eng.run_to_host(c, stage, first_iter=done)
+        for k, a in dest.items():
+            if a is not None:
+                a[:, done:done + c] = stage[k][:, :c]
+        done += c
+        if after_chunk is not None and (done == Niter or (write_Niter and done % write_Niter == 0)):
+            after_chunk(done)
+
 # --------------------------------------------------------------------------------------------
 class GCRMatrices:
     """What :func:`build_matrices` returns on the device path.
@@ -434,7 +481,7 @@ def _check_per_time_supported(solver, basis0, ninv_dense):
 
 
 def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng, solver, map_estimate, keep,
-                         seed, device, s_uniforms=None):
+                         seed, device, s_uniforms=None, ring_iters=0):
     """Engine with one chain loaded and (numpy mode) its draws injected."""
     vis = np.asarray(vis)
     ntimes, nfreqs = vis.shape
@@ -452,7 +499,7 @@ def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng,
                       refresh_omega=(rng == "philox"), keep=keep, general_basis0=basis0 is not None,
                       seed=0 if seed is None else seed, device=device,
                       force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=ninv_dense is not None,
-                      time_flags=per_time)
+                      time_flags=per_time, ring_iters=ring_iters)
     eng.load_chain(0, vis, flags, fgmodes, ninv_diag, lam0sq, ps_prior=ps_prior, basis0=basis0, ninv_dense=ninv_dense,
                    nih_dense=nih_dense)
     if rng == "numpy":
@@ -560,34 +607,36 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
             u = np.array([np.random.uniform() for _ in range(nfreqs)])[None, :]  # global stream, not reseeded
         else:
             u = np.random.RandomState(seed).uniform(size=(Niter, nfreqs))  # pspec.py:577
+    nmodes = fgmodes.shape[1]
     eng = _single_chain_engine(vis, flags, S_initial, fgmodes, Ninv, pr, Niter, rng, solver, map_estimate,
-                               ("cr", "fg", "chisq"), seed, device, s_uniforms=u)
-    write_time = 0.0
+                               ("cr", "fg", "chisq"), seed, device, s_uniforms=u, ring_iters=_RING_ITERS)
+    write_time = [0.0]
     try:
-        bufs = eng.host_buffers(Niter)
-        done = 0
-        while done < Niter:
-            chunk = min(write_Niter, Niter - done) if out_dir is not None else Niter - done
-            eng.run_to_host(chunk, bufs)
-            done += chunk
-            if out_dir is not None:
-                t0 = time.perf_counter()
-                utils.write_numpy_files(out_dir, bufs["signal_cr"][0, :done], eng.signal_S(0), bufs["signal_ps"][0, :done],
-                                        bufs["fg_amps"][0, :done], bufs["chisq"][0, :done], bufs["ln_post"][0, :done])
-                write_time += time.perf_counter() - t0
+        # the reference's return arrays (pspec.py:590-596), filled chunk by chunk from a bounded page-locked staging area
+        signal_cr = np.empty((1, Niter, ntimes, nfreqs), dtype=np.complex128)
+        signal_ps = np.empty((1, Niter, nfreqs))
+        fg_amps = np.empty((1, Niter, ntimes, nmodes), dtype=np.complex128)
+        chisq = np.empty((1, Niter, ntimes, nfreqs))
+        ln_post = np.empty((1, Niter))
+        dest = dict(signal_cr=signal_cr, signal_ps=signal_ps, fg_amps=fg_amps, chisq=chisq, ln_post=ln_post)
+
+        def write(done):
+            t0 = time.perf_counter()
+            utils.write_numpy_files(out_dir, signal_cr[0, :done], eng.signal_S(0), signal_ps[0, :done], fg_amps[0, :done],
+                                    chisq[0, :done], ln_post[0, :done])
+            write_time[0] += time.perf_counter() - t0
+
+        _staged_run(eng, Niter, dest, write_Niter=write_Niter if out_dir is not None else None,
+                    after_chunk=write if out_dir is not None else None)
         bad = eng.info()
         if np.any(bad != 0):
             raise np.linalg.LinAlgError("GCR system not positive definite (Cholesky failed in block column "
                                         f"{int(bad[0]) - 1})")
-        # copies: the page-locked staging arrays are released with the engine's buffers
-        signal_cr = np.array(bufs["signal_cr"][0])
         signal_S = eng.signal_S(0)
-        signal_ps = np.array(bufs["signal_ps"][0])
-        fg_amps = np.array(bufs["fg_amps"][0])
-        chisq = np.array(bufs["chisq"][0])
-        ln_post = np.array(bufs["ln_post"][0])
+        signal_cr, signal_ps, fg_amps, chisq, ln_post = signal_cr[0], signal_ps[0], fg_amps[0], chisq[0], ln_post[0]
     finally:
         eng.close()
+    write_time = write_time[0]
     if verbose:
         for i, lp in enumerate(ln_post):
             print(f"{i + 1:<9d}{lp:<12.1f}")
@@ -643,60 +692,130 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
         for p in prep:  # a batch is per-time as a whole
             if p["flags"].ndim == 1:
                 p["flags"] = np.broadcast_to(p["flags"], (ntimes, nfreqs)).copy()
-    eng = GibbsEngine(nb, ntimes, nfreqs, nmodes, Niter, rng=rng, cg_compat=(solver == "reference-cg"),
-                      refresh_omega=(rng == "philox"), keep=keep, general_basis0=general,
-                      seed=0 if seed is None else seed, device=device,
-                      force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=dense, time_flags=per_time,
-                      substreams=substreams)
-    if chain_ids is not None:
-        eng.set_chain_ids(chain_ids)
-    write_times = [0.0] * nb
-    try:
-        if rng == "numpy":
-            oma, omb = (None, None) if map_estimate else _reference_gcr_draws(ntimes, nfreqs)
-            if map_estimate:
-                u = np.array([np.random.uniform() for _ in range(nfreqs)])[None, :]
+    ids = np.arange(nb, dtype=np.int32) if chain_ids is None else np.ascontiguousarray(chain_ids, dtype=np.int32)
+    assert ids.shape == (nb,)
+    keep = tuple(keep)
+    if rng == "numpy":
+        oma, omb = (None, None) if map_estimate else _reference_gcr_draws(ntimes, nfreqs)
+        if map_estimate:
+            u = np.array([np.random.uniform() for _ in range(nfreqs)])[None, :]
+        else:
+            u = np.random.RandomState(seed).uniform(size=(Niter, nfreqs))
+
+    # ---- where the samples go.  In host RAM when they fit (HP_HOST_BUDGET_GB, default: half of the available memory);
+    # otherwise every baseline must have an out_dir and its big arrays are written through np.memmap'ed .npy files
+    # (the reference's file names), chunk by chunk -- neither host nor device memory grows with Niter x Nbaselines.
+    per_iter = _big_bytes_per_iter(nb, ntimes, nfreqs, nmodes, keep)
+    budget = os.environ.get("HP_HOST_BUDGET_GB")
+    if budget is not None:
+        budget = float(budget) * 2 ** 30
+    else:
+        try:
+            import psutil
+            budget = 0.5 * psutil.virtual_memory().available
+        except Exception:  # noqa: BLE001
+            budget = 64 * 2 ** 30
+    in_ram = per_iter * Niter <= budget
+    if not in_ram and any(b.get("out_dir") is None for b in baselines) and any(k in keep for k in ("cr", "fg", "chisq")):
+        raise MemoryError(f"the sample arrays of this batch need {per_iter * Niter / 2 ** 30:.1f} GiB of host memory: pass an "
+                          "out_dir per baseline (they are then written through memory-mapped .npy files), or keep=()")
+    shapes = dict(signal_cr=((Niter, ntimes, nfreqs), np.complex128, "cr", "gcr-eor.npy"),
+                  fg_amps=((Niter, ntimes, nmodes), np.complex128, "fg", "fg-amps.npy"),
+                  chisq=((Niter, ntimes, nfreqs), np.float64, "chisq", "chisq.npy"))
+    results = [dict(signal_ps=np.empty((Niter, nfreqs)), ln_post=np.empty(Niter)) for _ in range(nb)]
+    for c, b in enumerate(baselines):
+        for k, (shape, dt, kk, fname) in shapes.items():
+            if kk not in keep:
+                results[c][k] = None
+            elif in_ram:
+                results[c][k] = np.empty(shape, dtype=dt)
             else:
-                u = np.random.RandomState(seed).uniform(size=(Niter, nfreqs))
-        for c, p in enumerate(prep):
-            b0, nD, nH = p["basis0"], p["nD"], p["nH"]
-            if general and b0 is None:
-                b0 = np.ascontiguousarray(_unitary_dft(nfreqs).conj().T)
-            if dense and nD is None:
-                nD = np.diag(p["nd"]).astype(np.complex128)
-                if rng == "numpy" and not map_estimate:
-                    nH = np.diag(np.sqrt(p["nd"] * p["flags"].astype(float))).astype(np.complex128)
-            eng.load_chain(c, p["vis"], p["flags"], p["F"], p["nd"], p["lam0sq"], ps_prior=p["prior"], basis0=b0,
-                           ninv_dense=nD, nih_dense=nH)
-            if rng == "numpy":
-                eng.set_draws(c, oma, omb, _s_draws_from_uniforms(u, p["prior"], ntimes))
-        bufs = eng.host_buffers(Niter)
-        done = 0
-        any_out = any(b.get("out_dir") is not None for b in baselines)
-        while done < Niter:
-            chunk = min(write_Niter, Niter - done) if any_out else Niter - done
-            eng.run_to_host(chunk, bufs)
-            done += chunk
-            for c, b in enumerate(baselines):
-                if b.get("out_dir") is None:
-                    continue
-                t0 = time.perf_counter()
-                z = lambda k: bufs[k][c, :done] if k in bufs else np.zeros(0)  # noqa: E731
-                utils.write_numpy_files(b["out_dir"], z("signal_cr"), eng.signal_S(c), bufs["signal_ps"][c, :done],
-                                        z("fg_amps"), z("chisq"), bufs["ln_post"][c, :done])
-                write_times[c] += time.perf_counter() - t0
-        bad = eng.info()
-        if np.any(bad != 0):
-            c = int(np.flatnonzero(bad)[0])
-            raise np.linalg.LinAlgError(f"GCR system of baseline {c} of the batch is not positive definite "
-                                        f"(Cholesky failed in block column {int(bad[c]) - 1})")
-        out = []
-        for c in range(nb):
-            g = lambda k: np.array(bufs[k][c]) if k in bufs else None  # noqa: E731
-            out.append((g("signal_cr"), eng.signal_S(c), g("signal_ps"), g("fg_amps"), g("chisq"), g("ln_post"),
-                        write_times[c]))
-    finally:
-        eng.close()
+                results[c][k] = np.lib.format.open_memmap(os.path.join(str(b["out_dir"]), fname), mode="w+", dtype=dt, shape=shape)
+
+    # ---- how many chains share an engine: all of them unless the device arena would not fit (then groups run one after
+    # the other; the Philox chain ids keep the samples independent of the grouping)
+    Np = 32 * ((nfreqs + nmodes + 31) // 32)
+    Tp = 16 * ((ntimes + 15) // 16)
+    per_chain = 16 * Tp * Np * (4 if rng == "numpy" else 3) + 16 * Tp * nfreqs * 3 + 16 * nfreqs * Np * (2 if general else 1) \
+        + 8 * 3 * (Np * Np // 2 + 18 * Np) * 2 + _RING_ITERS * per_iter // nb + 8 * Niter * nfreqs * (2 if rng == "numpy" else 1)
+    if dense:
+        per_chain += 16 * nfreqs * nfreqs * 3 + 16 * Tp * nfreqs * 2
+    if per_time:
+        per_chain += 16 * Tp * (1 + nmodes) * Np + 8 * Tp * nfreqs
+    dev_budget = float(os.environ.get("HP_DEVICE_BUDGET_GB", "150")) * 2 ** 30
+    group = max(1, min(nb, int(dev_budget // per_chain)))
+    write_times = [0.0] * nb
+    signal_S = [None] * nb
+    any_out = any(b.get("out_dir") is not None for b in baselines)
+
+    for g0 in range(0, nb, group):
+        cs = list(range(g0, min(nb, g0 + group)))
+        eng = GibbsEngine(len(cs), ntimes, nfreqs, nmodes, Niter, rng=rng, cg_compat=(solver == "reference-cg"),
+                          refresh_omega=(rng == "philox"), keep=keep, general_basis0=general,
+                          seed=0 if seed is None else seed, device=device,
+                          force_dense_transforms=_FORCE_DENSE_TRANSFORMS and not per_time, dense_noise=dense,
+                          time_flags=per_time, substreams=substreams, ring_iters=_RING_ITERS)
+        try:
+            eng.set_chain_ids(ids[cs])
+            for lc, c in enumerate(cs):
+                p = prep[c]
+                b0, nD, nH = p["basis0"], p["nD"], p["nH"]
+                if general and b0 is None:
+                    b0 = np.ascontiguousarray(_unitary_dft(nfreqs).conj().T)
+                if dense and nD is None:
+                    nD = np.diag(p["nd"]).astype(np.complex128)
+                    if rng == "numpy" and not map_estimate:
+                        nH = np.diag(np.sqrt(p["nd"] * p["flags"].astype(float))).astype(np.complex128)
+                eng.load_chain(lc, p["vis"], p["flags"], p["F"], p["nd"], p["lam0sq"], ps_prior=p["prior"], basis0=b0,
+                               ninv_dense=nD, nih_dense=nH)
+                if rng == "numpy":
+                    eng.set_draws(lc, oma, omb, _s_draws_from_uniforms(u, p["prior"], ntimes))
+
+            class _Dest:
+                """[chain][iteration] view over the per-baseline destination arrays of this group."""
+                def __init__(self, key):
+                    self.key = key
+
+                def __setitem__(self, idx, val):
+                    _, its = idx
+                    for lc, c in enumerate(cs):
+                        results[c][self.key][its] = val[lc]
+
+            dest = {k: (_Dest(k) if (k in ("signal_ps", "ln_post") or results[cs[0]][k] is not None) else None)
+                    for k in ("signal_ps", "ln_post", "signal_cr", "fg_amps", "chisq")}
+
+            def write(done):
+                for lc, c in enumerate(cs):
+                    b = baselines[c]
+                    if b.get("out_dir") is None:
+                        continue
+                    t0 = time.perf_counter()
+                    r = results[c]
+                    if in_ram:
+                        z = lambda k: r[k][:done] if r[k] is not None else np.zeros(0)  # noqa: E731
+                        utils.write_numpy_files(b["out_dir"], z("signal_cr"), eng.signal_S(lc), r["signal_ps"][:done],
+                                                z("fg_amps"), z("chisq"), r["ln_post"][:done])
+                    else:
+                        for k in ("signal_cr", "fg_amps", "chisq"):
+                            if r[k] is not None:
+                                r[k].flush()
+                        np.save(os.path.join(str(b["out_dir"]), "cov-eor.npy"), eng.signal_S(lc))
+                        np.save(os.path.join(str(b["out_dir"]), "dps-eor.npy"), r["signal_ps"][:done])
+                        np.save(os.path.join(str(b["out_dir"]), "ln-post.npy"), r["ln_post"][:done])
+                    write_times[c] += time.perf_counter() - t0
+
+            _staged_run(eng, Niter, dest, write_Niter=write_Niter if any_out else None, after_chunk=write if any_out else None)
+            bad = eng.info()
+            if np.any(bad != 0):
+                lc = int(np.flatnonzero(bad)[0])
+                raise np.linalg.LinAlgError(f"GCR system of baseline {cs[lc]} of the batch is not positive definite "
+                                            f"(Cholesky failed in block column {int(bad[lc]) - 1})")
+            for lc, c in enumerate(cs):
+                signal_S[c] = eng.signal_S(lc)
+        finally:
+            eng.close()
+    out = [(results[c]["signal_cr"], signal_S[c], results[c]["signal_ps"], results[c]["fg_amps"], results[c]["chisq"],
+            results[c]["ln_post"], write_times[c]) for c in range(nb)]
     if verbose:
         for c in range(nb):
             print(f"baseline {c}: ln_post[-1] = {out[c][5][-1]:.1f}")

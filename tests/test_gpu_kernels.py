@@ -150,8 +150,11 @@ def test_two_devices_in_one_process():
     (384, 32, 40, 1, 0, True, 1),
     (500, 44, 20, 1, 0, False, 0),    # Np = 544: the largest k_solve2 takes (2-stage ring)
 ])
-def test_solve2(n, m, T, nsys, grid, use_wa, cg):
-    """k_solve2 (persistent register-blocked solve) against numpy: X, and the sum_t |x|^2 partial sums."""
+@pytest.mark.parametrize("variant", [2, 3])
+def test_solve2(n, m, T, nsys, grid, use_wa, cg, variant):
+    """k_solve2 / k_solve3 (persistent solves, hp_solve2.cu / hp_solve3.cu) against numpy: X, and the sum_t |x|^2 sums."""
+    if variant == 3 and n + m > 448:
+        pytest.skip("k_solve3 keeps two tiles in shared memory: Np <= 448")
     from oracle import hydra_oracle as ho  # checker only
     L = _lib()
     rng = np.random.default_rng(7 * n + m + T + nsys)
@@ -178,7 +181,7 @@ def test_solve2(n, m, T, nsys, grid, use_wa, cg):
     X = np.empty((nsys, T, N), dtype=np.complex128)
     psum = np.empty((nsys, n))
     L.check(L.lib().hp_test_solve2(n, m, T, nsys, L.ptr(G), L.ptr(lam), L.ptr(np.ascontiguousarray(Rfix)),
-                                   L.ptr(None if wa is None else np.ascontiguousarray(wa)), cg, grid, L.ptr(X), L.ptr(psum)))
+                                   L.ptr(None if wa is None else np.ascontiguousarray(wa)), cg, grid, variant, L.ptr(X), L.ptr(psum)))
     assert rel(X, Xw) < 1e-11
     if not cg:  # (with cg_compat the engine recomputes the sums after the scaling)
         assert rel(psum, np.sum(np.abs(Xw[:, :, :n]) ** 2, axis=1)) < 1e-11

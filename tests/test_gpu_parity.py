@@ -283,3 +283,62 @@ def test_headline_shape_batch_substreams_matches_oracle():
     for c in range(8):
         for o, w, k in zip(got[c][:6], want[c % 2], KEYS):
             assert rel(o, w) < TOL, (c, k)
+
+
+def test_long_chain_through_the_output_ring(monkeypatch, tmp_path):
+    """Niter >> ring depth (3 device slots) and a staging area of two iterations: every iteration's signal_cr / fg_amps /
+    chisq must still arrive (bounded device output ring), in RAM and through memory-mapped .npy files."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(77)
+    nt, nf, nm, niter = 20, 48, 4, 11
+    F = np.linalg.qr(crandn(rng, nf, nm))[0]
+    vis = crandn(rng, nt, nf) + (10 * crandn(rng, nt, nm)) @ F.T
+    flags = np.ones(nf, dtype=bool)
+    flags[[7, 30]] = False
+    prior = np.zeros((2, nf))
+    Ninv = np.eye(nf) * 1.5
+    want = ho.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, Ninv, prior, Niter=niter, seed=1, solver="direct")
+    per_iter = nt * nf * 24 + nt * nm * 16 + nf * 8 + 8
+    monkeypatch.setattr(pspec, "_STAGING_BYTES", 2 * per_iter)          # two iterations per chunk
+    got = pspec.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, Ninv, prior, Niter=niter, seed=1, verbose=False, solver="exact")
+    for o, w, k in zip(got[:6], want, KEYS):
+        assert rel(o, w) < TOL, k
+    # batch of three copies: in RAM ...
+    bls = [dict(vis=vis, flags=flags, S_initial=np.eye(nf), fgmodes=F, Ninv=Ninv, ps_prior=prior) for _ in range(3)]
+    monkeypatch.setattr(pspec, "_STAGING_BYTES", 2 * 3 * per_iter)
+    outs = pspec.gibbs_sample_batch(bls, Niter=niter, seed=1, rng="numpy", solver="exact", substreams=2)
+    for o in outs:
+        for a, w, k in zip(o[:6], want, KEYS):
+            assert rel(a, w) < TOL, k
+    # ... and through memory-mapped files when the host budget says the arrays do not fit
+    monkeypatch.setenv("HP_HOST_BUDGET_GB", "0")
+    for c, b in enumerate(bls):
+        b["out_dir"] = tmp_path / f"bl{c}"
+        b["out_dir"].mkdir()
+    outs = pspec.gibbs_sample_batch(bls, Niter=niter, seed=1, rng="numpy", solver="exact", write_Niter=4)
+    for c, o in enumerate(outs):
+        assert isinstance(o[0], np.memmap)
+        for a, w, k in zip(o[:6], want, KEYS):
+            assert rel(np.asarray(a), w) < TOL, k
+        d = bls[c]["out_dir"]
+        assert rel(np.load(d / "gcr-eor.npy"), want[0]) < TOL and rel(np.load(d / "chisq.npy"), want[4]) < TOL
+        assert rel(np.load(d / "dps-eor.npy"), want[2]) < TOL and rel(np.load(d / "ln-post.npy"), want[5]) < TOL
+    with pytest.raises(MemoryError):
+        pspec.gibbs_sample_batch([dict(b, out_dir=None) for b in bls], Niter=niter, seed=1, rng="numpy", solver="exact")
+
+
+def test_device_ring_read_window():
+    """hp_engine_read of a big output: the last `ring_iters` iterations are readable, older ones are refused."""
+    from hydra_pspec_b200 import pspec, _lib
+    rng = np.random.default_rng(5)
+    nt, nf, nm = 16, 32, 2
+    F = np.linalg.qr(crandn(rng, nf, nm))[0]
+    vis = crandn(rng, nt, nf)
+    eng = pspec.GibbsEngine(1, nt, nf, nm, max_iters=8, rng="philox", keep=("cr",), seed=3, ring_iters=3)
+    eng.load_chain(0, vis, np.ones(nf, bool), F, np.ones(nf), np.ones(nf))
+    eng.run(8)
+    last = eng.signal_cr(0, 5, 3)
+    assert last.shape == (3, nt, nf) and np.all(np.isfinite(last))
+    with pytest.raises(_lib.HydraLibError):
+        eng.signal_cr(0, 4, 1)
+    eng.close()
