@@ -453,18 +453,19 @@ struct TrinvSmem {
     double V[kLBlkDoubles];      // V_ii
 };
 
-// Fragment-major copies of W for k_solve3 (hp_solve3.cu).  One k-step (4 values of k) of one 16-row strip is 32 lanes x
-// [re, im] x 2 row groups = 128 doubles: lane 4 g + q holds A[8 wi + g][4 t + q] for wi = 0, 1.
+// Fragment-major copies of W for k_solve3 (hp_solve3.cu).  One k-step (4 values of k) of one 16-row strip is 2 row groups x
+// 32 lanes x [re, im] = 128 doubles: lane 4 g + q holds A[8 wi + g][4 t + q] at [wi][lane][re, im], so that each of the two
+// 16-byte loads of a warp covers 512 contiguous, fully used bytes.
 //   pass 1: A = W1 (rows R, k = column C);  strip R / 16 stores k-steps t < 4 (strip + 1) from offset 2 s (s + 1)
 //   pass 2: A = W^H (rows = columns C of W, k = row R);  strip C / 16 stores k-steps t >= 4 strip from offset 8 nblk s - 2 s (s - 1)
 __device__ __forceinline__ void store_frag1(double* Wf1, int R, int C, double re, double im) {
     const int s = R >> 4, t = C >> 2;
-    double* d = Wf1 + ((size_t)(2 * s * (s + 1) + t) * 128 + (4 * (R & 7) + (C & 3)) * 4 + 2 * ((R >> 3) & 1));
+    double* d = Wf1 + ((size_t)(2 * s * (s + 1) + t) * 128 + 64 * ((R >> 3) & 1) + (4 * (R & 7) + (C & 3)) * 2);
     *reinterpret_cast<double2*>(d) = make_double2(re, im);
 }
 __device__ __forceinline__ void store_frag2(double* Wf2, int nblk, int R, int C, double re, double im) {
     const int s = C >> 4, t = R >> 2;
-    double* d = Wf2 + ((size_t)(8 * nblk * s - 2 * s * (s - 1) + t - 4 * s) * 128 + (4 * (C & 7) + (R & 3)) * 4 + 2 * ((C >> 3) & 1));
+    double* d = Wf2 + ((size_t)(8 * nblk * s - 2 * s * (s - 1) + t - 4 * s) * 128 + 64 * ((C >> 3) & 1) + (4 * (C & 7) + (R & 3)) * 2);
     *reinterpret_cast<double2*>(d) = make_double2(re, im);
 }
 

@@ -117,7 +117,7 @@ void launch_cg_scale(double* X, const double* Rfix, const double* wa, const doub
                      int nsys, cudaStream_t st);
 
 // ---- k_solve3 (hp_solve3.cu): independent warps, W fragments streamed from L2 into registers ------------------------
-constexpr int kS3Warps = 8;          // warps of a k_solve3 CTA (all of them compute)
+constexpr int kS3Warps = 16;         // warps of a k_solve3 CTA (all of them compute): four per scheduler hide the L2 latency
 constexpr int kS3MaxStrips = 28;     // 16-row strips of the system (Np <= 448: two shared-memory tiles)
 constexpr int kS3MaxPerWarp = 8;
 struct Solve3Sched {                 // per pass and warp: the strips it owns, longest first (solve3_make_schedule)

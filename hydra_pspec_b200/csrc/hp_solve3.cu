@@ -5,15 +5,16 @@
 // walk one shared W-block ring and meet at a partial-sum exchange after every block row, so they issue DMMAs in lockstep
 // and do their per-block / per-row housekeeping in lockstep too, with the pipe idle.  Here:
 //
-//   * one persistent CTA (8 warps) per SM walks the (baseline, 16-time tile) list;
+//   * one persistent CTA (16 warps) per SM walks the (baseline, 16-time tile) list;
 //   * the tile of right-hand sides r (TMA bulk copy, tile-native layout of k_rhs_tile) and the tile of y = W1 r + xi live
 //     in two separate shared-memory buffers: nothing is updated in place, so block rows carry no ordering constraint;
 //   * a warp owns whole 16-row strips of the output (16 x 16 complex register tile, 3M DMMA products, full K range): no K
 //     split, no partial-sum exchange, no ring.  Strips are dealt to the warps by a longest-first schedule computed on the
 //     host so that every scheduler (warp pair) gets the same number of k-steps;
-//   * the A operand never touches shared memory: k_trinv writes W in fragment-major order (per strip and k-step 32 lanes x
-//     [re, im] x 2 row groups = 1 KiB contiguous), and every warp streams its own fragments from L2 into a 4-deep register
-//     queue that runs ahead across strip, pass and tile boundaries (the schedule is static);
+//   * the A operand never touches shared memory: k_trinv writes W in fragment-major order (per strip and k-step 2 row groups
+//     x 32 lanes x [re, im] = 1 KiB contiguous), and every warp streams its own fragments from L2 into registers one
+//     k-step ahead, across strip, pass and tile boundaries (the schedule is static); four warps per scheduler hide the L2
+//     latency (a deeper register queue does not: ptxas gives all prefetch sites one scoreboard);
 //   * B fragments (r or y) come from shared memory one k-step ahead; per k-step a warp issues 2 LDG.128 + 4 LDS.64 + 4 DADD
 //     for 12 DMMAs, all between its own DMMAs, so a single warp can keep the FP64 pipe of its scheduler busy;
 //   * pass 2 writes x from the accumulators to global and sum_t |x|^2 with it; the next tile's right-hand sides land during
@@ -41,11 +42,12 @@ constexpr int kRowDoubles3 = 2 * 32 * kTT;    // one block row of a tile: [plane
 constexpr int kFragDoubles = 128;             // one k-step of one strip in fragment-major order: 32 lanes x 4 doubles
 
 __device__ __forceinline__ double4 ldg_frag(const double* p) {
-    // streaming 32-byte fragment: every byte is used once per CTA, keep it out of L1
+    // streaming fragment ([row group][lane][re, im]: two 16-byte loads, each 512 contiguous bytes per warp); every byte is
+    // used once per CTA, keep it out of L1.  Volatile asm: the load keeps its place between the (volatile) DMMAs, after the
+    // first DMMA of a k-step has waited for the previous load -- one load group in flight per warp.
     double4 v;
-    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-    v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "l"(p + 64));
     return v;
 }
 
@@ -58,12 +60,15 @@ __device__ __forceinline__ void load_b(BFrag& f, const double* __restrict__ tile
     f.br[1] = b[bo1]; f.bi[1] = b[bo1 + 32 * kTT];
 }
 
-// 3M:  P0 += Ar.Br,  P1 += Ai.Bi,  P2 += (Ar +- Ai).(Br + Bi);  a = (ar0, ai0, ar1, ai1)
+// 3M:  P0 += Ar.Br,  P1 += Ai.Bi,  P2 += (Ar +- Ai).(Br + Bi);  a = (ar0, ai0, ar1, ai1).  The k-step is issued in two
+// parts so that the caller can place the next fragment load right after the first DMMA.
+__device__ __forceinline__ void mma_first(double (&P)[3][2][2][2], const double4& a, const BFrag& f) {
+    dmma884(P[0][0][0][0], P[0][0][0][1], a.x, f.br[0]);
+}
 template <bool kP2>
-__device__ __forceinline__ void mma_kstep(double (&P)[3][2][2][2], const double4& a, const BFrag& f) {
+__device__ __forceinline__ void mma_rest(double (&P)[3][2][2][2], const double4& a, const BFrag& f) {
     const double as0 = kP2 ? a.x - a.y : a.x + a.y, as1 = kP2 ? a.z - a.w : a.z + a.w;
     const double bs0 = f.br[0] + f.bi[0], bs1 = f.br[1] + f.bi[1];
-    dmma884(P[0][0][0][0], P[0][0][0][1], a.x, f.br[0]);
     dmma884(P[0][0][1][0], P[0][0][1][1], a.x, f.br[1]);
     dmma884(P[0][1][0][0], P[0][1][0][1], a.z, f.br[0]);
     dmma884(P[0][1][1][0], P[0][1][1][1], a.z, f.br[1]);
@@ -86,8 +91,8 @@ size_t solve3_frag_doubles(int nblk) { return (size_t)4 * nblk * (2 * nblk + 1) 
 static size_t solve3_smem_bytes(int nblk) { return sizeof(double) * 2 * (size_t)nblk * kRowDoubles3 + 64; }
 bool solve3_ok(int nblk, size_t max_smem) { return nblk >= 1 && 2 * nblk <= kS3MaxStrips && solve3_smem_bytes(nblk) <= max_smem; }
 
-// Longest-first schedule of the 2 nblk strips of each pass over the warps, then warps are paired so that each scheduler
-// (physical warps k and k + 4) carries the same number of k-steps.
+// Longest-first schedule of the 2 nblk strips of each pass over the warps; the warps are then dealt to the four schedulers
+// so that each carries the same number of k-steps.
 void solve3_make_schedule(int nblk, Solve3Sched* sc) {
     const int ns = 2 * nblk;
     for (int pass = 0; pass < 2; ++pass) {
@@ -105,15 +110,15 @@ void solve3_make_schedule(int nblk, Solve3Sched* sc) {
         std::vector<int> byload(kW3);
         for (int w = 0; w < kW3; ++w) byload[w] = w;
         std::sort(byload.begin(), byload.end(), [&](int a, int b) { return load[a] > load[b]; });
-        // heaviest with lightest on one scheduler: physical warps (k, k + 4) for k < 4
-        for (int k = 0; k < kW3 / 2; ++k) {
-            const int phys[2] = {k, k + kW3 / 2};
-            const int logical[2] = {byload[k], byload[kW3 - 1 - k]};
-            for (int h = 0; h < 2; ++h) {
-                const auto& L = lists[logical[h]];
-                sc->n[pass][phys[h]] = (uint8_t)L.size();
-                for (size_t e = 0; e < L.size() && e < (size_t)kS3MaxPerWarp; ++e) sc->strip[pass][phys[h]][e] = (uint8_t)L[e];
-            }
+        // warps to schedulers (physical warp id mod 4) in snake order of decreasing load: every scheduler gets the same
+        // number of warps and (nearly) the same number of k-steps
+        int cnt[4] = {0, 0, 0, 0};
+        for (int r = 0; r < kW3; ++r) {
+            const int lap = r / 4, pos = r % 4, sched = (lap & 1) ? 3 - pos : pos;
+            const int phys = sched + 4 * cnt[sched]++;
+            const auto& L = lists[byload[r]];
+            sc->n[pass][phys] = (uint8_t)L.size();
+            for (size_t e = 0; e < L.size() && e < (size_t)kS3MaxPerWarp; ++e) sc->strip[pass][phys][e] = (uint8_t)L[e];
         }
     }
 }
@@ -163,11 +168,11 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
         const int sys = pf_w / a.ntiles;
         if (pf_e < n1) {
             const int s = a.sched.strip[0][warp][pf_e];
-            pf_p = a.Wf1 + (size_t)sys * wf + (size_t)(2 * s * (s + 1)) * kFragDoubles + lane * 4;
+            pf_p = a.Wf1 + (size_t)sys * wf + (size_t)(2 * s * (s + 1)) * kFragDoubles + lane * 2;
             pf_left = 4 * (s + 1);
         } else {
             const int s = a.sched.strip[1][warp][pf_e - n1];
-            pf_p = a.Wf2 + (size_t)sys * wf + (size_t)(8 * nblk * s - 2 * s * (s - 1)) * kFragDoubles + lane * 4;
+            pf_p = a.Wf2 + (size_t)sys * wf + (size_t)(8 * nblk * s - 2 * s * (s - 1)) * kFragDoubles + lane * 2;
             pf_left = 8 * nblk - 4 * s;
         }
     };
@@ -185,9 +190,10 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
         --pf_left;
         return v;
     };
-    double4 aq[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) aq[u] = pf_next();
+    // Exactly one fragment load is in flight per warp (issued before the DMMAs of the current k-step, consumed by the next):
+    // ptxas tracks all prefetch sites with one scoreboard, so a deeper register queue would be waited for as a whole
+    // (profiles/r2_solve2_v1_notes.md); the L2 latency is hidden by the four warps of a scheduler instead.
+    double4 acur = pf_next();
 
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
     if (kTimers) tlast = clock64();
@@ -213,14 +219,16 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
                     for (int wj = 0; wj < 2; ++wj) P[p][wi][wj][0] = P[p][wi][wj][1] = 0.0;
             BFrag bf[2];
             load_b(bf[0], tileR, 0, bo0, bo1);
-            for (int t = 0; t < nk; t += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // B fragments one k-step ahead (the k-step after the strip's last one reads a valid, unused row group)
-                    load_b(bf[(u + 1) & 1], tileR, (t + u + 1 < nk) ? t + u + 1 : 0, bo0, bo1);
-                    mma_kstep<false>(P, aq[u], bf[u & 1]);
-                    aq[u] = pf_next();
-                }
+            for (int t = 0; t < nk; t += 2) {
+                // A and B fragments one k-step ahead (the k-step after the strip's last one reads a valid, unused row group)
+                mma_first(P, acur, bf[0]);
+                const double4 anx = pf_next();
+                load_b(bf[1], tileR, t + 1, bo0, bo1);
+                mma_rest<false>(P, acur, bf[0]);
+                mma_first(P, anx, bf[1]);
+                acur = pf_next();
+                load_b(bf[0], tileR, (t + 2 < nk) ? t + 2 : 0, bo0, bo1);
+                mma_rest<false>(P, anx, bf[1]);
             }
             S3_T(0);
             if (e == 0 && it > 0) { mbar_wait(yfree, (it - 1) & 1); S3_T(5); }   // the previous tile's pass 2 is done with y
@@ -271,13 +279,15 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
                     for (int wj = 0; wj < 2; ++wj) P[p][wi][wj][0] = P[p][wi][wj][1] = 0.0;
             BFrag bf[2];
             load_b(bf[0], tileY, k0, bo0, bo1);
-            for (int t = 0; t < nk; t += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    load_b(bf[(u + 1) & 1], tileY, (t + u + 1 < nk) ? k0 + t + u + 1 : 0, bo0, bo1);
-                    mma_kstep<true>(P, aq[u], bf[u & 1]);
-                    aq[u] = pf_next();
-                }
+            for (int t = 0; t < nk; t += 2) {
+                mma_first(P, acur, bf[0]);
+                const double4 anx = pf_next();
+                load_b(bf[1], tileY, k0 + t + 1, bo0, bo1);
+                mma_rest<true>(P, acur, bf[0]);
+                mma_first(P, anx, bf[1]);
+                acur = pf_next();
+                load_b(bf[0], tileY, (t + 2 < nk) ? k0 + t + 2 : 0, bo0, bo1);
+                mma_rest<true>(P, anx, bf[1]);
             }
             S3_T(3);
             // x = (P0 + P1) + i (P2 - P0 + P1)   (conj(A) B)
