@@ -6,7 +6,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "libhydra_pspec_b200.so"
+LIB_PATH = Path(os.environ.get("HP_LIB_PATH", _HERE / "csrc" / "libhydra_pspec_b200.so"))   # (HP_LIB_PATH: experiments)
 
 HP_RNG_INJECTED, HP_RNG_PHILOX = 0, 1
 HP_KEEP_CR, HP_KEEP_FG, HP_KEEP_CHISQ = 1, 2, 4
