@@ -154,9 +154,30 @@ def load_reference():
         sys.path.insert(0, str(ref))
     try:
         import hydra_pspec
-        return hydra_pspec
     except Exception:  # noqa: BLE001
         return None
+    # gcr_fgmodes (pspec.py:285) maps its per-time solves over `multiprocess.Pool(nproc)`; with nproc = 1 that is a serial map
+    # in one child process.  On this image Pool.__exit__ sporadically blocks for minutes (profiles/r2_reference_pool_stall.txt:
+    # 635 s for 16 times, 2 s for 64), so the benchmark arm maps in-process instead; every solve is still the reference's
+    # gcr_fgmodes_1d.  This replaces a runtime object of the imported module, not its source.
+    hydra_pspec.pspec.Pool = _SerialPool
+    return hydra_pspec
+
+
+class _SerialPool:
+    """Stand-in for multiprocess.Pool(1): `with Pool(1) as pool: pool.map(f, xs)` evaluated in-process."""
+
+    def __init__(self, *a, **kw):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def map(self, f, xs):
+        return [f(x) for x in xs]
 
 
 def _cpu_worker(job):
@@ -173,6 +194,19 @@ def _cpu_worker(job):
     Ninv = dense_ninv(nf) if c["mode"] == "dense" else np.diag(ninv_diag)
     prior = np.zeros((2, nf))
     hp = load_reference() if c["mode"] != "pertime" else None   # the reference asserts 1-D flags (pspec.py:428)
+    kind = "reference" if hp is not None else "port"
+    if hp is not None and not np.all(flags):
+        # build_matrices (pspec.py:362) takes scipy's sqrtm of the flagged N^-1; with this image's scipy that is NaN for most
+        # masks with several flagged channels -- the reference's whole chain is then NaN and every CG runs its 1e5 iterations
+        # (~30 s per time).  The unmodified reference is therefore timed on the same baseline without flags: same shapes, same
+        # dense operations per iteration.
+        import scipy.linalg
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fl = flags.astype(float)
+            if not np.all(np.isfinite(scipy.linalg.sqrtm((fl * Ninv * fl).astype(complex)))):
+                flags = np.ones(nf, dtype=bool)
+                kind = "reference (unflagged: scipy sqrtm of its flagged N^-1 is NaN)"
     t0 = time.perf_counter()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -185,7 +219,7 @@ def _cpu_worker(job):
             fl = per_time_flags(seed, flags, nt_sample) if c["mode"] == "pertime" else flags
             for it in range(niter):
                 ho.gibbs_sample_with_fg(vis, fl, np.eye(nf), F, Ninv, prior, Niter=1, seed=seed + it, solver="cg")
-    return time.perf_counter() - t0, ("reference" if hp is not None else "port")
+    return time.perf_counter() - t0, kind
 
 
 def cpu_throughput(cfg_id, steps, warmup):
@@ -197,7 +231,14 @@ def cpu_throughput(cfg_id, steps, warmup):
         os.environ[k] = "1"
     c = CONFIGS[cfg_id]
     cores = os.cpu_count() or 1
-    nt_sample = c["nt"] if cfg_id in (1, 3) else min(c["nt"], 32 if cfg_id == 2 else 128)
+    # bounded sample: about two minutes of wall clock for the whole call (one headline iteration of the unmodified reference
+    # takes ~23 s per core: 1024 scipy CG solves plus the right-hand-side assembly of gcr_fgmodes_1d)
+    if cfg_id == 1:
+        nt_sample = c["nt"]
+    elif cfg_id == 3:
+        nt_sample = int(min(c["nt"], max(32, (c["nt"] * 120 // (23 * max(steps, 1))) // 16 * 16)))
+    else:
+        nt_sample = min(c["nt"], 32 if cfg_id == 2 else 128)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         if warmup:
@@ -205,12 +246,17 @@ def cpu_throughput(cfg_id, steps, warmup):
         t0 = time.perf_counter()
         res = pool.map(_cpu_worker, [(cfg_id, i, nt_sample, steps) for i in range(cores)])
         dt = time.perf_counter() - t0
-    kind = res[0][1]
+    kind_full = res[0][1]
+    kind = kind_full.split(" ")[0]
     frac = nt_sample / c["nt"]   # fraction of a baseline-iteration that one sampled iteration is
     sample = (f"{cores} baselines x {steps} Gibbs iteration(s), one single-threaded process per core, "
               f"{'the unmodified reference (baseline/_ref)' if kind == 'reference' else 'the oracle port'}"
               + (f", {nt_sample} of {c['nt']} times per baseline (scaled by {frac:.4f})" if frac < 1 else "")
               + f"; every iteration restarts from S_initial = I; {dt:.1f} s")
+    if kind == "reference":
+        sample += "; multiprocess.Pool(1) of gcr_fgmodes mapped in-process (its teardown stalls sporadically on this image)"
+        if kind_full != kind:
+            sample += "; " + kind_full[len(kind) + 1:].strip("()")
     return cores * steps * frac / dt, cores, dt, kind, sample
 
 
@@ -395,14 +441,18 @@ def run_b200(args):
 
     Ninv_dense = dense_ninv(nf) if c["mode"] == "dense" else None
 
-    def load(eng, chain, seed, vis=None):
+    def host_inputs(seed):
+        """(vis, flags, fgmodes, ninv_diag, lam0sq) of one synthetic baseline in the form load_chain takes for this config"""
         v, flags, F, nd, l0 = make_baseline(seed, nt, nf, nm, flagged=c["flags"])
         if c["mode"] == "pertime":
-            eng.load_chain(chain, v if vis is None else vis, per_time_flags(seed, flags, nt), F, nd, l0)
+            flags = per_time_flags(seed, flags, nt)
         elif c["mode"] == "dense":
-            eng.load_chain(chain, v if vis is None else vis, flags, F, np.real(np.diagonal(Ninv_dense)).copy(), l0, ninv_dense=Ninv_dense)
-        else:
-            eng.load_chain(chain, v if vis is None else vis, flags, F, nd, l0)
+            nd = np.real(np.diagonal(Ninv_dense)).copy()
+        return v, flags, F, nd, l0
+
+    def load(eng, chain, inp, vis=None):
+        v, flags, F, nd, l0 = inp
+        eng.load_chain(chain, v if vis is None else vis, flags, F, nd, l0, ninv_dense=Ninv_dense)
 
     # ---- resident chains (baselines are independent: rank r holds global baselines first .. first + B - 1).  The big
     # per-iteration outputs (signal_cr, fg_amps, chisq) are written to a 2-slot device ring in every step.
@@ -413,7 +463,7 @@ def run_b200(args):
     eng.set_chain_ids(np.arange(first, first + B, dtype=np.int32))   # one key for the job, chain id = global baseline index
     t_load = time.perf_counter()
     for ch in range(B):
-        load(eng, ch, first + ch)
+        load(eng, ch, host_inputs(first + ch))
     t_load = time.perf_counter() - t_load
 
     eng.run(W)
@@ -541,12 +591,13 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         Ke = args.e2e_iters
-        pin = []
-        for ch in range(B):
-            v = make_baseline(10_000 + first + ch, nt, nf, nm, flagged=c["flags"])[0]
-            pv = _lib.pinned_empty(v.shape, np.complex128)
-            pv[...] = v
+        pin, hin = [], []
+        for ch in range(B):   # host inputs of the call, prepared once: the visibilities in page-locked memory
+            inp = host_inputs(10_000 + first + ch)
+            pv = _lib.pinned_empty(inp[0].shape, np.complex128)
+            pv[...] = inp[0]
             pin.append(pv)
+            hin.append(inp)
         stage = {}
         chunk = 2   # iterations of page-locked staging (bounded: the host side of a long chain re-uses it)
 
@@ -557,7 +608,7 @@ def run_b200(args):
             if keep not in stage:
                 stage[keep] = e.host_buffers(chunk)   # page-locked destination arrays, allocated once by the caller
             for ch in range(B):
-                load(e, ch, 10_000 + first + ch, vis=pin[ch])
+                load(e, ch, hin[ch], vis=pin[ch])
             done = 0
             while done < Ke:
                 n_ = min(chunk, Ke - done)

@@ -275,6 +275,8 @@ struct hp_engine {
     void* arena = nullptr;   // one device allocation holds every buffer below
     size_t arena_bytes = 0;
     hp::FftPlan plan{};
+    hp::FftPlan plan2f{}, plan2r{};   // k_post_fft2: forward plan and the same radices in reverse order
+    bool fft2_ok = false;
     bool fft_ok = false;
     int ntilesE = 0, ktp = 8;
     double *tw = nullptr, *Empart = nullptr, *Eupart = nullptr;
@@ -464,6 +466,12 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     e->ktp = hp::postfft_ktp(e->n, e->m, (size_t)max_smem);
     e->fft_ok = hp::make_fft_plan(e->n, &e->plan) && e->ktp > 0 &&
                 !cfg->force_dense_transforms;
+    {
+        const char* v1 = getenv("HP_POST_FFT_V1");   // experiments: keep the round-1 kernel
+        e->fft2_ok = e->fft_ok && !(v1 && v1[0] == '1') && hp::make_fft2_plan(e->n, &e->plan2f, &e->plan2r) &&
+                     hp::postfft2_smem_bytes(e->n, e->m) <= (size_t)max_smem / 2;
+        if (e->fft2_ok) e->ktp = 8;   // k_post_fft2 handles eight times per CTA
+    }
     e->ntilesE = hp::postfft_tiles(e->T, e->ktp > 0 ? e->ktp : 8);
     const bool dense = !e->fft_ok;                       // dense-transform scratch
     const bool need_ssc = dense || cfg->general_basis0;  // lam * ytilde as input of the dense back-transform
@@ -1076,7 +1084,8 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         pa.Empart = e->any_flagged ? OFFS(e->Empart, (size_t)e->ntilesE * n) : nullptr;
         pa.Eupart = general ? OFFS(e->Eupart, (size_t)e->ntilesE * n) : nullptr;
         pa.m = e->m; pa.Np = e->Np; pa.T = e->T; pa.Tp = e->Tp; pa.nsys = sb.nc; pa.do_inverse = fused_inverse ? 1 : 0; pa.ktp = e->ktp;
-        hp::launch_post_fft(pa, sb.st);
+        if (!(e->fft2_ok && pa.do_inverse && !pa.Eupart && hp::launch_post_fft2(pa, e->plan2f, e->plan2r, sb.st)))
+            hp::launch_post_fft(pa, sb.st);
         e->prof_end(CLS_POST, 1, sb.st);
         if (e->cfg.dense_noise) enqueue_dense_lnp1(e, sb);
         return;

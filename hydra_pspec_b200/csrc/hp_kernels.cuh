@@ -235,6 +235,10 @@ struct PostFftArgs {
     int ktp;               // times per CTA (postfft_ktp)
 };
 void launch_post_fft(const PostFftArgs& a, cudaStream_t st);
+// k_post_fft2 (hp_fft2.cu): register-resident FFTs, one shared-memory buffer; needs do_inverse = 1 and Eupart = NULL
+bool make_fft2_plan(int n, FftPlan* fwd, FftPlan* rev);   // false: Nfreqs not covered (k_post_fft takes it)
+size_t postfft2_smem_bytes(int n, int m);
+bool launch_post_fft2(const PostFftArgs& a, const FftPlan& fwd, const FftPlan& rev, cudaStream_t st);
 
 
 // small elementwise helpers used by the set-up

@@ -342,3 +342,26 @@ def test_device_ring_read_window():
     with pytest.raises(_lib.HydraLibError):
         eng.signal_cr(0, 4, 1)
     eng.close()
+
+
+@pytest.mark.parametrize("nt,nf,nm,seed", [(20, 128, 8, 1), (12, 256, 16, 2), (9, 384, 32, 3), (17, 128, 0, 4), (8, 256, 6, 5)])
+def test_register_fft_shapes_match_oracle(nt, nf, nm, seed):
+    """Nfreqs = 128 / 256 / 384 take k_post_fft2 (register-resident FFTs, plans 4.4.4.2 / 8.8.4 / 6.4.4.4): partial time tiles,
+    Nmodes = 0 and Nmodes not a multiple of 4, flagged channels (second transform), three iterations."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(500 + seed)
+    F = np.linalg.qr(crandn(rng, nf, max(nm, 1)))[0][:, :nm]
+    fop = ho.fourier_operator(nf)
+    S0 = fop.conj().T @ np.diag((0.5 + rng.random(nf)) / nf ** 2) @ fop
+    sig = 0.3 + rng.random(nf)
+    vis = crandn(rng, nt, nf) * sig + crandn(rng, nt, nf) @ np.linalg.cholesky(S0 + 1e-13 * np.eye(nf)).T
+    if nm:
+        vis = vis + (5 * crandn(rng, nt, nm)) @ F.T
+    flags = np.ones(nf, dtype=bool)
+    flags[rng.choice(nf, 5, replace=False)] = False
+    prior = np.zeros((2, nf))
+    Ninv = np.diag(1.0 / sig ** 2)
+    want = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=seed, solver="direct")
+    got = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=seed, verbose=False, solver="exact")
+    for o, w, k in zip(got[:6], want, KEYS):
+        assert rel(o, w) < TOL, k
