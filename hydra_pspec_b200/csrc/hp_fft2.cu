@@ -14,8 +14,9 @@
 //   * computes F f on the tensor pipe (3M) and finishes the residual in the accumulator layout: the foreground model never
 //     goes to shared memory (one buffer instead of two: three CTAs per SM instead of two).
 //
-// Taken when Nfreqs is a multiple of 32 with E in {4, 8, 12} and a plan of at most four passes exists (128, 256, 384, ...);
-// everything else (and the general-basis first iteration) stays on k_post_fft.
+// Taken for Nfreqs = 128, 256, 384 (plans 4.4.4.2, 8.8.4, 6.4.4.4 as template parameters: all index arithmetic but the lane is
+// compile-time -- the run-time version spent half of its 6.6 k instructions per transform pair on it); everything else (and
+// the general-basis first iteration) stays on k_post_fft.
 #include "hp_kernels.cuh"
 #include "hp_math.h"
 #include "hp_mma.cuh"
@@ -88,30 +89,32 @@ __device__ __forceinline__ void butterfly<8>(double2* a) {
 
 __device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
 
-// One Stockham pass of one warp's FFT.  v[u * R + r] = input r of butterfly j = lane + 32 u (index j + r * nb, nb = n / R).
+// One Stockham pass of one warp's FFT with everything but the lane known at compile time.
+//   v[u * R + r] = input r of butterfly j = lane + 32 u (index j + r * nb, nb = n / R)
+//   NS    : product of the radices of the earlier passes;  k = j mod NS, jq = j / NS
 //   kLoad : fetch the inputs from `row` (shared memory, index i at phys(i)); else they are in v already
-//   kStore: write the outputs to `row` (index jq Ns R + k + r Ns; k = j mod Ns, jq = j / Ns) between two __syncwarp;
-//           else they stay in v as output r of butterfly j = index j + r * Ns (only the last pass: Ns R = n)
-template <int E, int R, bool kLoad, bool kStore>
-__device__ __forceinline__ void fft_pass(double2 (&v)[E], double2* row, int n, int Ns, uint32_t magic, const double2* __restrict__ tw,
-                                         int lane) {
-    constexpr int NB = E / R;   // butterflies per lane
-    const int nb = n / R;
+//   kStore: write the outputs to `row` (index jq NS R + k + r NS) between two __syncwarp; else they stay in v as output r of
+//           butterfly j = index j + r * NS (only the last pass: NS R = n)
+//   twt   : this pass's twiddle table, twt[k * (R - 1) + r - 1] = exp(-2 pi i r k / (NS R)): consecutive lanes read consecutive
+//           entries (a look-up in the plain table exp(-2 pi i j / n) has a power-of-two stride and conflicts 8 - 16 ways)
+template <int E, int R, int NS, bool kLoad, bool kStore>
+__device__ __forceinline__ void fft_pass(double2 (&v)[E], double2* row, const double2* __restrict__ twt, int lane) {
+    constexpr int n = 32 * E, NB = E / R, nb = n / R;
+    static_assert(E % R == 0 && nb % 8 == 0, "a lane owns whole butterflies; rows of a butterfly are 8-aligned");
     if (kLoad) {
+        // phys(lane + 32 u + r nb) = phys(lane) + 36 u + r (9 nb / 8): one base, compile-time offsets
+        const double2* src = row + phys(lane);
 #pragma unroll
         for (int u = 0; u < NB; ++u)
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[u * R + r] = row[phys(lane + 32 * u + r * nb)];
+            for (int r = 0; r < R; ++r) v[u * R + r] = src[36 * u + r * (nb / 8 * 9)];
     }
-    const int tstep = nb / Ns;   // n / (Ns R)
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
-        const int j = lane + 32 * u;
-        const int jq = Ns > 1 ? (int)__umulhi((uint32_t)j, magic) : j;   // j / Ns
-        const int k = j - jq * Ns;
-        if (Ns > 1 && k) {
+        if (NS > 1) {
+            const int k = (lane + 32 * u) % NS;
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[u * R + r] = cmul(v[u * R + r], tw[r * k * tstep]);
+            for (int r = 1; r < R; ++r) v[u * R + r] = cmul(v[u * R + r], twt[k * (R - 1) + r - 1]);
         }
         butterfly<R>(&v[u * R]);
     }
@@ -119,46 +122,60 @@ __device__ __forceinline__ void fft_pass(double2 (&v)[E], double2* row, int n, i
         __syncwarp();   // every lane has its inputs in registers: the row may be overwritten
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
-            const int j = lane + 32 * u;
-            const int jq = Ns > 1 ? (int)__umulhi((uint32_t)j, magic) : j;
-            const int k = j - jq * Ns;
+            const int j = lane + 32 * u, jq = j / NS, k = j - jq * NS;
+            const int base = jq * (NS * R) + k;
 #pragma unroll
-            for (int r = 0; r < R; ++r) row[phys(jq * Ns * R + k + r * Ns)] = v[u * R + r];
+            for (int r = 0; r < R; ++r) row[phys(base + r * NS)] = v[u * R + r];
         }
         __syncwarp();
     }
 }
 
-// pass p of a plan, radix chosen at run time among the divisors of E
-template <int E, bool kLoad, bool kStore>
-__device__ __forceinline__ void fft_pass_any(int R, double2 (&v)[E], double2* row, int n, int Ns, uint32_t magic,
-                                             const double2* __restrict__ tw, int lane) {
-    if (R == 4) { if constexpr (E % 4 == 0) fft_pass<E, 4, kLoad, kStore>(v, row, n, Ns, magic, tw, lane); }
-    else if (R == 8) { if constexpr (E % 8 == 0) fft_pass<E, 8, kLoad, kStore>(v, row, n, Ns, magic, tw, lane); }
-    else if (R == 6) { if constexpr (E % 6 == 0) fft_pass<E, 6, kLoad, kStore>(v, row, n, Ns, magic, tw, lane); }
-    else if (R == 2) { if constexpr (E % 2 == 0) fft_pass<E, 2, kLoad, kStore>(v, row, n, Ns, magic, tw, lane); }
-    else if (R == 3) { if constexpr (E % 3 == 0) fft_pass<E, 3, kLoad, kStore>(v, row, n, Ns, magic, tw, lane); }
+// A whole transform: radices P0 P1 P2 (P3) (P3 = 1: three passes); the first pass takes its inputs from v (kFromRegs) or from
+// the row; the last pass leaves element u * R + r = index (lane + 32 u) + r * (n / R) in v.  Twiddle tables of pass p >= 1 at
+// tw + (NS_p - P0).
+template <int E, int P0, int P1, int P2, int P3, bool kFromRegs>
+__device__ __forceinline__ void fft_run(double2 (&v)[E], double2* row, const double2* __restrict__ tw, int lane) {
+    fft_pass<E, P0, 1, !kFromRegs, true>(v, row, tw, lane);
+    fft_pass<E, P1, P0, true, true>(v, row, tw, lane);
+    if constexpr (P3 > 1) {
+        fft_pass<E, P2, P0 * P1, true, true>(v, row, tw + (P0 * P1 - P0), lane);
+        fft_pass<E, P3, P0 * P1 * P2, true, false>(v, row, tw + (P0 * P1 * P2 - P0), lane);
+    } else {
+        fft_pass<E, P2, P0 * P1, true, false>(v, row, tw + (P0 * P1 - P0), lane);
+    }
+}
+
+// per-pass twiddle tables of a plan, packed one after the other (pass p starts at NS_p - P0; n - P0 entries in all)
+template <int E, int P0, int P1, int P2, int P3>
+__device__ __forceinline__ void build_twiddle_tables(double2* dst, const double2* __restrict__ twg, int tid, int nthreads) {
+    constexpr int n = 32 * E;
+    constexpr int rad[4] = {P0, P1, P2, P3};
+    int Ns = P0;
+#pragma unroll
+    for (int ps = 1; ps < 4; ++ps) {
+        const int R = rad[ps];
+        if (R <= 1) break;
+        const int tstep = n / (Ns * R), cnt = Ns * (R - 1);
+        double2* t = dst + (Ns - P0);
+        for (int e = tid; e < cnt; e += nthreads) {
+            const int k = e / (R - 1), r = e - k * (R - 1) + 1;
+            t[e] = twg[r * k * tstep];
+        }
+        Ns *= R;
+    }
 }
 
 }  // namespace
 
-// radices (each dividing E = n / 32, at most four passes) for the register-resident FFT; false: use k_post_fft
+// Nfreqs covered by k_post_fft2 (compile-time plans): 128 = 4.4.4.2, 256 = 8.8.4, 384 = 6.4.4.4.  The FftPlan outputs carry
+// the forward / reverse radices for reference; the kernel has them as template parameters.
 bool make_fft2_plan(int n, FftPlan* fwd, FftPlan* rev) {
-    if (n % 32 != 0) return false;
-    const int E = n / 32;
-    if (E != 4 && E != 8 && E != 12) return false;
-    int rad[8], nf = 0, rem = n;
-    const int cand[5] = {8, 6, 4, 3, 2};
-    while (rem > 1 && nf < 8) {
-        int pick = 0;
-        for (int c : cand)
-            if (E % c == 0 && rem % c == 0) { pick = c; break; }
-        if (!pick) return false;
-        rad[nf++] = pick;
-        rem /= pick;
-    }
-    if (rem != 1 || nf < 2 || nf > 4) return false;
-    // forward plan: smallest radix last would leave few outputs per butterfly in registers; order as found (largest first)
+    int rad[4], nf;
+    if (n == 384) { rad[0] = 6; rad[1] = 4; rad[2] = 4; rad[3] = 4; nf = 4; }
+    else if (n == 256) { rad[0] = 8; rad[1] = 8; rad[2] = 4; rad[3] = 1; nf = 3; }
+    else if (n == 128) { rad[0] = 4; rad[1] = 4; rad[2] = 4; rad[3] = 2; nf = 4; }
+    else return false;
     for (int dir = 0; dir < 2; ++dir) {
         FftPlan* p = dir ? rev : fwd;
         p->n = n; p->nf = nf;
@@ -175,18 +192,20 @@ bool make_fft2_plan(int n, FftPlan* fwd, FftPlan* rev) {
 size_t postfft2_smem_bytes(int n, int m) {
     const int mk = ((m + 3) / 4) * 4;
     const int ld = n + n / 8 + 1;   // padded row: index i at i + i / 8, row stride == 1 (mod 8) sixteen-byte units
-    return sizeof(double2) * ((size_t)kTP2 * ld + n + (size_t)kTP2 * (mk + 1)) + 80 * sizeof(double);
+    return sizeof(double2) * ((size_t)kTP2 * ld + 2 * (size_t)n + (size_t)kTP2 * (((mk + 7) / 8) * 8 + 4)) + 80 * sizeof(double);
 }
 
-template <int E>
-__global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftArgs a, FftPlan prev) {
+// E = Nfreqs / 32; forward radices P0 P1 P2 (P3); the second transform runs them in reverse order
+template <int E, int P0, int P1, int P2, int P3>
+__global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftArgs a) {
     constexpr int kThreads = 32 * kTP2;
+    constexpr int n = 32 * E, ld = n + n / 8 + 1;
+    constexpr int RL = P3 > 1 ? P3 : P2;      // last forward radix = first reverse radix
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FftPlan& pfwd = a.plan;
-    const int n = pfwd.n, m = a.m, mk = ((m + 3) / 4) * 4, ldf = mk + 1, ld = n + n / 8 + 1;
+    const int m = a.m, mk = ((m + 3) / 4) * 4, ldf = ((mk + 7) / 8) * 8 + 4;   // ldf == 4 (mod 8): conflict-free fragment loads
     double2* A = reinterpret_cast<double2*>(smem_raw);          // [8][ld]: one FFT row per warp; later s in frequency space
-    double2* tw = A + (size_t)kTP2 * ld;                         // [n]
-    double2* fs = tw + n;                                        // [8][ldf] foreground amplitudes of the tile's times
+    double2* tw = A + (size_t)kTP2 * ld;                         // [2][n] per-pass twiddle tables: forward plan, reverse plan
+    double2* fs = tw + 2 * (size_t)n;                            // [8][ldf] foreground amplitudes of the tile's times
     double* red = reinterpret_cast<double*>(fs + (size_t)kTP2 * ldf);   // [8 warps][8 times]
     const int sys = blockIdx.y, tile = blockIdx.x, t0 = tile * kTP2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,12 +228,12 @@ __global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftAr
     const bool live = t0 + t < a.T;
     double2 v[E];
     {
-        const int R0 = pfwd.radix[0], nb0 = n / R0;
+        constexpr int nb0 = n / P0;
         const double* xr = X + 2 * (size_t)t * a.Np;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            // element e = u * R0 + r  <->  index (lane + 32 u) + r * nb0
-            const int u = e / R0, r = e - u * R0;   // (R0 is warp-uniform; E / R0 butterflies per lane)
+            // element e = u * P0 + r  <->  index (lane + 32 u) + r * nb0
+            const int u = e / P0, r = e - u * P0;
             const int k = lane + 32 * u + r * nb0;
             double2 y = make_double2(0.0, 0.0);
             double l = 0.0;
@@ -223,7 +242,11 @@ __global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftAr
             v[e] = make_double2(sg * y.x, -sg * y.y);
         }
     }
-    for (int j = tid; j < n; j += kThreads) tw[j] = twg[j];
+    build_twiddle_tables<E, P0, P1, P2, P3>(tw, twg, tid, kThreads);
+    if (a.Empart) {
+        if constexpr (P3 > 1) build_twiddle_tables<E, P3, P2, P1, P0>(tw + n, twg, tid, kThreads);
+        else build_twiddle_tables<E, P2, P1, P0, 1>(tw + n, twg, tid, kThreads);
+    }
     for (int e = tid; e < kTP2 * ldf; e += kThreads) {
         const int tt = e / ldf, j = e - tt * ldf;
         double2 f = make_double2(0.0, 0.0);
@@ -236,18 +259,10 @@ __global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftAr
     double2* row = A + (size_t)t * ld;
     // ---- FFT 1 (forward plan): first pass from registers, middle passes through the row, last pass stays in registers
     {
-        const int nf = pfwd.nf;
-        int Ns = 1;
-        fft_pass_any<E, false, true>(pfwd.radix[0], v, row, n, Ns, pfwd.magic[0], tw, lane);
-        Ns *= pfwd.radix[0];
-        for (int p = 1; p < nf - 1; ++p) {
-            fft_pass_any<E, true, true>(pfwd.radix[p], v, row, n, Ns, pfwd.magic[p], tw, lane);
-            Ns *= pfwd.radix[p];
-        }
-        fft_pass_any<E, true, false>(pfwd.radix[nf - 1], v, row, n, Ns, pfwd.magic[nf - 1], tw, lane);
+        fft_run<E, P0, P1, P2, P3, true>(v, row, tw, lane);
         // outputs: element u * R + r = index x = lane + 32 u + r * Ns (Ns = n / R).  s = conj(out * (-1)^x * c0) / sqrt(n)
-        const int R = pfwd.radix[nf - 1];
-        const double2 c0 = tw[(int)(((long long)(n / 2) * (n / 2)) % n)];   // exp(-2 pi i h^2 / n), h = n / 2
+        constexpr int R = RL, Ns = n / RL;
+        const double2 c0 = twg[(int)(((long long)(n / 2) * (n / 2)) % n)];   // exp(-2 pi i h^2 / n), h = n / 2
         __syncwarp();   // the last pass has read the row
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -270,38 +285,49 @@ __global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftAr
         const bool tlive = t0 + g < a.T;
         const double* wrow = w + (size_t)g * a.w_ts;
         double lnp = 0.0;
-        double2 bnx[4];
-        auto load_b = [&](int ct, int kc, double2 (&b)[4]) {
+        // One group of global loads in flight per warp: the B fragments of all k-steps (mk <= 32: eight; more modes: the
+        // first eight, the rest on demand) and the data of the NEXT tile are requested before this tile's products.
+        constexpr int kBF = 8;
+        double2 bnx[kBF], dnx[2];
+        auto load_tile = [&](int ct, double2 (&b)[kBF], double2 (&d)[2]) {
             const int x = 8 * ct + g;
 #pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                const int k = kc + 4 * s4 + q;
-                b[s4] = (k < m && ct < nct) ? *reinterpret_cast<const double2*>(Ft + 2 * ((size_t)k * n + x)) : make_double2(0.0, 0.0);
+            for (int s8 = 0; s8 < kBF; ++s8) {
+                const int k = 4 * s8 + q;
+                b[s8] = (k < m && ct < nct) ? *reinterpret_cast<const double2*>(Ft + 2 * ((size_t)k * n + x)) : make_double2(0.0, 0.0);
+            }
+            d[0] = d[1] = make_double2(0.0, 0.0);
+            if (tlive && ct < nct) {
+                d[0] = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)g * n + 8 * ct + 2 * q));
+                d[1] = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)g * n + 8 * ct + 2 * q + 1));
             }
         };
-        load_b(warp, 0, bnx);
+        load_tile(warp, bnx, dnx);
         for (int ct = warp; ct < nct; ct += kTP2) {
             double p1[2] = {0.0, 0.0}, p2[2] = {0.0, 0.0}, p3[2] = {0.0, 0.0};
-            // this tile's data and mask (32 contiguous bytes per lane), in flight during the products
             const int x0 = 8 * ct + 2 * q;
-            double2 d0 = make_double2(0.0, 0.0), d1 = d0;
-            if (tlive) {
-                d0 = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)g * n + x0));
-                d1 = *reinterpret_cast<const double2*>(wd + 2 * ((size_t)g * n + x0 + 1));
-            }
-            for (int kc = 0; kc < mk; kc += 16) {   // chunks of four k-steps: A fragments from shared memory, B one chunk ahead
-                double2 bc[4];
+            double2 bc[kBF];
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) bc[s4] = bnx[s4];
-                if (kc + 16 < mk) load_b(ct, kc + 16, bnx); else load_b(ct + kTP2, 0, bnx);
+            for (int s8 = 0; s8 < kBF; ++s8) bc[s8] = bnx[s8];
+            const double2 d0 = dnx[0], d1 = dnx[1];
+            load_tile(ct + kTP2, bnx, dnx);
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    const int k = kc + 4 * s4 + q;
-                    const double2 af = (k < mk) ? fs[(size_t)g * ldf + k] : make_double2(0.0, 0.0);
-                    dmma884(p1[0], p1[1], af.x, bc[s4].x);
-                    dmma884(p2[0], p2[1], af.y, bc[s4].y);
-                    dmma884(p3[0], p3[1], af.x + af.y, bc[s4].x + bc[s4].y);
+            for (int s8 = 0; s8 < kBF; ++s8) {
+                const int k = 4 * s8 + q;
+                if (4 * s8 < mk) {
+                    const double2 af = fs[(size_t)g * ldf + k];
+                    dmma884(p1[0], p1[1], af.x, bc[s8].x);
+                    dmma884(p2[0], p2[1], af.y, bc[s8].y);
+                    dmma884(p3[0], p3[1], af.x + af.y, bc[s8].x + bc[s8].y);
                 }
+            }
+            for (int kc = 4 * kBF; kc < mk; kc += 4) {   // more than 32 foreground modes: remaining k-steps straight from L2
+                const int k = kc + q;
+                const double2 af = fs[(size_t)g * ldf + k];
+                const double2 b = k < m ? *reinterpret_cast<const double2*>(Ft + 2 * ((size_t)k * n + 8 * ct + g)) : make_double2(0.0, 0.0);
+                dmma884(p1[0], p1[1], af.x, b.x);
+                dmma884(p2[0], p2[1], af.y, b.y);
+                dmma884(p3[0], p3[1], af.x + af.y, b.x + b.y);
             }
             const double2 s0 = A[(size_t)g * ld + phys(x0)], s1 = A[(size_t)g * ld + phys(x0 + 1)];
             const double wx0 = (a.w_ts == 0 || tlive) ? wrow[x0] : 0.0, wx1 = (a.w_ts == 0 || tlive) ? wrow[x0 + 1] : 0.0;
@@ -337,14 +363,9 @@ __global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftAr
     }
     // ---- |U (w s)|^2 summed over the tile's times (second term of ln_post, pspec.py:479-483): reverse plan
     if (a.Empart) {
-        const int nf = prev.nf;
-        int Ns = 1;
-        for (int p = 0; p < nf - 1; ++p) {
-            fft_pass_any<E, true, true>(prev.radix[p], v, row, n, Ns, prev.magic[p], tw, lane);
-            Ns *= prev.radix[p];
-        }
-        fft_pass_any<E, true, false>(prev.radix[nf - 1], v, row, n, Ns, prev.magic[nf - 1], tw, lane);
-        const int R = prev.radix[nf - 1];
+        if constexpr (P3 > 1) fft_run<E, P3, P2, P1, P0, false>(v, row, tw + n, lane);
+        else fft_run<E, P2, P1, P0, 1, false>(v, row, tw + n, lane);
+        constexpr int R = P0, Ns = n / P0;
         __syncwarp();   // the last pass has read the row: park |.|^2 in it (doubles, index k)
         double* erow = reinterpret_cast<double*>(row);
 #pragma unroll
@@ -365,23 +386,22 @@ __global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftAr
 
 // true: the launch was taken by k_post_fft2
 bool launch_post_fft2(const PostFftArgs& a, const FftPlan& fwd, const FftPlan& rev, cudaStream_t st) {
-    const int n = fwd.n, E = n / 32;
+    (void)rev;
+    const int n = fwd.n;
     const size_t smem = postfft2_smem_bytes(n, a.m);
     static size_t attr_dev[kMaxDev][3] = {{0}};
-    const int slot = E == 4 ? 0 : (E == 8 ? 1 : 2);
+    const int slot = n == 128 ? 0 : (n == 256 ? 1 : 2);
     size_t& attr = attr_dev[current_device_slot()][slot];
-    PostFftArgs b = a;
-    b.plan = fwd;
     const dim3 grid((a.T + kTP2 - 1) / kTP2, a.nsys);
-    if (E == 4) {
-        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-        k_post_fft2<4><<<grid, 32 * kTP2, smem, st>>>(b, rev);
-    } else if (E == 8) {
-        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-        k_post_fft2<8><<<grid, 32 * kTP2, smem, st>>>(b, rev);
-    } else if (E == 12) {
-        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-        k_post_fft2<12><<<grid, 32 * kTP2, smem, st>>>(b, rev);
+    if (n == 128) {
+        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<4, 4, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+        k_post_fft2<4, 4, 4, 4, 2><<<grid, 32 * kTP2, smem, st>>>(a);
+    } else if (n == 256) {
+        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<8, 8, 8, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+        k_post_fft2<8, 8, 8, 4, 1><<<grid, 32 * kTP2, smem, st>>>(a);
+    } else if (n == 384) {
+        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<12, 6, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+        k_post_fft2<12, 6, 4, 4, 4><<<grid, 32 * kTP2, smem, st>>>(a);
     } else {
         return false;
     }

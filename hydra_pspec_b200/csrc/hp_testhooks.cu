@@ -180,6 +180,21 @@ int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double*
     return e == cudaSuccess ? HP_OK : HP_ERR_CUDA;
 }
 
+// k_solve3's static work schedule (host logic; no device needed): n[2][kS3Warps], strips[2][kS3Warps][kS3MaxPerWarp]
+int hp_test_solve3_schedule(int nblk, unsigned char* n, unsigned char* strips, int* nwarps, int* max_per_warp) {
+    if (nblk < 1 || 2 * nblk > hp::kS3MaxStrips) return HP_ERR_SIZE;
+    hp::Solve3Sched sc{};
+    hp::solve3_make_schedule(nblk, &sc);
+    for (int p = 0; p < 2; ++p)
+        for (int w = 0; w < hp::kS3Warps; ++w) {
+            n[p * hp::kS3Warps + w] = sc.n[p][w];
+            for (int e = 0; e < hp::kS3MaxPerWarp; ++e) strips[(p * hp::kS3Warps + w) * hp::kS3MaxPerWarp + e] = sc.strip[p][w][e];
+        }
+    *nwarps = hp::kS3Warps;
+    *max_per_warp = hp::kS3MaxPerWarp;
+    return HP_OK;
+}
+
 // ---- measurement helpers -----------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {

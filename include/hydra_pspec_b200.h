@@ -187,6 +187,10 @@ int hp_test_chol_solve(int n, int m, int T, const double* G, const double* lam, 
 int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double* lam, const double* Rfix, const double* wa,
                    int cg_compat, int grid_limit, int variant, double* X, double* psum);
 
+/* k_solve3's static strip schedule for a system of nblk 32-row blocks (host logic, no device needed):
+ * n[2][nwarps] strips per pass and warp, strips[2][nwarps][max_per_warp] their 16-row strip indices */
+int hp_test_solve3_schedule(int nblk, unsigned char* n, unsigned char* strips, int* nwarps, int* max_per_warp);
+
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* FP64 tensor-pipe (DMMA.8x8x4) peak of the device measured with an issue loop for ~`seconds`; TFLOP/s. */
 double hp_fp64_peak_tflops(int device, double seconds);

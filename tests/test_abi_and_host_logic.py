@@ -158,3 +158,29 @@ def test_header_compiles_as_c_and_links(tmp_path):
                     "-L", str(_lib.LIB_PATH.parent), "-lhydra_pspec_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == len(names) and "hydra_pspec_b200" in " ".join(out[1:])
+
+
+@pytest.mark.parametrize("nblk", [1, 2, 5, 13, 14])
+def test_solve3_schedule_covers_every_strip_once(nblk):
+    """k_solve3's static work schedule (hp_solve3.cu: longest-first over the warps): in both passes every 16-row strip of the
+    system is owned by exactly one warp, and at the headline size no warp carries more than 1.25 x the mean load."""
+    import ctypes as C
+    from hydra_pspec_b200 import _lib
+    L = _lib.lib()
+    n = np.zeros(2 * 64, dtype=np.uint8)
+    strips = np.zeros(2 * 64 * 16, dtype=np.uint8)
+    nw, mp = C.c_int(), C.c_int()
+    assert L.hp_test_solve3_schedule(nblk, _lib.ptr(n), _lib.ptr(strips), C.byref(nw), C.byref(mp)) == 0
+    nw, mp = nw.value, mp.value
+    n = n[:2 * nw].reshape(2, nw)
+    strips = strips[:2 * nw * mp].reshape(2, nw, mp)
+    for p in range(2):
+        owned = [int(strips[p, w, e]) for w in range(nw) for e in range(n[p, w])]
+        assert sorted(owned) == list(range(2 * nblk))
+        length = (lambda s: 4 * (s + 1)) if p == 0 else (lambda s: 8 * nblk - 4 * s)
+        loads = np.array([sum(length(int(strips[p, w, e])) for e in range(n[p, w])) for w in range(nw)], dtype=float)
+        # the warps of every scheduler (warp id mod 4) together carry about a quarter of the pass
+        sched = np.array([loads[s::4].sum() for s in range(4)])
+        if nblk == 13:
+            assert sched.max() <= 1.03 * sched.mean(), sched
+            assert loads.max() <= 1.25 * loads.mean(), loads
