@@ -247,7 +247,11 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
                         if (a.philox && row < a.N && t0 + col < a.T) {
                             u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(t0 + col); ctr.z = a.iter; ctr.w = chain;
                             double x0, x1;
+#ifdef HP_PHILOX_DOUBLE   // experiment (profiles/r2_summary.md): what full double-precision Box-Muller costs this kernel
+                            normal_pair(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), x0, x1);
+#else
                             normal_pair_fast(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), x0, x1);
+#endif
                             vr += x0 * 0.70710678118654752440; vi += x1 * 0.70710678118654752440;
                         }
                         const int c = col ^ ((rl & 3) << 2);
