@@ -606,13 +606,13 @@ def run_b200(args):
                                   stream=stream, substreams=substreams, **mode_kw)
             e.set_chain_ids(np.arange(first, first + B, dtype=np.int32))
             if keep not in stage:
-                stage[keep] = e.host_buffers(chunk)   # page-locked destination arrays, allocated once by the caller
+                stage[keep] = e.host_buffers(chunk, iter_major=True)   # page-locked destination arrays, allocated once by the caller
             for ch in range(B):
                 load(e, ch, hin[ch], vis=pin[ch])
             done = 0
             while done < Ke:
                 n_ = min(chunk, Ke - done)
-                e.run_to_host(n_, stage[keep], first_iter=done)   # compute overlapped with the device-to-host copies
+                e.run_to_host(n_, stage[keep], first_iter=done, iter_major=True)   # compute overlapped with the device-to-host copies
                 done += n_
             e.close()
 

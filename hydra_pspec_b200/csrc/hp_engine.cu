@@ -1177,10 +1177,12 @@ static void enqueue_iteration_sub(hp_engine* e, const Sub& sb, int it, uint32_t 
     Basis& b = general ? e->b0 : e->bF;
     IterOut o{};
     const size_t R = e->ring, slot = (size_t)it % R;   // big outputs: ring slot; signal_ps / ln_post: one entry per iteration
-    o.sf = e->cr_out ? e->cr_out + 2 * slot * T * n : e->Sf;
-    o.sf_bs = e->cr_out ? (long long)(R * T * n) : (long long)(Tp * n);
-    o.fg = e->fg_out ? e->fg_out + 2 * slot * T * m : nullptr; o.fg_bs = 2 * (long long)(R * T * m);
-    o.chisq = e->chisq_out ? e->chisq_out + slot * T * n : nullptr; o.chisq_bs = (long long)(R * T * n);
+    // ring layout [slot][chain][...]: one iteration's array of all chains is contiguous (one plain copy to the host)
+    const size_t Cn = (size_t)e->C;
+    o.sf = e->cr_out ? e->cr_out + 2 * slot * Cn * T * n : e->Sf;
+    o.sf_bs = e->cr_out ? (long long)(T * n) : (long long)(Tp * n);
+    o.fg = e->fg_out ? e->fg_out + 2 * slot * Cn * T * m : nullptr; o.fg_bs = 2 * (long long)(T * m);
+    o.chisq = e->chisq_out ? e->chisq_out + slot * Cn * T * n : nullptr; o.chisq_bs = (long long)(T * n);
     enqueue_gcr(e, b, o, sb, draw_iter);
 
     e->prof_begin(CLS_SAMPLE, sb.st);
@@ -1283,16 +1285,30 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
             cudaEventRecord(e->sub_done[i], subs[i].st);
             cudaStreamWaitEvent(e->copy_st, e->sub_done[i], 0);
         }
-        // one strided copy per array (rows = chains; device pitch = a chain's ring, host pitch = a chain's host array)
-        if (sink->signal_cr)
-            cerr = copy_rows_d2h(sink->signal_cr + 2 * (hs * T * n), HI * T * n * 16, e->cr_out + 2 * (slot * T * n), R * T * n * 16,
-                                 T * n * 16, C, e->copy_st);
-        if (sink->fg_amps && m && cerr == cudaSuccess)
-            cerr = copy_rows_d2h(sink->fg_amps + 2 * (hs * T * m), HI * T * m * 16, e->fg_out + 2 * (slot * T * m), R * T * m * 16,
-                                 T * m * 16, C, e->copy_st);
-        if (sink->chisq && cerr == cudaSuccess)
-            cerr = copy_rows_d2h(sink->chisq + hs * T * n, HI * T * n * 8, e->chisq_out + slot * T * n, R * T * n * 8, T * n * 8, C,
-                                 e->copy_st);
+        // The ring is [slot][chain][...]: an iteration's array of all chains is one contiguous block.  iter_major sinks
+        // ([iters][nchains][...]) take it with one plain copy per array; chain-major sinks ([nchains][iters][...]) with one
+        // strided copy per array (rows = chains).
+        if (sink->iter_major) {
+            if (sink->signal_cr)
+                cerr = cudaMemcpyAsync(sink->signal_cr + 2 * (hs * C * T * n), e->cr_out + 2 * (slot * C * T * n), C * T * n * 16,
+                                       cudaMemcpyDeviceToHost, e->copy_st);
+            if (sink->fg_amps && m && cerr == cudaSuccess)
+                cerr = cudaMemcpyAsync(sink->fg_amps + 2 * (hs * C * T * m), e->fg_out + 2 * (slot * C * T * m), C * T * m * 16,
+                                       cudaMemcpyDeviceToHost, e->copy_st);
+            if (sink->chisq && cerr == cudaSuccess)
+                cerr = cudaMemcpyAsync(sink->chisq + hs * C * T * n, e->chisq_out + slot * C * T * n, C * T * n * 8,
+                                       cudaMemcpyDeviceToHost, e->copy_st);
+        } else {
+            if (sink->signal_cr)
+                cerr = copy_rows_d2h(sink->signal_cr + 2 * (hs * T * n), HI * T * n * 16, e->cr_out + 2 * (slot * C * T * n), T * n * 16,
+                                     T * n * 16, C, e->copy_st);
+            if (sink->fg_amps && m && cerr == cudaSuccess)
+                cerr = copy_rows_d2h(sink->fg_amps + 2 * (hs * T * m), HI * T * m * 16, e->fg_out + 2 * (slot * C * T * m), T * m * 16,
+                                     T * m * 16, C, e->copy_st);
+            if (sink->chisq && cerr == cudaSuccess)
+                cerr = copy_rows_d2h(sink->chisq + hs * T * n, HI * T * n * 8, e->chisq_out + slot * C * T * n, T * n * 8, T * n * 8, C,
+                                     e->copy_st);
+        }
         cudaEventRecord(e->copy_done[slot], e->copy_st);
     }
     join_subs(e, subs);
@@ -1369,7 +1385,7 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
         case HP_BUF_CR:
         case HP_BUF_FG:
         case HP_BUF_CHISQ: {
-            // ring of e->ring slots per chain: iteration i lives in slot i % ring until iteration i + ring overwrites it
+            // ring [slot][chain][...]: iteration i lives in slot i % ring until iteration i + ring overwrites it
             const double* base = buffer == HP_BUF_CR ? e->cr_out : (buffer == HP_BUF_FG ? e->fg_out : e->chisq_out);
             if (!base) return fail(HP_ERR_ARG, "this output was not kept (cfg.keep)");
             const size_t R = e->ring;
@@ -1380,7 +1396,7 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
                 return fail(HP_ERR_ARG, "iteration no longer in the device ring (cfg.ring_iters): stream it with hp_engine_run_to_host");
             for (int k = 0; k < niter; ++k) {
                 const size_t slot = (size_t)(iter0 + k) % R;
-                if (per) CU_TRY(cudaMemcpy((char*)dst + (size_t)k * per * 8, base + ((size_t)c * R + slot) * per, per * 8, cudaMemcpyDeviceToHost));
+                if (per) CU_TRY(cudaMemcpy((char*)dst + (size_t)k * per * 8, base + (slot * (size_t)e->C + (size_t)c) * per, per * 8, cudaMemcpyDeviceToHost));
             }
             return HP_OK;
         }

@@ -283,21 +283,24 @@ class GibbsEngine:
     def run(self, niter):
         _lib.check(_lib.lib().hp_engine_run(self._h, int(niter)))
 
-    def host_buffers(self, iters=None, pinned=True):
-        """Host arrays ``[nchains][iters][...]`` for :meth:`run_to_host` (page-locked by default)."""
+    def host_buffers(self, iters=None, pinned=True, iter_major=False):
+        """Host arrays for :meth:`run_to_host` (page-locked by default): ``[nchains][iters][...]``, or -- ``iter_major`` --
+        ``[iters][nchains][...]`` for the big arrays (signal_cr, fg_amps, chisq): an iteration's array of all chains is then
+        one contiguous block on both sides of the copy (``signal_ps`` / ``ln_post`` stay ``[nchains][iters]``)."""
         iters = self.max_iters if iters is None else iters
         mk = _lib.pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
         C, T, n, m = self.nchains, self.ntimes, self.nfreqs, self.nmodes
+        lead = (iters, C) if iter_major else (C, iters)
         out = {"signal_ps": mk((C, iters, n), np.float64), "ln_post": mk((C, iters), np.float64)}
         if "cr" in self.keep:
-            out["signal_cr"] = mk((C, iters, T, n), np.complex128)
+            out["signal_cr"] = mk(lead + (T, n), np.complex128)
         if "fg" in self.keep:
-            out["fg_amps"] = mk((C, iters, T, m), np.complex128)
+            out["fg_amps"] = mk(lead + (T, m), np.complex128)
         if "chisq" in self.keep:
-            out["chisq"] = mk((C, iters, T, n), np.float64)
+            out["chisq"] = mk(lead + (T, n), np.float64)
         return out
 
-    def run_to_host(self, niter, bufs, first_iter=0):
+    def run_to_host(self, niter, bufs, first_iter=0, iter_major=False):
         """Run ``niter`` iterations and stream every iteration's arrays into ``bufs`` (from
         :meth:`host_buffers`) while the next iteration computes; returns when all data has landed.
         Iteration ``i`` of the chain lands in slot ``i - first_iter`` of the host arrays: a bounded staging area is
@@ -306,10 +309,12 @@ class GibbsEngine:
         for k in ("signal_ps", "ln_post", "signal_cr", "fg_amps", "chisq"):
             a = bufs.get(k)
             if a is not None:
-                assert a.flags["C_CONTIGUOUS"] and a.shape[0] == self.nchains
+                big = iter_major and k in ("signal_cr", "fg_amps", "chisq")
+                assert a.flags["C_CONTIGUOUS"] and a.shape[1 if big else 0] == self.nchains
                 setattr(sink, k, a.ctypes.data)
         sink.iters = int(bufs["signal_ps"].shape[1])
         sink.first_iter = int(first_iter)
+        sink.iter_major = int(bool(iter_major))
         _lib.check(_lib.lib().hp_engine_run_to_host(self._h, int(niter), _lib.C.byref(sink)))
 
     def gcr(self):
@@ -424,16 +429,17 @@ def _staged_run(eng, Niter, dest, write_Niter=None, after_chunk=None):
     chunk = max(1, min(Niter, _STAGING_BYTES // max(per_iter, 1)))
     if write_Niter:
         chunk = min(chunk, write_Niter)
-    stage = eng.host_buffers(chunk)
+    stage = eng.host_buffers(chunk, iter_major=True)   # iteration-major staging: one plain copy per array and iteration
     done = 0
     while done < Niter:
         c = min(chunk, Niter - done)
         if write_Niter:   # never run past a write boundary (pspec.py:625: files every write_Niter iterations)
             c = min(c, write_Niter - done % write_Niter)
-        eng.run_to_host(c, stage, first_iter=done)
+        eng.run_to_host(c, stage, first_iter=done, iter_major=True)
         for k, a in dest.items():
             if a is not None:
-                a[:, done:done + c] = stage[k][:, :c]
+                big = k in ("signal_cr", "fg_amps", "chisq")
+                a[:, done:done + c] = np.swapaxes(stage[k][:c], 0, 1) if big else stage[k][:, :c]
         done += c
         if after_chunk is not None and (done == Niter or (write_Niter and done % write_Niter == 0)):
             after_chunk(done)

@@ -128,12 +128,17 @@ int hp_engine_set_draws(hp_engine* e, int chain, const double* omega_a, const do
  * Asynchronous on the engine's stream. */
 int hp_engine_run(hp_engine* e, int niter);
 /* Host destinations of the sample arrays (page-locked memory recommended: hp_pinned_alloc).  Layout
- * [nchains][iters][...] with the shapes of hp_buffer; NULL = not wanted. */
+ * [nchains][iters][...] with the shapes of hp_buffer (or [iters][nchains][...] for the big arrays, see iter_major);
+ * NULL = not wanted. */
 typedef struct hp_host_sink {
     double* signal_ps; double* ln_post; double* signal_cr; double* fg_amps; double* chisq;
     int iters;           /* capacity (second dimension) of the host arrays */
     int first_iter;      /* iteration index stored in host slot 0: iteration i lands in slot i - first_iter.  A bounded
                             staging area is re-used chunk after chunk by advancing first_iter (0 = whole chain) */
+    int iter_major;      /* 0: signal_cr / fg_amps / chisq host arrays are [nchains][iters][...] (one strided copy per array and
+                            iteration); 1: [iters][nchains][...] -- an iteration's array of all chains is then one contiguous block
+                            on both sides and leaves with one plain copy (full PCIe rate).  signal_ps / ln_post are always
+                            [nchains][iters][...] */
 } hp_host_sink;
 /* hp_engine_run + copy-out: every iteration's arrays are streamed to the host on a second stream
  * while the next iteration computes.  Returns when everything has landed. */
