@@ -128,8 +128,8 @@ int hp_engine_set_draws(hp_engine* e, int chain, const double* omega_a, const do
  * Asynchronous on the engine's stream. */
 int hp_engine_run(hp_engine* e, int niter);
 /* Host destinations of the sample arrays (page-locked memory recommended: hp_pinned_alloc).  Layout
- * [nchains][iters][...] with the shapes of hp_buffer (or [iters][nchains][...] for the big arrays, see iter_major);
- * NULL = not wanted. */
+ * [nchains][iters][...] with the shapes listed under enum hp_buffer -- or [iters][nchains][...] for the big arrays, see
+ * iter_major; NULL = not wanted. */
 typedef struct hp_host_sink {
     double* signal_ps; double* ln_post; double* signal_cr; double* fg_amps; double* chisq;
     int iters;           /* capacity (second dimension) of the host arrays */

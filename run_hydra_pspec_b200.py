@@ -130,7 +130,7 @@ def read_visibilities(file_paths, ant_str, freq_range):
     from hydra_pspec_b200 import utils
     try:
         from pyuvdata import UVData  # pragma: no cover - not in this image
-        have_pyuvdata = True
+        have_pyuvdata = hasattr(UVData, "read")   # (a stub module stands in for it when the reference is imported)
     except ImportError:
         have_pyuvdata = False
     if have_pyuvdata:  # pragma: no cover
