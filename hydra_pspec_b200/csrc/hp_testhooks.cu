@@ -127,11 +127,11 @@ int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double*
     hp::launch_trinv(dLp, dLinv, dWp, hp::TrinvExtra{dWp1, dWf1, dWf2, wa ? nullptr : dlam}, nblk, 1, 0);
     if (variant != 3 && wa) cudaMemcpy(dWp1, dWp, 8 * tri, cudaMemcpyDeviceToDevice);
     for (int s = 0; s < nsys; ++s) {
-        // lam is shared: k_rhs_tile indexes lam by system, so build one system at a time
+        // lam is shared by the systems while k_rhs_tile indexes lam by system: build the tiles one system at a time
         hp::launch_rhs_tile(dRt + (size_t)s * ntiles * nblk * 2 * 32 * hp::kTT, dR + 2ull * s * Tp * Np,
                             dW ? dW + 2ull * s * Tp * Np : nullptr, wa ? dlam : nullptr, nblk, n, N, T, Tp, ntiles, 1, 0);
     }
-    // one launch over all systems needs per-system W: replicate the factor
+    // one solve launch covers all systems and expects per-system W: replicate the one factor
     double *dWall, *dW1all;
     cudaMalloc(&dWall, 8 * tri * nsys); cudaMalloc(&dW1all, 8 * tri * nsys);
     for (int s = 0; s < nsys; ++s) {
