@@ -40,14 +40,24 @@ constexpr int kW3 = kS3Warps;                 // consumer warps (all warps of th
 constexpr int kS3Threads = 32 * kW3;
 constexpr int kRowDoubles3 = 2 * 32 * kTT;    // one block row of a tile: [plane][32 rows][16 columns, XOR-swizzled]
 constexpr int kFragDoubles = 128;             // one k-step of one strip in fragment-major order: 32 lanes x 4 doubles
+#ifndef HP_S3_L1_PREFETCH
+#define HP_S3_L1_PREFETCH 2                   // k-steps of L1 prefetch distance (0: loads bypass L1, no prefetch)
+#endif
 
 __device__ __forceinline__ double4 ldg_frag(const double* p) {
     // streaming fragment ([row group][lane][re, im]: two 16-byte loads, each 512 contiguous bytes per warp); every byte is
     // used once per CTA, keep it out of L1.  Volatile asm: the load keeps its place between the (volatile) DMMAs, after the
     // first DMMA of a k-step has waited for the previous load -- one load group in flight per warp.
     double4 v;
+#if HP_S3_L1_PREFETCH > 0
+    // loads through L1: the group HP_S3_L1_PREFETCH k-steps ahead was requested into L1 by a prefetch (no destination
+    // register, hence no scoreboard): more fragment data in flight without the scoreboard aliasing.  5.27 -> 5.15 ms.
+    asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "l"(p + 64));
+#else
     asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "l"(p + 64));
+#endif
     return v;
 }
 
@@ -188,6 +198,12 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
         const double4 v = ldg_frag(pf_p);
         pf_p += kFragDoubles;
         --pf_left;
+#if HP_S3_L1_PREFETCH > 0
+        if (pf_left >= HP_S3_L1_PREFETCH) {   // the group HP_S3_L1_PREFETCH k-steps after the one just requested
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf_p + (HP_S3_L1_PREFETCH - 1) * kFragDoubles));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf_p + (HP_S3_L1_PREFETCH - 1) * kFragDoubles + 64));
+        }
+#endif
         return v;
     };
     // Exactly one fragment load is in flight per warp (issued before the DMMAs of the current k-step, consumed by the next):
