@@ -260,7 +260,11 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
                         const int col = 8 * wj + 2 * q + x;
                         double vr = P[0][wi][wj][x] - P[1][wi][wj][x];
                         double vi = P[2][wi][wj][x] - P[0][wi][wj][x] - P[1][wi][wj][x];
+#ifdef HP_S3_EXPERIMENT_NO_NOISE   // timing experiment only (wrong statistics): what the Philox draws cost
+                        if (false) {
+#else
                         if (a.philox && row < a.N && t0 + col < a.T) {
+#endif
                             u32x4 ctr; ctr.x = (uint32_t)row; ctr.y = (uint32_t)(t0 + col); ctr.z = a.iter; ctr.w = chain;
                             double x0, x1;
 #ifdef HP_PHILOX_DOUBLE   // experiment (profiles/r2_summary.md): what full double-precision Box-Muller costs this kernel
@@ -278,7 +282,9 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
             S3_T(1);
         }
         if (n1 == 0 && it > 0) mbar_wait(yfree, (it - 1) & 1);   // keep the phase bookkeeping of idle warps in step
+#ifndef HP_S3_EXPERIMENT_NO_BARRIER   // timing experiment only (wrong results): what the per-tile barrier costs
         consumer_sync3();   // y complete; r is dead
+#endif
         S3_T(2);
         if (tid == 0 && w + (int)gridDim.x < total) {
             // the next tile's right-hand sides land while pass 2 runs
