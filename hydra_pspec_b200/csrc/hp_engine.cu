@@ -253,6 +253,15 @@ struct hp_engine {
     double *wT = nullptr, *Hpt = nullptr, *niT = nullptr, *Bsel = nullptr, *ptScratch = nullptr;  // per-time flags
     int* ptSame = nullptr;   // [C][Tp]: flags of time t equal those of t - 1
     int pt_ctas = 0;
+    // per-time flags in low-rank form (hp_ptlow.cu): the shared system of the channels unflagged at any time goes through
+    // chol / trinv / k_solve3 with n extra right-hand sides (rows Tp0 .. of Rfix / X), k_pt_lowrank corrects every time
+    bool pt_low = false;     // engine runs the low-rank form (cleared when a chain has a time with > kPtLowMaxRank extra flags)
+    int Tp0 = 0;             // padded number of times; Tp = Tp0 + padded Nfreqs when pt_low was possible at creation
+    int pt_kcap = 0;         // largest number of extra flagged channels of any loaded (chain, time)
+    double* Pm = nullptr;    // [C][n][n] complex
+    uint16_t* ptFidx = nullptr;   // [C][T][kPtLowMaxRank]
+    int* ptFcnt = nullptr;   // [C][T]
+    std::vector<int> pt_kmax;     // per chain: largest extra-flag count
     int gd_slots = 1;
     std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
     bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
@@ -436,6 +445,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     e->Np = e->nblk * hp::kNB;
     e->ntiles = (e->T + hp::kTT - 1) / hp::kTT;
     e->Tp = e->ntiles * hp::kTT;
+    e->Tp0 = e->Tp;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     e->big_solve = cfg->force_dense_solve || !hp::solve_resident_ok(e->nblk, (size_t)max_smem);
@@ -445,6 +455,16 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         const int want = kv ? atoi(kv) : 3;
         const bool resident = !e->big_solve && !cfg->time_flags;
         e->solve3 = resident && want >= 3 && hp::solve3_ok(e->nblk, (size_t)max_smem);
+        // per-time flags: low-rank form on top of k_solve3 unless HP_PT_DIRECT=1 (A/B runs, tests of k_pt_cholsolve)
+        const char* pd = getenv("HP_PT_DIRECT");
+        if (cfg->time_flags && !(pd && pd[0] == '1') && !cfg->force_dense_solve && hp::solve3_ok(e->nblk, (size_t)max_smem) &&
+            e->n < 65536) {
+            e->pt_low = true;
+            e->solve3 = true;
+            e->Tp0 = e->Tp;
+            e->Tp += hp::kTT * ((e->n + hp::kTT - 1) / hp::kTT);
+            e->ntiles = e->Tp / hp::kTT;
+        }
         e->solve2 = resident && !e->solve3 && want >= 2 && hp::solve2_stages(e->nblk, (size_t)max_smem) >= 2;
         if (e->solve3) hp::solve3_make_schedule(e->nblk, &e->sched3);
     }
@@ -505,6 +525,11 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         ap.want(&e->niT, Tp * n);
         ap.want(&e->Bsel, 2 * n * (1 + m));
         ap.want(&e->ptScratch, (size_t)e->pt_ctas * hp::pt_scratch_doubles_per_cta(e->nblk));
+        if (e->pt_low) {
+            ap.want(&e->Pm, 2 * C * n * n);
+            ap.want(&e->ptFidx, C * T * hp::kPtLowMaxRank);
+            ap.want(&e->ptFcnt, C * T);
+        }
     }
     if (cfg->dense_noise) {
         ap.want(&e->NiD, 2 * C * n * n);
@@ -532,6 +557,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         }
     }
     e->flagged.assign(C, 0);
+    e->pt_kmax.assign(C, 0);
     e->pending.assign(C, 0);
     e->have_omega.assign(C, 0);
     {
@@ -603,9 +629,11 @@ static int build_basis_products(hp_engine* e, Basis& b, int c) {
         r.dk = e->cfg.time_flags ? e->ninvd + (size_t)c * n : e->ni + (size_t)c * n;
     }
     hp::launch_zgemm(r, e->st);
+    // low-rank form of per-time flags: the columns of A = D B^H sqrt(wbar N^-1) are n more right-hand sides (rows Tp0 + x)
+    if (e->ptFidx) hp::launch_pt_arows(b.Rfix + 2 * (size_t)c * e->Tp * Np, Bm, e->ni + (size_t)c * n, n, Np, e->Tp0, e->st);
     if (b.Rt && e->cfg.rng_mode == HP_RNG_PHILOX)
         hp::launch_rhs_tile(b.Rt + 2 * (size_t)c * e->Tp * Np, b.Rfix + 2 * (size_t)c * e->Tp * Np, nullptr, nullptr, e->nblk, e->n, e->N,
-                            e->T, e->Tp, e->ntiles, 1, e->st);
+                            e->ptFidx ? e->Tp : e->T, e->Tp, e->ntiles, 1, e->st);
     if (e->cfg.time_flags) {
         // H_t = [Q|F]^H (w_t N^-1) [q_0 | F]  for every time: column 0 is the generator chat_t of the circulant
         // signal block, the rest are the foreground columns of G_t (hp_pertime.cu)
@@ -689,7 +717,10 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     bool anyf = false;
     if (pt) {
         for (size_t i = 0; i < (size_t)T * n; ++i) { wtv[i] = flags[i] ? 1.0 : 0.0; }
-        for (int x = 0; x < n; ++x) wv[x] = 1.0;
+        // wbar: channels unflagged at any time (the shared system of the low-rank form; unused by k_pt_cholsolve)
+        for (int x = 0; x < n; ++x) wv[x] = 0.0;
+        for (int t = 0; t < T; ++t)
+            for (int x = 0; x < n; ++x) if (flags[(size_t)t * n + x]) wv[x] = 1.0;
         anyf = true;  // the masked-signal term of ln_post is always evaluated with the per-time mask
     } else {
         for (int x = 0; x < n; ++x) { wv[x] = flags[x] ? 1.0 : 0.0; anyf |= !flags[x]; }
@@ -706,6 +737,30 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
         std::vector<int> same(Tp, 0);
         for (int t = 1; t < T; ++t) same[t] = std::memcmp(flags + (size_t)t * n, flags + (size_t)(t - 1) * n, n) == 0 ? 1 : 0;
         CU_TRY(cudaMemcpyAsync(e->ptSame + (size_t)c * Tp, same.data(), (size_t)Tp * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (e->ptFidx) {
+            // channels flagged at time t beyond the all-times mask
+            std::vector<uint16_t> fidx((size_t)T * hp::kPtLowMaxRank, 0);
+            std::vector<int> fcnt(T, 0);
+            int kmax = 0;
+            for (int t = 0; t < T; ++t) {
+                int k = 0;
+                for (int x = 0; x < n; ++x)
+                    if (wv[x] != 0.0 && !flags[(size_t)t * n + x]) {
+                        if (k < hp::kPtLowMaxRank) fidx[(size_t)t * hp::kPtLowMaxRank + k] = (uint16_t)x;
+                        ++k;
+                    }
+                fcnt[t] = k;
+                if (k > kmax) kmax = k;
+            }
+            e->pt_kmax[c] = kmax;
+            CU_TRY(cudaMemcpyAsync(e->ptFidx + (size_t)c * T * hp::kPtLowMaxRank, fidx.data(), fidx.size() * sizeof(uint16_t),
+                                   cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMemcpyAsync(e->ptFcnt + (size_t)c * T, fcnt.data(), (size_t)T * sizeof(int), cudaMemcpyHostToDevice, st));
+            e->pt_kcap = 0;
+            for (int v : e->pt_kmax) if (v > e->pt_kcap) e->pt_kcap = v;
+            // a time with more extra flags than the low-rank kernel takes: the whole engine uses k_pt_cholsolve
+            e->pt_low = e->pt_kcap <= hp::kPtLowMaxRank;
+        }
     }
     // (wv / wtv are pageable locals: cudaMemcpyAsync has staged them before it returns; `vis` may be page-locked and is
     //  only guaranteed consumed by the stream synchronisation at the end of this function)
@@ -885,7 +940,8 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     const bool pt = e->cfg.time_flags != 0;
     bool any_omega = false;
     for (auto h : e->have_omega) any_omega |= (h != 0);
-    if (pt) {
+    const bool pt_low = pt && e->pt_low;
+    if (pt && !pt_low) {
         // one factorisation + solve per (chain, time); sub-batches share the SMs, each gets its share of the
         // persistent grid and of the scratch slots
         const int nsub = e->C > 0 ? (e->C + sb.nc - 1) / sb.nc : 1;
@@ -978,8 +1034,8 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         int nl = 1;
         const double* wa_sb = (!philox && any_omega) ? OFFS(b.wa, 2 * Tp * Np) : nullptr;
         if (!philox) {
-            hp::launch_rhs_tile(OFFS(b.Rt, 2 * Tp * Np), OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->nblk, e->n, e->N, e->T,
-                                e->Tp, e->ntiles, sb.nc, sb.st);
+            hp::launch_rhs_tile(OFFS(b.Rt, 2 * Tp * Np), OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->nblk, e->n, e->N,
+                                pt_low ? e->Tp : e->T, e->Tp, e->ntiles, sb.nc, sb.st);
             ++nl;
         }
         hp::Solve3Args sa{};
@@ -993,6 +1049,27 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         sa.chain_ids = OFFS(e->chain_ids, 1); sa.chain0 = sb.c0;
         sa.sched = e->sched3;
         hp::launch_solve3(sa, sb.st);
+        if (pt_low) {
+            // per-time flags: rows Tp0 + x of X now hold R = M_0^-1 A.  P = A^H R, then the rank-k_t correction of every time
+            hp::ZgemmArgs pz{};
+            pz.A = OFFS(b.Rfix, 2 * Tp * Np) + 2 * (size_t)e->Tp0 * Np; pz.sAi = e->Np; pz.sAk = 1; pz.bsA = (long long)e->Tp * e->Np;
+            pz.conjA = 1; pz.dk = OFFS(e->lam, Np); pz.bsD = e->Np;
+            pz.B = sa.X + 2 * (size_t)e->Tp0 * Np; pz.sBk = 1; pz.sBj = e->Np; pz.bsB = (long long)e->Tp * e->Np;
+            pz.C = OFFS(e->Pm, 2 * n * n); pz.sCi = e->n; pz.sCj = 1; pz.bsC = (long long)e->n * e->n;
+            pz.M = e->n; pz.N = e->n; pz.K = e->N; pz.alpha = 1.0; pz.batch = sb.nc;
+            hp::launch_zgemm(pz, sb.st);
+            hp::PtLowArgs la{};
+            la.Rfix = OFFS(b.Rfix, 2 * Tp * Np); la.wa = wa_sb; la.lam = OFFS(e->lam, Np); la.X = sa.X; la.Pm = OFFS(e->Pm, 2 * n * n);
+            la.fidx = e->ptFidx + (size_t)sb.c0 * e->T * hp::kPtLowMaxRank; la.fcnt = e->ptFcnt + (size_t)sb.c0 * e->T;
+            la.info = e->info + sb.c0;
+            la.n = e->n; la.N = e->N; la.Np = e->Np; la.T = e->T; la.Tp = e->Tp; la.Tp0 = e->Tp0; la.nsys = sb.nc; la.nblk = e->nblk;
+            la.kcap = e->pt_kcap; la.philox = philox ? 1 : 0;
+            la.key0 = (uint32_t)e->cfg.seed; la.key1 = (uint32_t)(e->cfg.seed >> 32); la.iter = draw_iter;
+            la.chain_ids = OFFS(e->chain_ids, 1); la.chain0 = sb.c0;
+            hp::launch_pt_lowrank(la, sb.st);
+            hp::launch_colsumsq(sa.X, OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
+            nl += 3;
+        }
         if (e->cfg.cg_compat) {
             hp::launch_cg_scale(sa.X, OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->n, e->N, e->Np, e->T, e->Tp, sb.nc, sb.st);
             hp::launch_colsumsq(sa.X, OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);

@@ -186,6 +186,31 @@ size_t pt_scratch_doubles_per_cta(int nblk);
 int pt_grid(int nsys, int T);   // persistent grid: 2 CTAs per SM, at most one per (system, time) pair
 void launch_pt_cholsolve(const PtArgs& a, int grid, cudaStream_t st);
 
+// ---- per-time flags, low-rank form (hp_ptlow.cu): M_t = M_0 - V_t^H V_t with M_0 the system of the channels that are
+// unflagged at any time (one shared factorisation, k_solve3) and V_t the k_t rows of the channels flagged at time t only.
+//   x_t = x0_t + R_f K_t^-1 ((R^H b_t)_f [+ L_K zeta]),   K_t = I - P_ff = L_K L_K^H,   R = M_0^-1 A,   P = A^H R
+// A = D [Q|F]^H sqrt(wbar N^-1) rides through k_solve3 as n extra right-hand sides (rows Tp0 .. Tp0 + n of Rfix / X).
+constexpr int kPtLowMaxRank = 64;     // channels flagged at one time beyond the all-times mask; more -> k_pt_cholsolve
+struct PtLowArgs {
+    const double* Rfix;    // [nsys][Tp][Np] complex: rows t < T right-hand sides (unscaled), rows Tp0 + x the columns of A / D
+    const double* wa;      // [nsys][Tp][Np] complex or null (injected draws)
+    const double* lam;     // [nsys][Np]
+    double* X;             // [nsys][Tp][Np] complex: rows t < T hold x0_t (in) / x_t (out); rows Tp0 + x hold R[:, x]
+    const double* Pm;      // [nsys][n][n] complex, P = A^H R (lower triangle read)
+    const uint16_t* fidx;  // [nsys][T][kPtLowMaxRank] channels flagged at time t only
+    const int* fcnt;       // [nsys][T]
+    int* info;             // [nsys]: atomicMax(nblk + 1) when a K_t is not positive definite
+    int n, N, Np, T, Tp, Tp0, nsys, nblk, kcap;   // kcap: largest count in fcnt (shared-memory sizing)
+    int philox;
+    uint32_t key0, key1, iter;
+    const int* chain_ids;
+    int chain0;
+};
+size_t pt_lowrank_smem_bytes(int kcap, int warps);
+void launch_pt_lowrank(const PtLowArgs& a, cudaStream_t st);
+// Rfix rows Tp0 + x = sqrt(ni[x]) conj(Bmat[x][:]) for one system
+void launch_pt_arows(double* Rfix_sys, const double* Bmat_sys, const double* ni_sys, int n, int Np, int Tp0, cudaStream_t st);
+
 struct SampleArgs {
     const double* Ppart;   // [nsys][ntiles][n]  (beta_mode 0)
     const double* Eu;      // [nsys][n]: sum_t |U s|^2 (beta_mode 1: general-basis iteration)

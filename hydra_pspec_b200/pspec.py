@@ -477,7 +477,8 @@ def build_matrices(Nparams, flags, signal_S, Ninv, fgmodes):
 def _check_per_time_supported(solver, basis0, ninv_dense):
     """Per-time flags ``(Ntimes, Nfreqs)`` are an extension of the reference (it asserts 1-D flags,
     pspec.py:428, and its driver collapses them, run-hydra-pspec.py:520-526): every time gets its own
-    factorisation (csrc/hp_pertime.cu)."""
+    factorisation (csrc/hp_pertime.cu), or -- when no time has more than 64 channels flagged beyond the all-times
+    mask -- as a low-rank correction of one shared factorisation (csrc/hp_ptlow.cu)."""
     if solver != "exact":
         raise NotImplementedError("per-time flags: only solver='exact' (the reference has no per-time CG to reproduce)")
     if basis0 is not None:
@@ -747,7 +748,9 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
     if dense:
         per_chain += 16 * nfreqs * nfreqs * 3 + 16 * Tp * nfreqs * 2
     if per_time:
-        per_chain += 16 * Tp * (1 + nmodes) * Np + 8 * Tp * nfreqs
+        # low-rank form (csrc/hp_ptlow.cu): Nfreqs more right-hand sides ride through the solve, plus P and the flag lists
+        Tx = Tp + 16 * ((nfreqs + 15) // 16)
+        per_chain = per_chain * Tx // Tp + 16 * Tx * (1 + nmodes) * Np + 8 * Tx * nfreqs + 16 * nfreqs * nfreqs + 132 * ntimes
     dev_budget = float(os.environ.get("HP_DEVICE_BUDGET_GB", "150")) * 2 ** 30
     group = max(1, min(nb, int(dev_budget // per_chain)))
     write_times = [0.0] * nb

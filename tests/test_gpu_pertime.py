@@ -48,9 +48,20 @@ def make_case(nt, nf, nm, frac, seed):
     return vis, flags, S0, F, np.diag(1.0 / sig ** 2), prior
 
 
+@pytest.fixture(params=["lowrank", "direct"])
+def pt_form(request, monkeypatch):
+    """Both forms of the per-time solve: the low-rank correction of one shared factorisation (hp_ptlow.cu, default) and
+    one factorisation per time (hp_pertime.cu: HP_PT_DIRECT=1, read at engine creation)."""
+    if request.param == "direct":
+        monkeypatch.setenv("HP_PT_DIRECT", "1")
+    else:
+        monkeypatch.delenv("HP_PT_DIRECT", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("nt,nf,nm,frac,seed", [(6, 32, 4, 0.1, 1), (9, 45, 5, 0.2, 2), (12, 120, 12, 0.05, 3),
                                                 (5, 64, 0, 0.3, 4), (7, 96, 33, 0.1, 5), (4, 256, 16, 0.1, 6)])
-def test_per_time_chain_matches_oracle(nt, nf, nm, frac, seed):
+def test_per_time_chain_matches_oracle(nt, nf, nm, frac, seed, pt_form):
     from hydra_pspec_b200 import pspec
     vis, flags, S0, F, Ninv, prior = make_case(nt, nf, nm, frac, seed)
     niter = 3
@@ -71,7 +82,7 @@ def test_constant_per_time_flags_equal_shared_factorisation():
         assert rel(y, x) < (1e-8 if k == "chisq" else TOL), k
 
 
-def test_per_time_solution_solves_each_time_system():
+def test_per_time_solution_solves_each_time_system(pt_form):
     """Size-independent property at the configs[2] system size (Nfreq=256, Nfg=16): residual of every
     per-time system M_t x = b_t, map_estimate (no fluctuation terms)."""
     from hydra_pspec_b200 import pspec
@@ -135,7 +146,7 @@ def test_per_time_unsupported_combinations_raise():
 
 
 @pytest.mark.parametrize("nt,nf,nm,seed", [(2, 8, 1, 1), (3, 12, 2, 2), (5, 16, 0, 3)])
-def test_per_time_tiny_shapes(nt, nf, nm, seed):
+def test_per_time_tiny_shapes(nt, nf, nm, seed, pt_form):
     from hydra_pspec_b200 import pspec
     vis, flags, S0, F, Ninv, _ = make_case(nt, nf, nm, 0.2, 50 + seed)
     prior = np.zeros((2, nf))
@@ -145,7 +156,7 @@ def test_per_time_tiny_shapes(nt, nf, nm, seed):
         assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
 
 
-def test_per_time_fully_flagged_integration_is_refused():
+def test_per_time_fully_flagged_integration_is_refused(pt_form):
     """An integration with every channel flagged leaves the (flat-prior) foreground amplitudes of that time
     unconstrained: the system is singular and the chain is refused with LinAlgError instead of returning NaNs."""
     from hydra_pspec_b200 import pspec
@@ -156,7 +167,7 @@ def test_per_time_fully_flagged_integration_is_refused():
 
 
 @pytest.mark.parametrize("hold", [2, 5, 100])
-def test_per_time_repeated_masks_reuse_the_factor(hold):
+def test_per_time_repeated_masks_reuse_the_factor(hold, pt_form):
     """Consecutive times with identical flag vectors re-use the factorisation held in the CTA's scratch slot
     (forward + backward substitution only): results must not depend on it."""
     from hydra_pspec_b200 import pspec
@@ -173,3 +184,45 @@ def test_per_time_repeated_masks_reuse_the_factor(hold):
     one = pspec.gibbs_sample_with_fg(bls[3]["vis"], flags, S0, F, Ninv, prior, Niter=2, seed=7, verbose=False)
     for o, r, k in zip(outs[3][:6], one[:6], KEYS):
         assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
+
+
+@pytest.mark.parametrize("frac,expect_lowrank", [(0.2, True), (0.45, False)])
+def test_per_time_rank_limit_selects_the_form(frac, expect_lowrank):
+    """Nfreq=256: 20 % per-time flags stay below the 64-channel limit of the low-rank form (ranks up to ~60); 45 % exceed it
+    and the engine falls back to one factorisation per time.  Both against the oracle."""
+    from hydra_pspec_b200 import pspec
+    vis, flags, S0, F, Ninv, prior = make_case(6, 256, 16, frac, 61)
+    if expect_lowrank:
+        wbar = flags.any(axis=0)
+        flags[1, np.flatnonzero(wbar)[:64]] = False       # one time at exactly the limit
+        flags[1, np.flatnonzero(wbar)[64:]] = True
+    kmax = int(np.max(np.sum(flags.any(axis=0)[None, :] & ~flags, axis=1)))
+    assert (kmax <= 64) == expect_lowrank
+    ref = ho.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=9, solver="direct")
+    out = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=2, seed=9, verbose=False)
+    for o, r, k in zip(out[:6], ref, KEYS):
+        assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
+
+
+def test_per_time_forms_agree_at_config2_shape():
+    """BASELINE.json configs[2] shape (Nfreq=256, Nfg=16, 5 % per-time flags on top of a 5 % all-times mask), 64 times, four
+    chains in one engine: low-rank form == one factorisation per time to round-off (injected draws, two iterations)."""
+    import os
+    from hydra_pspec_b200 import pspec
+    bls = []
+    for c in range(4):
+        vis, flags, S0, F, Ninv, prior = make_case(64, 256, 16, 0.05, 70 + c)
+        flags[:, np.random.default_rng(c).choice(256, 12, replace=False)] = False
+        bls.append(dict(vis=vis, flags=flags, S_initial=S0, fgmodes=F, Ninv=Ninv, ps_prior=prior))
+    old = os.environ.pop("HP_PT_DIRECT", None)
+    try:
+        low = pspec.gibbs_sample_batch(bls, Niter=2, seed=5, rng="numpy", solver="exact")
+        os.environ["HP_PT_DIRECT"] = "1"
+        direct = pspec.gibbs_sample_batch(bls, Niter=2, seed=5, rng="numpy", solver="exact")
+    finally:
+        os.environ.pop("HP_PT_DIRECT", None)
+        if old is not None:
+            os.environ["HP_PT_DIRECT"] = old
+    for a, b in zip(low, direct):
+        for x, y, k in zip(a[:6], b[:6], KEYS):
+            assert rel(x, y) < (1e-8 if k == "chisq" else TOL), k

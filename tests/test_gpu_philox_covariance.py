@@ -40,16 +40,22 @@ def nrm(C, Sigma):
     return np.max(np.abs(C) / np.outer(d, d))
 
 
-@pytest.mark.parametrize("variant", ["solve2", "dense_solve", "time_flags"])
-def test_philox_gcr_covariance_multiblock(variant):
+@pytest.mark.parametrize("variant", ["solve2", "dense_solve", "time_flags", "time_flags_direct"])
+def test_philox_gcr_covariance_multiblock(variant, monkeypatch):
     from hydra_pspec_b200 import pspec
+    # per-time flags: the low-rank form (k_solve3 + k_pt_lowrank with its own zeta draws; default) and one factorisation
+    # per time (k_pt_cholsolve)
+    if variant == "time_flags_direct":
+        monkeypatch.setenv("HP_PT_DIRECT", "1")
+    else:
+        monkeypatch.delenv("HP_PT_DIRECT", raising=False)
     nt, nf, nm, nch, ndraw = 48, 96, 8, 4, 4000          # N = 104: 4 block rows; 3 time tiles; 4 chains
     rng = np.random.default_rng(2024)
     F = np.linalg.qr(crandn(rng, nf, nm))[0]
     ps = nf * (0.5 + 2.0 * rng.random(nf))                # fixed spectrum: lam^2 = ps / nf in [0.5, 2.5]
     ninv_diag = 1.0 + rng.random(nf)
     vis = crandn(rng, nch, nt, nf) + (3 * crandn(rng, nch, nt, nm)) @ F.T
-    per_time = variant == "time_flags"
+    per_time = variant.startswith("time_flags")
     if per_time:
         masks = np.ones((2, nf), dtype=bool)
         masks[0, [5, 40, 41]] = False
