@@ -39,8 +39,8 @@ FP64_PEAK_NOMINAL_TFLOPS = 37.2  # 148 SMs x 64 FP64 FMA/clk x 2 x 1.965 GHz
 CONFIGS = {
     1: dict(nt=64, nf=128, nm=8, per_gpu=1, total=None, mode="std", flags=False, scaling="replicas", steps=200,
             what="single synthetic baseline, diagonal noise, no flags (one replica per GPU)"),
-    2: dict(nt=512, nf=256, nm=16, per_gpu=None, total=128, mode="pertime", flags=True, scaling="strong", steps=5,
-            what="128 baselines in total, a different random RFI mask at every time (in-painting, no shared factorisation)"),
+    2: dict(nt=512, nf=256, nm=16, per_gpu=None, total=128, mode="pertime", flags=True, scaling="strong", steps=40,
+            what="128 baselines in total, a different random RFI mask at every time (in-painting: every time has its own GCR system)"),
     3: dict(nt=1024, nf=384, nm=32, per_gpu=128, total=None, mode="std", flags=True, scaling="weak", steps=20,
             what="HERA-like, 128 baselines per GPU (1024 / 8), time-invariant flags (5 %), diagonal noise"),
     4: dict(nt=1024, nf=1024, nm=64, per_gpu=32, total=None, mode="dense", flags=True, scaling="weak", steps=10,
@@ -503,10 +503,19 @@ def run_b200(args):
     # ---- roofline of the dominant kernel
     peak = _lib.lib().hp_fp64_peak_tflops(local_rank, 0.3)
     solve_ms, solve_launches = kms["solve"]
-    if c["mode"] == "pertime":
+    pt_form, pt_kmax = eng.pt_form() if c["mode"] == "pertime" else (None, 0)
+    direct_flops = (4.0 * N ** 3 / 3 + 8.0 * N * N) * nt * B   # one factorisation + two substitutions per (baseline, time)
+    if c["mode"] == "pertime" and pt_form == "direct":
         kernel = "k_pt_cholsolve"
-        flops_per_launch = (4.0 * N ** 3 / 3 + 8.0 * N * N) * nt * B   # one factorisation + two substitutions per (baseline, time)
+        flops_per_launch = direct_flops
         note = "4 N^3/3 + 8 N^2 flops per (baseline, time) system"
+    elif c["mode"] == "pertime":
+        # low-rank form (csrc/hp_ptlow.cu): one shared factorisation per baseline; k_solve3 solves the Ntimes right-hand sides
+        # and the Nfreq columns of A = D [Q|F]^H sqrt(wbar N^-1); per time a rank-k_t correction (k_pt_lowrank)
+        kernel = "k_solve3"
+        flops_per_launch = 8.0 * N * N * (nt + nf) * B
+        note = ("8 N^2 (Ntimes + Nfreq) flops per baseline-iteration: two triangular products with W = L^-1 for the Ntimes right-hand "
+                "sides and the Nfreq columns of A (low-rank form of the per-time systems)")
     else:
         kernel = "k_solve3" if N <= 448 else ("k_solve2 / k_solve" if N <= 576 else "k_zgemm (dense-product solve)")
         flops_per_launch = 8.0 * N * N * nt * B
@@ -527,7 +536,18 @@ def run_b200(args):
     }
     # algorithmic flops of a step: complex Cholesky N^3/6 complex MACs (= 4 N^3 / 3 real flops) + two triangular
     # solves for T right-hand sides (N^2 T complex MACs = 8 N^2 T); the explicit W = L^-1 is an implementation choice
-    step_flops = flops_per_launch if c["mode"] == "pertime" else (4.0 * N ** 3 / 3 + 8.0 * N * N * nt) * B
+    if c["mode"] == "pertime" and pt_form == "low-rank":
+        # + P = A^H R (Hermitian: 4 n^2 N) + per time a k x k Cholesky and 2 k N complex MACs (mean k = rank of the correction)
+        kbar = float(np.mean([np.mean(np.sum(f.any(axis=0)[None, :] & ~f, axis=1)) for f in
+                              (host_inputs(first + ch)[1] for ch in range(min(B, 4)))]))
+        step_flops = (4.0 * N ** 3 / 3 + 8.0 * N * N * (nt + nf) + 4.0 * nf * nf * N + nt * (4.0 * kbar ** 3 / 3 + 16.0 * kbar * N)) * B
+        roofline["per_time_form"] = {"form": pt_form, "max_rank": pt_kmax, "mean_rank": kbar,
+                                     "lowrank_ms_per_step": kms["lowrank"][0] / KP,
+                                     "direct_form_equivalent_tflops": direct_flops * K / (ms * 1e-3) * 1e-12,
+                                     "note": "step_tflops counts the flops of the low-rank form; direct_form_equivalent_tflops is what "
+                                             "one factorisation per (baseline, time) would need at this rate (may exceed the peak)"}
+    else:
+        step_flops = flops_per_launch if c["mode"] == "pertime" else (4.0 * N ** 3 / 3 + 8.0 * N * N * nt) * B
     roofline["step_tflops"] = step_flops * K / (ms * 1e-3) * 1e-12
     roofline["step_frac_of_peak"] = roofline["step_tflops"] / peak if peak > 0 else None
     if c["mode"] != "pertime":

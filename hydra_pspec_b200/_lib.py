@@ -12,7 +12,7 @@ HP_RNG_INJECTED, HP_RNG_PHILOX = 0, 1
 HP_KEEP_CR, HP_KEEP_FG, HP_KEEP_CHISQ = 1, 2, 4
 (HP_BUF_PS, HP_BUF_LNPOST, HP_BUF_CR, HP_BUF_FG, HP_BUF_CHISQ, HP_BUF_LAST_CR, HP_BUF_LAST_FG,
  HP_BUF_PS_CUR) = range(8)
-HP_NUM_KERNEL_CLASSES = 5
+HP_NUM_KERNEL_CLASSES = 6
 
 
 class HPConfig(C.Structure):
@@ -59,6 +59,7 @@ _SIGNATURES = {
     "hp_engine_set_chain_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hp_engine_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "hp_engine_launch_count": (C.c_longlong, [C.c_void_p]),
+    "hp_engine_pt_form": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hp_kernel_class_name": (C.c_char_p, [C.c_int]),
     "hp_sample_S": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hp_fourier_operator": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),

@@ -231,7 +231,7 @@ struct Basis {
     double* Rt = nullptr;    // [C][ntiles][nblk][2][32][16]  right-hand sides in k_solve2's tile layout (k_rhs_tile)
 };
 
-enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4 };
+enum { CLS_CHOL = 0, CLS_SOLVE = 1, CLS_TRANSFORM = 2, CLS_POST = 3, CLS_SAMPLE = 4, CLS_LOWRANK = 5 };
 
 }  // namespace
 
@@ -408,7 +408,7 @@ void hp_release_cached_memory(void) {
     cudaSetDevice(cur);
 }
 const char* hp_kernel_class_name(int cls) {
-    static const char* names[HP_NUM_KERNEL_CLASSES] = {"chol", "solve", "transform", "post", "sample"};
+    static const char* names[HP_NUM_KERNEL_CLASSES] = {"chol", "solve", "transform", "post", "sample", "lowrank"};
     return (cls >= 0 && cls < HP_NUM_KERNEL_CLASSES) ? names[cls] : "?";
 }
 
@@ -1051,12 +1051,16 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         hp::launch_solve3(sa, sb.st);
         if (pt_low) {
             // per-time flags: rows Tp0 + x of X now hold R = M_0^-1 A.  P = A^H R, then the rank-k_t correction of every time
+            e->prof_end(CLS_SOLVE, nl, sb.st);
+            nl = 0;
+            e->prof_begin(CLS_LOWRANK, sb.st);
             hp::ZgemmArgs pz{};
             pz.A = OFFS(b.Rfix, 2 * Tp * Np) + 2 * (size_t)e->Tp0 * Np; pz.sAi = e->Np; pz.sAk = 1; pz.bsA = (long long)e->Tp * e->Np;
             pz.conjA = 1; pz.dk = OFFS(e->lam, Np); pz.bsD = e->Np;
             pz.B = sa.X + 2 * (size_t)e->Tp0 * Np; pz.sBk = 1; pz.sBj = e->Np; pz.bsB = (long long)e->Tp * e->Np;
             pz.C = OFFS(e->Pm, 2 * n * n); pz.sCi = e->n; pz.sCj = 1; pz.bsC = (long long)e->n * e->n;
             pz.M = e->n; pz.N = e->n; pz.K = e->N; pz.alpha = 1.0; pz.batch = sb.nc;
+            pz.lower_out = 1;   // k_pt_lowrank reads the lower triangle of P only
             hp::launch_zgemm(pz, sb.st);
             hp::PtLowArgs la{};
             la.Rfix = OFFS(b.Rfix, 2 * Tp * Np); la.wa = wa_sb; la.lam = OFFS(e->lam, Np); la.X = sa.X; la.Pm = OFFS(e->Pm, 2 * n * n);
@@ -1068,7 +1072,8 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
             la.chain_ids = OFFS(e->chain_ids, 1); la.chain0 = sb.c0;
             hp::launch_pt_lowrank(la, sb.st);
             hp::launch_colsumsq(sa.X, OFFS(e->Ppart, (size_t)e->pp_tiles * n), e->T, e->Tp, e->n, sb.nc, sb.st, e->Np);
-            nl += 3;
+            e->prof_end(CLS_LOWRANK, 3, sb.st);
+            e->prof_begin(CLS_SOLVE, sb.st);   // (empty for per-time flags: no reference-CG mode, fused inverse transform)
         }
         if (e->cfg.cg_compat) {
             hp::launch_cg_scale(sa.X, OFFS(b.Rfix, 2 * Tp * Np), wa_sb, OFFS(e->lam, Np), e->n, e->N, e->Np, e->T, e->Tp, sb.nc, sb.st);
@@ -1445,6 +1450,12 @@ int hp_engine_rewind(hp_engine* e) {
     return HP_OK;
 }
 long long hp_engine_launch_count(const hp_engine* e) { return e ? e->launches : -1; }
+int hp_engine_pt_form(const hp_engine* e, int* low_rank, int* max_rank) {
+    if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (low_rank) *low_rank = (e->cfg.time_flags && e->pt_low) ? 1 : 0;
+    if (max_rank) *max_rank = e->pt_kcap;
+    return HP_OK;
+}
 
 int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* dst, size_t dst_bytes) {
     if (!e || !dst) return fail(HP_ERR_ARG, "null argument");

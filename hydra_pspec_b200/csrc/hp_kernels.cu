@@ -50,8 +50,11 @@ __global__ void __launch_bounds__(256, 2) k_zgemm(ZgemmArgs a) {
     double* C = a.C + 2 * a.bsC * b;
     const double* dk = a.dk ? a.dk + a.bsD * b : nullptr;
     const int i0 = blockIdx.y * ZG_BM, j0 = blockIdx.x * ZG_BN;
+    if (a.lower_out && j0 > i0 + ZG_BM - 1) return;   // Hermitian result: only tiles that touch the lower triangle
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = warp >> 2, wc = warp & 3;  // warp tile 32 x 16
+    // (3M accumulation was tried here: 48 accumulators + the register double buffer exceed the 128 registers of two CTAs per
+    //  SM, and the spills cost more than the saved DMMAs: configs[4] solve 14.0 -> 15.3 ms)
     double cr[4][2][2], ci[4][2][2];
     warp_zero<4, 2>(cr, ci);
     const bool a_kfast = a.sAk <= a.sAi;

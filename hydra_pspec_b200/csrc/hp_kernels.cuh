@@ -44,6 +44,7 @@ struct ZgemmArgs {
     double alpha;
     int batch;
     int tri;   // 0: dense B;  1: B[k][j] = 0 for k > j;  2: B[k][j] = 0 for k < j  (the zero K range of a column tile is skipped)
+    int lower_out;   // 1: only the 64 x 64 tiles of C that touch the lower triangle (j <= i) are computed (Hermitian result)
 };
 void launch_zgemm(const ZgemmArgs& a, cudaStream_t st);
 

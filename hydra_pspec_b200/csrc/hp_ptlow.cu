@@ -28,7 +28,7 @@
 namespace hp {
 namespace {
 
-constexpr int kPLMaxJ = 14;   // Np / 32 <= 14 (k_solve3 sizes)
+constexpr int kPLMaxJ = 14;   // Np / 32 <= 14 (k_solve3 sizes); the kernel is instantiated for 5, 9 and 14 rows per lane
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // a conj(b)
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) k_pt_arows(double* __restrict__ Rfix, con
     reinterpret_cast<double2*>(Rfix)[(size_t)Tp0 * Np + e] = make_double2(s * b.x, -s * b.y);
 }
 
+template <int kNJ>
 __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -73,9 +74,9 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
         const double2* Rr = Xs + (size_t)a.Tp0 * Np;           // row x: R[:, x]
         const double2* Pm = reinterpret_cast<const double2*>(a.Pm) + (size_t)sys * n * n;
         // right-hand side of this time, lane owns rows lane + 32 i
-        double2 b[kPLMaxJ];
+        double2 b[kNJ];
 #pragma unroll
-        for (int i = 0; i < kPLMaxJ; ++i) {
+        for (int i = 0; i < kNJ; ++i) {
             const int j = lane + 32 * i;
             b[i] = make_double2(0.0, 0.0);
             if (i < nj && j < N) {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
             const double2* row1 = Rr + (size_t)fl[r + 1 < k ? r + 1 : r] * Np;
             double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int i = 0; i < kPLMaxJ; ++i) {
+            for (int i = 0; i < kNJ; ++i) {
                 const int j = lane + 32 * i;
                 if (i < nj && j < N) {
                     const double2 v0 = row0[j], v1 = row1[j];
@@ -175,14 +176,14 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
             __syncwarp();
         }
         // x_t += R_f z
-        double2 acc[kPLMaxJ];
+        double2 acc[kNJ];
 #pragma unroll
-        for (int i = 0; i < kPLMaxJ; ++i) acc[i] = make_double2(0.0, 0.0);
+        for (int i = 0; i < kNJ; ++i) acc[i] = make_double2(0.0, 0.0);
         for (int r = 0; r < k; ++r) {
             const double2* row = Rr + (size_t)fl[r] * Np;
             const double2 z = cv[r];
 #pragma unroll
-            for (int i = 0; i < kPLMaxJ; ++i) {
+            for (int i = 0; i < kNJ; ++i) {
                 const int j = lane + 32 * i;
                 if (i < nj && j < N) {
                     const double2 v = row[j];
@@ -192,12 +193,13 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
         }
         double2* xt = Xs + (size_t)t * Np;
 #pragma unroll
-        for (int i = 0; i < kPLMaxJ; ++i) {
+        for (int i = 0; i < kNJ; ++i) {
             const int j = lane + 32 * i;
             if (i < nj && j < N) { double2 v = xt[j]; v.x += acc[i].x; v.y += acc[i].y; xt[j] = v; }
         }
     }
 }
+
 
 }  // namespace
 
@@ -216,6 +218,10 @@ void launch_pt_lowrank(const PtLowArgs& a_in, cudaStream_t st) {
         cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev);
     }
     a.kcap = (a.kcap + 3) & ~3;
+    const long long nitems = (long long)a.nsys * a.T;
+    // (a 128-thread CTA per system with the rows R[:, x] parked in shared memory between the two products -- half the L2
+    //  traffic -- was 2.6x slower: the kernel is bound by the per-system dependency chain, not by L2 bandwidth;
+    //  profiles/r2_summary.md)
     // warps per CTA: as many as keep >= 2 CTAs (<= 100 KB each) on an SM, at most 8
     int warps = 8;
     while (warps > 1 && pt_lowrank_smem_bytes(a.kcap, warps) > 100 * 1024) warps >>= 1;
@@ -223,14 +229,23 @@ void launch_pt_lowrank(const PtLowArgs& a_in, cudaStream_t st) {
     static size_t attr_dev[kMaxDev] = {0};
     size_t& attr_smem = attr_dev[current_device_slot()];
     if (smem > attr_smem) {
-        cudaFuncSetAttribute(k_pt_lowrank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pt_lowrank<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pt_lowrank<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pt_lowrank<kPLMaxJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_smem = smem;
     }
-    const long long nitems = (long long)a.nsys * a.T;
+    const int nj = (a.N + 31) / 32;   // rows of the system per lane
+    int per_sm = 0;
+    if (nj <= 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_lowrank<5>, 32 * warps, smem);
+    else if (nj <= 9) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_lowrank<9>, 32 * warps, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_lowrank<kPLMaxJ>, 32 * warps, smem);
+    if (per_sm < 1) per_sm = 1;
     long long grid = (nitems + warps - 1) / warps;
-    const long long cap = (long long)num_sm * (smem > 48 * 1024 ? 2 : 4) * (8 / warps > 0 ? 8 / warps : 1);
+    const long long cap = (long long)num_sm * per_sm;   // persistent: every resident warp strides over the systems
     if (grid > cap) grid = cap;
-    k_pt_lowrank<<<(int)grid, 32 * warps, smem, st>>>(a);
+    if (nj <= 5) k_pt_lowrank<5><<<(int)grid, 32 * warps, smem, st>>>(a);
+    else if (nj <= 9) k_pt_lowrank<9><<<(int)grid, 32 * warps, smem, st>>>(a);
+    else k_pt_lowrank<kPLMaxJ><<<(int)grid, 32 * warps, smem, st>>>(a);
 }
 
 void launch_pt_arows(double* Rfix_sys, const double* Bmat_sys, const double* ni_sys, int n, int Np, int Tp0, cudaStream_t st) {

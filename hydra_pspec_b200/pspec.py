@@ -334,6 +334,14 @@ class GibbsEngine:
     def launch_count(self):
         return _lib.lib().hp_engine_launch_count(self._h)
 
+    def pt_form(self):
+        """Per-time flags: ("low-rank" | "direct", largest number of channels flagged at one time beyond the all-times
+        mask) for the chains loaded so far (csrc/hp_ptlow.cu / csrc/hp_pertime.cu)."""
+        import ctypes as C
+        low, kmax = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.lib().hp_engine_pt_form(self._h, C.byref(low), C.byref(kmax)))
+        return ("low-rank" if low.value else "direct"), kmax.value
+
     def set_chain_ids(self, ids):
         """Philox chain id of every chain (default: its index).  Passing the global baseline indices (and the same
         seed on every rank) makes the device draws independent of how baselines are sharded over GPUs."""

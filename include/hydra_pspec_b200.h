@@ -81,7 +81,7 @@ typedef struct hp_config {
 } hp_config;
 
 /* Number of kernel classes reported by hp_engine_kernel_ms and their names. */
-#define HP_NUM_KERNEL_CLASSES 5
+#define HP_NUM_KERNEL_CLASSES 6
 const char* hp_kernel_class_name(int cls);
 
 int hp_engine_create(const hp_config* cfg, hp_engine** out);
@@ -170,6 +170,12 @@ int hp_engine_set_chain_ids(hp_engine* e, const int* ids);
 int hp_engine_set_substreams(hp_engine* e, int n);
 /* Switch the per-kernel event timing on or off at run time. */
 int hp_engine_set_profile(hp_engine* e, int on);
+/* Per-time flags (cfg.time_flags): which form of the per-time solve the engine runs for the chains loaded so far.
+ *   *low_rank = 1: one shared factorisation per chain + a rank-k_t correction per time (csrc/hp_ptlow.cu); 0: one
+ *   factorisation per (chain, time) (csrc/hp_pertime.cu: a time has more than 64 channels flagged beyond the chain's
+ *   all-times mask, Nfreqs + Nmodes > 448, or HP_PT_DIRECT=1).  *max_rank = largest k_t of the loaded chains.
+ * Replaces nothing in the reference (it has no per-time flags, pspec.py:428); either pointer may be NULL. */
+int hp_engine_pt_form(const hp_engine* e, int* low_rank, int* max_rank);
 /* Total kernel launches issued by hp_engine_run / hp_engine_gcr so far. */
 long long hp_engine_launch_count(const hp_engine* e);
 
