@@ -489,7 +489,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     {
         const char* v1 = getenv("HP_POST_FFT_V1");   // experiments: keep the round-1 kernel
         e->fft2_ok = e->fft_ok && !(v1 && v1[0] == '1') && hp::make_fft2_plan(e->n, &e->plan2f, &e->plan2r) &&
-                     hp::postfft2_smem_bytes(e->n, e->m) <= (size_t)max_smem / 2;
+                     hp::postfft2_smem_bytes(e->n, e->m) <= (size_t)max_smem / (e->n >= 512 ? 1 : 2);   // one CTA per SM from 512 channels on
         if (e->fft2_ok) e->ktp = 8;   // k_post_fft2 handles eight times per CTA
     }
     e->ntilesE = hp::postfft_tiles(e->T, e->ktp > 0 ? e->ktp : 8);

@@ -14,7 +14,8 @@
 //   * computes F f on the tensor pipe (3M) and finishes the residual in the accumulator layout: the foreground model never
 //     goes to shared memory (one buffer instead of two: three CTAs per SM instead of two).
 //
-// Taken for Nfreqs = 128, 256, 384 (plans 4.4.4.2, 8.8.4, 6.4.4.4 as template parameters: all index arithmetic but the lane is
+// Taken for Nfreqs = 128, 256, 384, 512, 1024 (plans 4.4.4.2, 8.8.4, 6.4.4.4, 8.8.4.2, 8.8.4.4 as template parameters; from 512 on one
+// CTA per SM: 16 / 32 points per lane need the whole register file: all index arithmetic but the lane is
 // compile-time -- the run-time version spent half of its 6.6 k instructions per transform pair on it); everything else (and
 // the general-basis first iteration) stays on k_post_fft.
 #include "hp_kernels.cuh"
@@ -168,11 +169,13 @@ __device__ __forceinline__ void build_twiddle_tables(double2* dst, const double2
 
 }  // namespace
 
-// Nfreqs covered by k_post_fft2 (compile-time plans): 128 = 4.4.4.2, 256 = 8.8.4, 384 = 6.4.4.4.  The FftPlan outputs carry
+// Nfreqs covered by k_post_fft2 (compile-time plans): 128 = 4.4.4.2, 256 = 8.8.4, 384 = 6.4.4.4, 512 = 8.8.4.2, 1024 = 8.8.4.4.  The FftPlan outputs carry
 // the forward / reverse radices for reference; the kernel has them as template parameters.
 bool make_fft2_plan(int n, FftPlan* fwd, FftPlan* rev) {
     int rad[4], nf;
     if (n == 384) { rad[0] = 6; rad[1] = 4; rad[2] = 4; rad[3] = 4; nf = 4; }
+    else if (n == 1024) { rad[0] = 8; rad[1] = 8; rad[2] = 4; rad[3] = 4; nf = 4; }
+    else if (n == 512) { rad[0] = 8; rad[1] = 8; rad[2] = 4; rad[3] = 2; nf = 4; }
     else if (n == 256) { rad[0] = 8; rad[1] = 8; rad[2] = 4; rad[3] = 1; nf = 3; }
     else if (n == 128) { rad[0] = 4; rad[1] = 4; rad[2] = 4; rad[3] = 2; nf = 4; }
     else return false;
@@ -197,7 +200,7 @@ size_t postfft2_smem_bytes(int n, int m) {
 
 // E = Nfreqs / 32; forward radices P0 P1 P2 (P3); the second transform runs them in reverse order
 template <int E, int P0, int P1, int P2, int P3>
-__global__ void __launch_bounds__(32 * kTP2, HP_FFT2_CTAS) k_post_fft2(PostFftArgs a) {
+__global__ void __launch_bounds__(32 * kTP2, (E >= 16 ? 1 : HP_FFT2_CTAS)) k_post_fft2(PostFftArgs a) {
     constexpr int kThreads = 32 * kTP2;
     constexpr int n = 32 * E, ld = n + n / 8 + 1;
     constexpr int RL = P3 > 1 ? P3 : P2;      // last forward radix = first reverse radix
@@ -389,8 +392,8 @@ bool launch_post_fft2(const PostFftArgs& a, const FftPlan& fwd, const FftPlan& r
     (void)rev;
     const int n = fwd.n;
     const size_t smem = postfft2_smem_bytes(n, a.m);
-    static size_t attr_dev[kMaxDev][3] = {{0}};
-    const int slot = n == 128 ? 0 : (n == 256 ? 1 : 2);
+    static size_t attr_dev[kMaxDev][5] = {{0}};
+    const int slot = n == 128 ? 0 : (n == 256 ? 1 : (n == 384 ? 2 : (n == 512 ? 3 : 4)));
     size_t& attr = attr_dev[current_device_slot()][slot];
     const dim3 grid((a.T + kTP2 - 1) / kTP2, a.nsys);
     if (n == 128) {
@@ -402,6 +405,12 @@ bool launch_post_fft2(const PostFftArgs& a, const FftPlan& fwd, const FftPlan& r
     } else if (n == 384) {
         if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<12, 6, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
         k_post_fft2<12, 6, 4, 4, 4><<<grid, 32 * kTP2, smem, st>>>(a);
+    } else if (n == 512) {
+        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<16, 8, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+        k_post_fft2<16, 8, 8, 4, 2><<<grid, 32 * kTP2, smem, st>>>(a);
+    } else if (n == 1024) {
+        if (smem > attr) { cudaFuncSetAttribute(k_post_fft2<32, 8, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+        k_post_fft2<32, 8, 8, 4, 4><<<grid, 32 * kTP2, smem, st>>>(a);
     } else {
         return false;
     }

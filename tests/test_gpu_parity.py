@@ -344,10 +344,12 @@ def test_device_ring_read_window():
     eng.close()
 
 
-@pytest.mark.parametrize("nt,nf,nm,seed", [(20, 128, 8, 1), (12, 256, 16, 2), (9, 384, 32, 3), (17, 128, 0, 4), (8, 256, 6, 5)])
+@pytest.mark.parametrize("nt,nf,nm,seed", [(20, 128, 8, 1), (12, 256, 16, 2), (9, 384, 32, 3), (17, 128, 0, 4), (8, 256, 6, 5),
+                                           (11, 512, 20, 6), (10, 1024, 40, 7), (9, 1024, 64, 8)])
 def test_register_fft_shapes_match_oracle(nt, nf, nm, seed):
-    """Nfreqs = 128 / 256 / 384 take k_post_fft2 (register-resident FFTs, plans 4.4.4.2 / 8.8.4 / 6.4.4.4): partial time tiles,
-    Nmodes = 0 and Nmodes not a multiple of 4, flagged channels (second transform), three iterations."""
+    """Nfreqs = 128 / 256 / 384 / 512 / 1024 take k_post_fft2 (register-resident FFTs, plans 4.4.4.2 / 8.8.4 / 6.4.4.4 / 8.8.4.2 /
+    8.8.4.4): partial time tiles, Nmodes = 0, Nmodes not a multiple of 4 and beyond the 32 pre-fetched foreground k-steps,
+    flagged channels (second transform), three iterations."""
     from hydra_pspec_b200 import pspec
     rng = np.random.default_rng(500 + seed)
     F = np.linalg.qr(crandn(rng, nf, max(nm, 1)))[0][:, :nm]
