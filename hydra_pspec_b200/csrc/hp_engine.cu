@@ -972,12 +972,12 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     ca.Gp = OFFS(b.Gp, tri * hp::kBlkDoubles); ca.lam = OFFS(e->lam, Np); ca.Lp = OFFS(e->Lp, tri * hp::kLBlkDoubles);
     ca.Linvp = OFFS(e->Linvp, (size_t)e->nblk * hp::kLBlkDoubles); ca.info = e->info + sb.c0;
     ca.nblk = e->nblk; ca.n = e->n; ca.N = e->N; ca.nsys = sb.nc;
-    const int nchol = hp::launch_chol(ca, sb.st);
+    int nchol;
     {
         // Philox mode: the stored right-hand-side tiles are the unscaled Rfix, so pass 1 multiplies by W diag(lam)
         hp::TrinvExtra ex{OFFS(e->Wp1, tri * hp::kLBlkDoubles), OFFS(e->Wf1, hp::solve3_frag_doubles(e->nblk)),
                           OFFS(e->Wf2, hp::solve3_frag_doubles(e->nblk)), philox ? OFFS(e->lam, Np) : nullptr};
-        hp::launch_trinv(ca.Lp, ca.Linvp, OFFS(e->Wp, tri * hp::kLBlkDoubles), ex, e->nblk, sb.nc, sb.st);
+        nchol = hp::launch_chol_trinv(ca, OFFS(e->Wp, tri * hp::kLBlkDoubles), ex, sb.st) - 1;
     }
     e->prof_end(CLS_CHOL, nchol + 1, sb.st);
 

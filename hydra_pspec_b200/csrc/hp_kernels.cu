@@ -590,6 +590,234 @@ void launch_trinv(const double* Lp, const double* Linvp, double* Wp, const Trinv
     k_trinv<<<dim3(nblk, nsys), kCT, sizeof(TrinvSmem), st>>>(Lp, Linvp, Wp, ex, nblk);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_chol_w: the block-column Cholesky of k_chol_col with the inverse W = L^-1 built on the way, row by row:
+//      W_kk = V_kk,     W_kj' = -V_kk sum_{j = j'}^{k-1} L_kj W_jj'      (j' < k)
+// Row k of W needs row k of L (finished by the panel launches of the columns < k), the rows < k of W and V_kk, i.e.
+// exactly what the panel launch of column k waits for: its grid takes the nblk - k - 1 panel blocks (i, k) AND the k
+// blocks (k, j') of W.  The number of CTAs per launch is nblk - 1 for every column, so the late columns, whose panels
+// leave most SMs idle (one or two blocks per system), carry most of the inverse: the separate k_trinv launch (0.65 ms at
+// the headline shape) disappears into launches that were under-filled.
+// The diagonal block of the NEXT column rides along as well (look-ahead): block (k + 1, k + 1) needs row k + 1 of L up to
+// column k, and its last piece L_{k+1,k} is the first panel block of this launch -- the CTA that computes it goes on to
+// update, factor and invert block (k + 1, k + 1) while the other CTAs of the launch work through the rest of the column.
+// One launch per block column (plus one for block (0, 0)) instead of two: the 17 - 30 us of the latency-bound diagonal
+// kernels (128 CTAs with one 32 x 32 factorisation each) no longer sit between the launches.
+//   first = 1: grid (nsys, 1):        block (0, 0)
+//   first = 0: grid (nsys, nblk - 1): blockIdx.y = 0: panel block (k + 1, k), then diagonal block (k + 1, k + 1);
+//              0 < blockIdx.y < nblk - k - 1: panel block (k + 1 + blockIdx.y, k);  else W block (k, j')
+//              (systems along x: the look-ahead CTAs of all systems start in the first wave)
+__global__ void __launch_bounds__(kCT, 2) k_chol_w(CholArgs a, TrinvExtra ex, double* Wp_all, int k, int first) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CholColSmem& s = *reinterpret_cast<CholColSmem*>(smem_raw);
+    const int sys = blockIdx.x;
+    const int nblk = a.nblk, Np = nblk * 32;
+    const int npanel = nblk - k - 1;
+    const bool wrow = !first && (int)blockIdx.y >= npanel;
+    const int jp = wrow ? (int)blockIdx.y - npanel : 0;    // W block column
+    const double* Gp = a.Gp + (size_t)sys * tri_blocks(nblk) * kBlkDoubles;
+    double* Lp = a.Lp + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    double* Linvp = a.Linvp + (size_t)sys * nblk * kLBlkDoubles;
+    double* Wp = Wp_all + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles;
+    const double* lam = a.lam + (size_t)sys * Np;
+    double* Wp1 = (ex.Wp1 && ex.lam) ? ex.Wp1 + (size_t)sys * tri_blocks(nblk) * kLBlkDoubles : nullptr;
+    const size_t wf = (size_t)4 * nblk * (2 * nblk + 1) * 128;
+    double* Wf1 = ex.Wf1 ? ex.Wf1 + (size_t)sys * wf : nullptr;
+    double* Wf2 = ex.Wf2 ? ex.Wf2 + (size_t)sys * wf : nullptr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int ti = warp >> 2, tj = warp & 3;
+    double* Ar = s.A[0];
+    double* Ai = s.A[0] + kLPlane;
+    double* Vr = s.V;
+    double* Vi = s.V + kLPlane;
+
+    if (wrow) {
+        // ---- W block (k, jp):  -V_kk sum_{j = jp}^{k-1} L_kj W_j,jp
+        const double* lamj = ex.lam ? ex.lam + (size_t)sys * Np + 32 * jp : nullptr;
+        double P3m[3][1][1][2], cr[1][1][2], ci[1][1][2];
+        warp_zero3m<1, 1>(P3m);
+        load_block_async_ct(s.V, Linvp + (size_t)k * kLBlkDoubles);
+        load_block_async_ct(s.A[0], Lp + blk_index(k, jp) * kLBlkDoubles);
+        load_block_async_ct(s.B[0], Wp + blk_index(jp, jp) * kLBlkDoubles);
+        cp_async_commit();
+        for (int j = jp; j < k; ++j) {
+            const int st = (j - jp) & 1;
+            if (j + 1 < k) {
+                load_block_async_ct(s.A[st ^ 1], Lp + blk_index(k, j + 1) * kLBlkDoubles);
+                load_block_async_ct(s.B[st ^ 1], Wp + blk_index(j + 1, jp) * kLBlkDoubles);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            warp_zgemm3m<1, 1, false, false, false, false>(P3m, s.A[st] + 8 * ti * kLdBlk, s.A[st] + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                           s.B[st] + 8 * tj, s.B[st] + kLPlane + 8 * tj, kLdBlk, 32);
+            __syncthreads();
+        }
+        warp_zgemm3m_finish<1, 1, false, false>(P3m, cr, ci);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+            s.A[0][r * kLdBlk + c] = -cr[0][0][e];
+            s.A[0][kLPlane + r * kLdBlk + c] = -ci[0][0][e];
+        }
+        __syncthreads();
+        double dr[1][1][2], di[1][1][2], Q3m[3][1][1][2];
+        warp_zero3m<1, 1>(Q3m);
+        // V_kk is lower triangular: rows 8 ti.. only need k < 8 (ti + 1)
+        warp_zgemm3m<1, 1, false, false, false, false>(Q3m, s.V + 8 * ti * kLdBlk, s.V + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                       s.A[0] + 8 * tj, s.A[0] + kLPlane + 8 * tj, kLdBlk, 8 * (ti + 1));
+        warp_zgemm3m_finish<1, 1, false, false>(Q3m, dr, di);
+        double* Wb = Wp + blk_index(k, jp) * kLBlkDoubles;
+        const int r = 8 * ti + g, c = 8 * tj + 2 * q;
+        *reinterpret_cast<double2*>(Wb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
+        *reinterpret_cast<double2*>(Wb + kLPlane + r * kLdBlk + c) = make_double2(di[0][0][0], di[0][0][1]);
+        if (Wp1) {
+            double* Wb1 = Wp1 + blk_index(k, jp) * kLBlkDoubles;
+            const double l0 = lamj[c], l1 = lamj[c + 1];
+            *reinterpret_cast<double2*>(Wb1 + r * kLdBlk + c) = make_double2(l0 * dr[0][0][0], l1 * dr[0][0][1]);
+            *reinterpret_cast<double2*>(Wb1 + kLPlane + r * kLdBlk + c) = make_double2(l0 * di[0][0][0], l1 * di[0][0][1]);
+        }
+        if (Wf1 || Wf2) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int R = 32 * k + r, C = 32 * jp + c + e;
+                if (Wf1) {
+                    const double l = lamj ? lamj[c + e] : 1.0;
+                    store_frag1(Wf1, R, C, l * dr[0][0][e], l * di[0][0][e]);
+                }
+                if (Wf2) store_frag2(Wf2, nblk, R, C, dr[0][0][e], di[0][0][e]);
+            }
+        }
+        return;
+    }
+
+    // ---- Cholesky block (i, kc): the update, then the factorisation + inverse (diag) or L_i,kc = C V_kc^H; as k_chol_col
+    auto chol_block = [&](int i, int kc, bool diag) {
+        double cr[1][1][2], ci[1][1][2], P3m[3][1][1][2];
+        warp_zero<1, 1>(cr, ci);
+        warp_zero3m<1, 1>(P3m);
+        double mr_[2], mi_[2];
+        {
+            const double* Gb = Gp + blk_index(i, kc) * kBlkDoubles;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+                const int gi = 32 * i + r, gj = 32 * kc + c;
+                const double sc = lam[gi] * lam[gj];
+                mr_[e] = sc * Gb[r * 32 + c];
+                mi_[e] = sc * Gb[1024 + r * 32 + c];
+                if (gi == gj && (gi < a.n || gi >= a.N)) mr_[e] += 1.0;
+            }
+        }
+        if (!diag) load_block_async_ct(s.V, Linvp + (size_t)kc * kLBlkDoubles);
+        if (kc > 0) {
+            load_block_async_ct(s.A[0], Lp + blk_index(i, 0) * kLBlkDoubles);
+            if (!diag) load_block_async_ct(s.B[0], Lp + blk_index(kc, 0) * kLBlkDoubles);
+        }
+        cp_async_commit();
+        for (int j = 0; j < kc; ++j) {
+            const int st = j & 1;
+            if (j + 1 < kc) {
+                load_block_async_ct(s.A[st ^ 1], Lp + blk_index(i, j + 1) * kLBlkDoubles);
+                if (!diag) load_block_async_ct(s.B[st ^ 1], Lp + blk_index(kc, j + 1) * kLBlkDoubles);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const double* ar = s.A[st];
+            const double* br = diag ? s.A[st] : s.B[st];
+            warp_zgemm3m<1, 1, false, false, true, true>(P3m, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk, kLdBlk,
+                                                         br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk, kLdBlk, 32);
+            __syncthreads();
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        warp_zgemm3m_finish<1, 1, false, true>(P3m, cr, ci);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int r = 8 * ti + g, c = 8 * tj + 2 * q + e;
+            Ar[r * kLdBlk + c] = mr_[e] - cr[0][0][e];
+            Ai[r * kLdBlk + c] = mi_[e] - ci[0][0][e];
+        }
+        __syncthreads();
+        if (diag) {
+            const bool bad = diag_chol_inverse_block(Ar, Ai, Vr, Vi, tid, kCT);
+            __syncthreads();
+            double* Lb = Lp + blk_index(kc, kc) * kLBlkDoubles;
+            double* Vb = Linvp + (size_t)kc * kLBlkDoubles;
+            double* Wb = Wp + blk_index(kc, kc) * kLBlkDoubles;
+            const double* lamk = ex.lam ? ex.lam + (size_t)sys * Np + 32 * kc : nullptr;
+            for (int e = tid; e < kLBlkDoubles; e += kCT) {
+                const double v = s.V[e];
+                Lb[e] = s.A[0][e];
+                Vb[e] = v;
+                Wb[e] = v;                                   // W_kk = V_kk
+                if (Wp1) {
+                    const int c = (e % kLPlane) % kLdBlk;
+                    Wp1[blk_index(kc, kc) * kLBlkDoubles + e] = c < 32 ? v * lamk[c] : 0.0;
+                }
+            }
+            if (Wf1 || Wf2) {
+                // diagonal block (lower triangular; the zeros above the diagonal are part of the 16-row strips' k range)
+                for (int e = tid; e < 1024; e += kCT) {
+                    const int r = e >> 5, c = e & 31;
+                    const double re = Vr[r * kLdBlk + c], im = Vi[r * kLdBlk + c];
+                    if (Wf1 && c < 16 * ((r >> 4) + 1)) {
+                        const double l = lamk ? lamk[c] : 1.0;
+                        store_frag1(Wf1, 32 * kc + r, 32 * kc + c, l * re, l * im);
+                    }
+                    if (Wf2 && r >= 16 * (c >> 4)) store_frag2(Wf2, nblk, 32 * kc + r, 32 * kc + c, re, im);
+                }
+            }
+            if (bad && tid == 0 && a.info) atomicMax(a.info + sys, kc + 1);
+        } else {
+            double dr[1][1][2], di[1][1][2], Q3m[3][1][1][2];
+            warp_zero3m<1, 1>(Q3m);
+            warp_zgemm3m<1, 1, false, false, true, true>(Q3m, Ar + 8 * ti * kLdBlk, Ai + 8 * ti * kLdBlk, kLdBlk, Vr + 8 * tj * kLdBlk,
+                                                         Vi + 8 * tj * kLdBlk, kLdBlk, 32);
+            warp_zgemm3m_finish<1, 1, false, true>(Q3m, dr, di);
+            double* Lb = Lp + blk_index(i, kc) * kLBlkDoubles;
+            int r = 8 * ti + g, c = 8 * tj + 2 * q;
+            *reinterpret_cast<double2*>(Lb + r * kLdBlk + c) = make_double2(dr[0][0][0], dr[0][0][1]);
+            *reinterpret_cast<double2*>(Lb + kLPlane + r * kLdBlk + c) = make_double2(di[0][0][0], di[0][0][1]);
+        }
+    };
+    if (first) { chol_block(0, 0, true); return; }
+    chol_block(k + 1 + (int)blockIdx.y, k, false);
+    if (blockIdx.y == 0) {
+        // look-ahead: this CTA has just written L_{k+1,k}, the last block row k + 1 of L was waiting for
+        __syncthreads();   // its global stores are visible to the whole CTA (the cp.async reads below are the CTA's own)
+        chol_block(k + 1, k + 1, true);
+    }
+}
+
+// Cholesky + explicit inverse of the factor in one sequence of block-column launches (nblk + 1 of them)
+int launch_chol_trinv(const CholArgs& a, double* Wp, const TrinvExtra& ex, cudaStream_t st) {
+    static bool attr_dev[kMaxDev] = {false};
+    bool& attr_set = attr_dev[current_device_slot()];
+    static int fused = -1;   // HP_CHOL_FUSED=0: k_chol_col + k_trinv (A/B runs)
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_chol_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholColSmem));
+        const char* ev = getenv("HP_CHOL_FUSED");
+        fused = (ev && ev[0] == '0') ? 0 : 1;
+        attr_set = true;
+    }
+    if (!fused || a.nblk < 2) {
+        const int n = launch_chol(a, st);
+        launch_trinv(a.Lp, a.Linvp, Wp, ex, a.nblk, a.nsys, st);
+        return n + 1;
+    }
+    if (a.info) cudaMemsetAsync(a.info, 0, sizeof(int) * a.nsys, st);
+    k_chol_w<<<dim3(a.nsys, 1), kCT, sizeof(CholColSmem), st>>>(a, ex, Wp, 0, 1);
+    for (int k = 0; k < a.nblk; ++k) k_chol_w<<<dim3(a.nsys, a.nblk - 1), kCT, sizeof(CholColSmem), st>>>(a, ex, Wp, k, 0);
+    return a.nblk + 1;
+}
+
 // ==========================================================================================
 // k_post: one CTA per (time, system): model = s + F f, residual, chi^2, flagged copies.
 __global__ void __launch_bounds__(128) k_post(PostArgs a) {

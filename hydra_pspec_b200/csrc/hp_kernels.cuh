@@ -71,6 +71,9 @@ int launch_chol(const CholArgs& a, cudaStream_t st);   // returns the number of 
 //   (hp_solve3.cu: Wf1 = pass-1 operand, scaled by lam when ex.lam is given; Wf2 = W in pass-2 (transposed) fragment order)
 struct TrinvExtra { double* Wp1; double* Wf1; double* Wf2; const double* lam; };
 void launch_trinv(const double* Lp, const double* Linvp, double* Wp, const TrinvExtra& ex, int nblk, int nsys, cudaStream_t st);
+// Both in one sequence of block-column launches: the panel launch of column k also carries row k of W (k_chol_w).  Returns
+// the number of launches.  HP_CHOL_FUSED=0 falls back to launch_chol + launch_trinv.
+int launch_chol_trinv(const CholArgs& a, double* Wp, const TrinvExtra& ex, cudaStream_t st);
 
 struct SolveArgs {
     const double* Wp;      // [nsys][tri_blocks][2304]  W = L^-1 (k_trinv)

@@ -603,6 +603,7 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
     Extra keyword arguments: ``rng`` / ``solver`` (see the module docstring) and ``device``.
     ``nproc`` is accepted and ignored (all times are solved in one batched launch).
     """
+    t_start = time.perf_counter()
     if map_estimate:
         Niter = 1
         write_Niter = 1
@@ -653,8 +654,19 @@ def gibbs_sample_with_fg(vis, flags, S_initial, fgmodes, Ninv, ps_prior, Niter=1
         eng.close()
     write_time = write_time[0]
     if verbose:
+        # the reference's per-iteration table (pspec.py:602-604, 306-309, 453-458), printed after the run: the chain never
+        # leaves the device between iterations.  Time = wall time of the call / Niter; Info = 0 and |Ax - b| = "exact" for the
+        # direct solves (the reference prints its CG status and residual there)
+        per_it = (time.perf_counter() - t_start) / max(Niter, 1)
+        fl = flags if flags.ndim == 1 else None
+        print("Iter     Time [s]    Info    |Ax - b|    Chisq    ln Post")
+        print("-----    --------    ----    --------    -----    -------")
         for i, lp in enumerate(ln_post):
-            print(f"{i + 1:<9d}{lp:<12.1f}")
+            cm = float(chisq[i][:, fl].mean()) if fl is not None else float(chisq[i][flags].mean())
+            cs = f"{cm:<9.1e}" if cm > 10 else f"{cm:<9.3f}"
+            eff = solver or ("reference-cg" if (rng == "numpy" and flags.ndim == 1) else "exact")
+            res = "exact" if eff != "reference-cg" else "(cg)"
+            print(f"{i + 1:<9d}{per_it:<12.4f}{0.0:<8.1f}{res:<12s}{cs}{lp:<12.1f}")
         print()
     return signal_cr, signal_S, signal_ps, fg_amps, chisq, ln_post, write_time
 

@@ -367,3 +367,22 @@ def test_register_fft_shapes_match_oracle(nt, nf, nm, seed):
     got = pspec.gibbs_sample_with_fg(vis, flags, S0, F, Ninv, prior, Niter=3, seed=seed, verbose=False, solver="exact")
     for o, w, k in zip(got[:6], want, KEYS):
         assert rel(o, w) < TOL, k
+
+
+def test_verbose_prints_the_reference_table(capsys):
+    """pspec.py:602-604: header and one row per iteration (Iter, Time, Info, |Ax - b|, Chisq, ln Post)."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(3)
+    nt, nf, nm = 6, 32, 3
+    F = np.linalg.qr(crandn(rng, nf, nm))[0]
+    vis = crandn(rng, nt, nf) + (3 * crandn(rng, nt, nm)) @ F.T
+    flags = np.ones(nf, dtype=bool)
+    flags[4] = False
+    out = pspec.gibbs_sample_with_fg(vis, flags, np.eye(nf), F, np.eye(nf), np.zeros((2, nf)), Niter=3, seed=1, verbose=True)
+    text = capsys.readouterr().out.splitlines()
+    assert text[0].split() == "Iter Time [s] Info |Ax - b| Chisq ln Post".split()
+    rows = [ln.split() for ln in text[2:5]]
+    assert [r[0] for r in rows] == ["1", "2", "3"]
+    for r, lp, cs in zip(rows, out[5], out[4]):
+        assert abs(float(r[-1]) - lp) <= 0.05 + 1e-6 * abs(lp)
+        assert abs(float(r[-2]) - cs[:, flags].mean()) <= 1e-3 * max(1.0, cs[:, flags].mean())
