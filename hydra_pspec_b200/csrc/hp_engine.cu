@@ -466,7 +466,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
             e->ntiles = e->Tp / hp::kTT;
         }
         e->solve2 = resident && !e->solve3 && want >= 2 && hp::solve2_stages(e->nblk, (size_t)max_smem) >= 2;
-        if (e->solve3) hp::solve3_make_schedule(e->nblk, &e->sched3);
+        if (e->solve3) hp::solve3_make_schedule(e->nblk, &e->sched3, (e->N + 15) / 16);
     }
     if (cfg->time_flags && (cfg->general_basis0 || cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms)) {
         delete e;
@@ -1047,7 +1047,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
         sa.philox = philox ? 1 : 0;
         sa.key0 = (uint32_t)e->cfg.seed; sa.key1 = (uint32_t)(e->cfg.seed >> 32); sa.iter = draw_iter;
         sa.chain_ids = OFFS(e->chain_ids, 1); sa.chain0 = sb.c0;
-        sa.sched = e->sched3;
+        sa.sched = e->sched3; sa.nstrip = (e->N + 15) / 16;
         hp::launch_solve3(sa, sb.st);
         if (pt_low) {
             // per-time flags: rows Tp0 + x of X now hold R = M_0^-1 A.  P = A^H R, then the rank-k_t correction of every time

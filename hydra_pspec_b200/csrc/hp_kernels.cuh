@@ -140,12 +140,13 @@ struct Solve3Args {
     const int* chain_ids;
     int chain0;
     int grid_limit;
+    int nstrip;            // 16-row strips holding rows of the system, ceil(N / 16) (0: all 2 nblk); must match the schedule
     Solve3Sched sched;
 };
 void launch_solve3(const Solve3Args& a, cudaStream_t st);
 bool solve3_ok(int nblk, size_t max_smem);
 size_t solve3_frag_doubles(int nblk);               // doubles per system of Wf1 (and of Wf2)
-void solve3_make_schedule(int nblk, Solve3Sched* sc);
+void solve3_make_schedule(int nblk, Solve3Sched* sc, int nstrip = 0);
 
 struct PostArgs {
     const double* Sf;      // [nsys][>=T][n] complex: signal in frequency space (rows t < T are read)

@@ -103,11 +103,14 @@ bool solve3_ok(int nblk, size_t max_smem) { return nblk >= 1 && 2 * nblk <= kS3M
 
 // Longest-first schedule of the 2 nblk strips of each pass over the warps; the warps are then dealt to the four schedulers
 // so that each carries the same number of k-steps.
-void solve3_make_schedule(int nblk, Solve3Sched* sc) {
-    const int ns = 2 * nblk;
+void solve3_make_schedule(int nblk, Solve3Sched* sc, int nstrip) {
+    // nstrip: 16-row strips that hold rows of the system (ceil(N / 16)); a trailing strip of pure padding (N mod 32 in 1..16)
+    // is left out of both passes and of the k-range of pass 2 (272 rows in a 288-row layout: 10.5 % of the k-steps)
+    const int ns = (nstrip > 0 && nstrip < 2 * nblk) ? nstrip : 2 * nblk;
     for (int pass = 0; pass < 2; ++pass) {
+        for (int w = 0; w < kW3; ++w) sc->n[pass][w] = 0;
         std::vector<int> len(ns), order(ns);
-        for (int s = 0; s < ns; ++s) { len[s] = pass == 0 ? 4 * (s + 1) : 8 * nblk - 4 * s; order[s] = s; }
+        for (int s = 0; s < ns; ++s) { len[s] = pass == 0 ? 4 * (s + 1) : 4 * ns - 4 * s; order[s] = s; }
         std::sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
         std::vector<std::vector<int>> lists(kW3);
         std::vector<long long> load(kW3, 0);
@@ -142,6 +145,7 @@ template <bool kTimers>
 __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nblk = a.nblk, Np = nblk * 32;
+    const int nstrip = (a.nstrip > 0 && a.nstrip < 2 * nblk) ? a.nstrip : 2 * nblk;   // strips with rows of the system
     double* tileR = reinterpret_cast<double*>(smem_raw);                 // [nblk][2][32][16]  right-hand sides
     double* tileY = tileR + (size_t)nblk * kRowDoubles3;                 // [nblk][2][32][16]  y = W1 r + xi
     uint64_t* rhs_full = reinterpret_cast<uint64_t*>(tileY + (size_t)nblk * kRowDoubles3);
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
         } else {
             const int s = a.sched.strip[1][warp][pf_e - n1];
             pf_p = a.Wf2 + (size_t)sys * wf + (size_t)(8 * nblk * s - 2 * s * (s - 1)) * kFragDoubles + lane * 2;
-            pf_left = 8 * nblk - 4 * s;
+            pf_left = 4 * nstrip - 4 * s;
         }
     };
     auto pf_next = [&]() -> double4 {
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(kS3Threads, 1) k_solve3(Solve3Args a) {
         double* Pp = a.Ppart + ((size_t)sys * a.ntiles + tile) * a.n;
         for (int e = 0; e < n2; ++e) {
             const int s = a.sched.strip[1][warp][e];
-            const int k0 = 4 * s, nk = 8 * nblk - 4 * s;
+            const int k0 = 4 * s, nk = 4 * nstrip - 4 * s;
 #pragma unroll
             for (int p = 0; p < 3; ++p)
 #pragma unroll

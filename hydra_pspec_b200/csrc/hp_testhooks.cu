@@ -147,7 +147,8 @@ int hp_test_solve2(int n, int m, int T, int nsys, const double* G, const double*
         s3.Wf1 = dWf1; s3.Wf2 = dWf2; s3.Rt = dRt; s3.X = dX; s3.Ppart = dP;
         s3.nblk = nblk; s3.n = n; s3.N = N; s3.Tp = Tp; s3.ntiles = ntiles; s3.nsys = nsys; s3.T = T;
         s3.philox = 0; s3.grid_limit = grid_limit;
-        hp::solve3_make_schedule(nblk, &s3.sched);
+        s3.nstrip = (N + 15) / 16;
+        hp::solve3_make_schedule(nblk, &s3.sched, s3.nstrip);
         hp::launch_solve3(s3, 0);
     } else {
     hp::Solve2Args sa{};

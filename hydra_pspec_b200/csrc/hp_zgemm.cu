@@ -14,6 +14,9 @@
 //     matrix or the triangular K range), three stages of 64 x 32 (A) and 32 x 64 (B), one barrier per 32-deep k-tile;
 //   * interleaved (re, im) shared-memory tiles read as conflict-free LDS.128 fragments (leading dimensions 36 and 66
 //     complex elements); conjugation and the diagonal scale are applied to the fragments.
+// Tried and not kept: persistent CTAs (one per SM) with the cp.async pipeline running across output tiles -- the static
+// tile assignment loses more to the uneven k-ranges of a triangular B than the hidden pipeline fills gain (configs[4] solve
+// class 12.2 -> 12.5 ms, ln-posterior term 5.0 -> 5.2 ms even with a grid size coprime to the number of column tiles).
 #include "hp_kernels.cuh"
 #include "hp_mma.cuh"
 #include <cstdlib>
