@@ -46,16 +46,33 @@ __global__ void __launch_bounds__(256) k_pt_arows(double* __restrict__ Rfix, con
     reinterpret_cast<double2*>(Rfix)[(size_t)Tp0 * Np + e] = make_double2(s * b.x, -s * b.y);
 }
 
+// Shared memory: a CTA-wide table that maps a packed lower-triangle index e to (row, column) (the inverse of
+// tri(r) + c: lets a warp spread a triangle of entries over its lanes), then per warp the packed K_t, three k-vectors
+// (c / z, w, 1 / L_jj) and the channel list.
+#ifndef HP_PTLOW_MINB
+#define HP_PTLOW_MINB 2   // resident CTAs per SM the register budget is sized for
+#endif
 template <int kNJ>
-__global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
+__global__ void __launch_bounds__(256, HP_PTLOW_MINB) k_pt_lowrank(PtLowArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int kcap = a.kcap;
-    const size_t per_warp = (size_t)tri(kcap) * 16 + (size_t)kcap * 16 + (size_t)kcap * 4;
-    unsigned char* base = smem_raw + (size_t)warp * ((per_warp + 15) & ~size_t(15));
+    const int kcap = a.kcap, ntri = tri(kcap);
+    uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw);    // tab[tri(r) + c] = r << 8 | c
+    const size_t tab_bytes = ((size_t)ntri * 2 + 15) & ~size_t(15);
+    const size_t per_warp = ((size_t)ntri * 16 + (size_t)kcap * (16 + 16 + 8 + 4) + 15) & ~size_t(15);
+    unsigned char* base = smem_raw + tab_bytes + (size_t)warp * per_warp;
     double2* Kp = reinterpret_cast<double2*>(base);           // packed lower triangle, row i at tri(i)
-    double2* cv = Kp + tri(kcap);
-    int* fl = reinterpret_cast<int*>(cv + kcap);
+    double2* cv = Kp + ntri;                                  // (R^H b)_f, later z
+    double2* wv = cv + kcap;                                  // forward-substitution result w = L^-1 c (+ zeta)
+    double* dv = reinterpret_cast<double*>(wv + kcap);        // 1 / L_jj
+    int* fl = reinterpret_cast<int*>(dv + kcap);
+    for (int e = threadIdx.x; e < ntri; e += blockDim.x) {
+        int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (tri(r + 1) <= e) ++r;
+        while (tri(r) > e) --r;
+        tab[e] = (uint16_t)((r << 8) | (e - tri(r)));
+    }
+    __syncthreads();
     const int Np = a.Np, N = a.N, n = a.n;
     const long long nitems = (long long)a.nsys * a.T;
     const long long gw = (long long)blockIdx.x * nwarp + warp, gstride = (long long)gridDim.x * nwarp;
@@ -87,13 +104,12 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
             }
         }
         __syncwarp();
-        // K = I - P_ff (lower triangle)
-        for (int r = 0; r < k; ++r) {
-            const size_t prow = (size_t)fl[r] * n;
-            for (int c = lane; c <= r; c += 32) {
-                const double2 p = Pm[prow + fl[c]];
-                Kp[tri(r) + c] = make_double2((c == r ? 1.0 : 0.0) - p.x, c == r ? 0.0 : -p.y);
-            }
+        // K = I - P_ff (lower triangle): the k (k + 1) / 2 entries spread over the lanes, all loads independent
+        const int ktri = tri(k);
+        for (int e = lane; e < ktri; e += 32) {
+            const int rc = tab[e], r = rc >> 8, c = rc & 255;
+            const double2 p = Pm[(size_t)fl[r] * n + fl[c]];
+            Kp[e] = make_double2((c == r ? 1.0 : 0.0) - p.x, c == r ? 0.0 : -p.y);
         }
         // c = (R^H b)_f, two channels at a time
         for (int r = 0; r < k; r += 2) {
@@ -118,35 +134,34 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
             if (lane == 0) { cv[r] = s0; if (r + 1 < k) cv[r + 1] = s1; }
         }
         __syncwarp();
-        // Cholesky K = L L^H (right-looking, packed rows) with the forward substitution folded in
+        // Cholesky K = L L^H, right-looking, with the forward substitution w = L^-1 c folded in.  Column j is kept unscaled
+        // (L_ij = K_ij / sqrt(d_j), 1 / sqrt(d_j) in dv): nothing is written where the step reads, one warp barrier per column.
         bool bad = false;
         for (int j = 0; j < k; ++j) {
-            const double djj = Kp[tri(j) + j].x;
-            const double2 cj0 = cv[j];
+            const int tj = tri(j);
+            const double djj = Kp[tj + j].x;
             // the diagonal of K_t lies in (0, 1]: a pivot at round-off level means M_t is singular (e.g. a fully flagged time
             // with flat-prior foreground modes), which the direct factorisation reports through an exactly zero pivot
             if (!(djj > 1.5e-14)) bad = true;
-            const double inv = bad ? 1.0 : rsqrt(djj) ;
-            // one Newton step on the reciprocal square root: full double precision
-            const double invr = bad ? 1.0 : inv * (1.5 - 0.5 * djj * inv * inv);
-            const double2 cj = make_double2(cj0.x * invr, cj0.y * invr);
-            __syncwarp();
-            if (lane == 0) { Kp[tri(j) + j] = make_double2(djj * invr, 0.0); cv[j] = cj; }
+            double inv = bad ? 1.0 : rsqrt(djj);
+            inv = bad ? 1.0 : inv * (1.5 - 0.5 * djj * inv * inv);        // one Newton step: full double precision
+            const double rd = inv * inv;                                      // 1 / d_j
+            const double2 cj = cv[j];
+            const double2 wj = make_double2(cj.x * inv, cj.y * inv);         // w_j = c_j / L_jj
+            if (lane == 0) { wv[j] = wj; dv[j] = inv; }
+            // c_i -= L_ij w_j = K_ij w_j / sqrt(d_j)
             for (int i = j + 1 + lane; i < k; i += 32) {
-                double2 l = Kp[tri(i) + j];
-                l.x *= invr; l.y *= invr;
-                Kp[tri(i) + j] = l;
-                const double2 u = cmul(l, cj);
+                const double2 u = cmul(Kp[tri(i) + j], make_double2(wj.x * inv, wj.y * inv));
                 cv[i].x -= u.x; cv[i].y -= u.y;
             }
-            __syncwarp();
-            for (int i = j + 1 + lane; i < k; i += 32) {
-                const double2 lij = Kp[tri(i) + j];
-                double2* row = Kp + tri(i);
-                for (int l = j + 1; l <= i; ++l) {
-                    const double2 u = cmulc(lij, Kp[tri(l) + j]);
-                    row[l].x -= u.x; row[l].y -= u.y;
-                }
+            // trailing update K_il -= K_ij conj(K_lj) / d_j over the pairs j < l <= i < k
+            const int mrem = k - j - 1, npair = tri(mrem);
+            for (int e = lane; e < npair; e += 32) {
+                const int rc = tab[e], i = j + 1 + (rc >> 8), l = j + 1 + (rc & 255);
+                const double2 aij = Kp[tri(i) + j], alj = Kp[tri(l) + j];
+                const double2 u = cmulc(aij, alj);
+                double2* dst = Kp + tri(i) + l;
+                dst->x -= u.x * rd; dst->y -= u.y * rd;
             }
             __syncwarp();
         }
@@ -157,21 +172,21 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
                 u32x4 ctr; ctr.x = 0x80000000u + (uint32_t)e; ctr.y = (uint32_t)t; ctr.z = a.iter; ctr.w = chain;
                 double x0, x1;
                 normal_pair(philox4x32_10(ctr, a.key0, a.key1 ^ 0xA5A5A5A5u), x0, x1);
-                cv[e].x += x0 * 0.70710678118654752440; cv[e].y += x1 * 0.70710678118654752440;
+                wv[e].x += x0 * 0.70710678118654752440; wv[e].y += x1 * 0.70710678118654752440;
             }
             __syncwarp();
         }
-        // backward substitution L^H z = w
+        // backward substitution L^H z = w:  z_j = w_j / L_jj, then w_i -= conj(L_ji) z_j for i < j (row j of K, unscaled)
         for (int j = k - 1; j >= 0; --j) {
-            const double ljj = Kp[tri(j) + j].x;
-            const double2 wj = cv[j];
-            const double2 zj = make_double2(wj.x / ljj, wj.y / ljj);
-            __syncwarp();
+            const double2 wj = wv[j];
+            const double dj = dv[j];
+            const double2 zj = make_double2(wj.x * dj, wj.y * dj);
             if (lane == 0) cv[j] = zj;
             const double2* row = Kp + tri(j);
             for (int i = lane; i < j; i += 32) {
-                const double2 u = cmul(make_double2(row[i].x, -row[i].y), zj);
-                cv[i].x -= u.x; cv[i].y -= u.y;
+                const double di = dv[i];
+                const double2 u = cmul(make_double2(row[i].x * di, -row[i].y * di), zj);
+                wv[i].x -= u.x; wv[i].y -= u.y;
             }
             __syncwarp();
         }
@@ -200,12 +215,13 @@ __global__ void __launch_bounds__(256) k_pt_lowrank(PtLowArgs a) {
     }
 }
 
-
 }  // namespace
 
 size_t pt_lowrank_smem_bytes(int kcap, int warps) {
-    const size_t per_warp = ((size_t)kcap * (kcap + 1) / 2 * 16 + (size_t)kcap * 16 + (size_t)kcap * 4 + 15) & ~size_t(15);
-    return per_warp * warps;
+    const size_t ntri = (size_t)kcap * (kcap + 1) / 2;
+    const size_t tab = (ntri * 2 + 15) & ~size_t(15);
+    const size_t per_warp = (ntri * 16 + (size_t)kcap * (16 + 16 + 8 + 4) + 15) & ~size_t(15);
+    return tab + per_warp * warps;
 }
 
 void launch_pt_lowrank(const PtLowArgs& a_in, cudaStream_t st) {
