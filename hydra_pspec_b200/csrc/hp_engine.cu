@@ -468,10 +468,12 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         e->solve2 = resident && !e->solve3 && want >= 2 && hp::solve2_stages(e->nblk, (size_t)max_smem) >= 2;
         if (e->solve3) hp::solve3_make_schedule(e->nblk, &e->sched3, (e->N + 15) / 16);
     }
-    if (cfg->time_flags && (cfg->general_basis0 || cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms)) {
+    // a general (non-delay-diagonal) S_initial is possible in the low-rank form only: k_pt_cholsolve relies on the circulant
+    // signal block of the delay basis
+    if (cfg->time_flags && (cfg->dense_noise || cfg->cg_compat || cfg->force_dense_transforms || (cfg->general_basis0 && !e->pt_low))) {
         delete e;
-        return fail(HP_ERR_ARG, "per-time flags need a delay-diagonal S_initial, diagonal noise, the exact solver and an "
-                                "FFT-able Nfreqs");
+        return fail(HP_ERR_ARG, "per-time flags need diagonal noise, the exact solver and an FFT-able Nfreqs (and a delay-diagonal "
+                                "S_initial unless Nfreqs + Nmodes <= 448)");
     }
     if (cfg->time_flags && (hp::pt_smem_bytes(e->nblk, e->n) > (size_t)max_smem || !hp::make_fft_plan(e->n, &e->plan) ||
                             hp::postfft_ktp(e->n, e->m, (size_t)max_smem) == 0)) {
@@ -634,7 +636,7 @@ static int build_basis_products(hp_engine* e, Basis& b, int c) {
     if (b.Rt && e->cfg.rng_mode == HP_RNG_PHILOX)
         hp::launch_rhs_tile(b.Rt + 2 * (size_t)c * e->Tp * Np, b.Rfix + 2 * (size_t)c * e->Tp * Np, nullptr, nullptr, e->nblk, e->n, e->N,
                             e->ptFidx ? e->Tp : e->T, e->Tp, e->ntiles, 1, e->st);
-    if (e->cfg.time_flags) {
+    if (e->cfg.time_flags && &b == &e->bF) {
         // H_t = [Q|F]^H (w_t N^-1) [q_0 | F]  for every time: column 0 is the generator chat_t of the circulant
         // signal block, the rest are the foreground columns of G_t (hp_pertime.cu)
         const int m = e->m;
@@ -760,6 +762,9 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
             for (int v : e->pt_kmax) if (v > e->pt_kcap) e->pt_kcap = v;
             // a time with more extra flags than the low-rank kernel takes: the whole engine uses k_pt_cholsolve
             e->pt_low = e->pt_kcap <= hp::kPtLowMaxRank;
+            if (!e->pt_low && e->cfg.general_basis0)
+                return fail(HP_ERR_SIZE, "per-time flags with a general S_initial: a time has more than 64 channels flagged beyond the "
+                                         "all-times mask (only the low-rank form of the per-time solve takes a general first basis)");
         }
     }
     // (wv / wtv are pageable locals: cudaMemcpyAsync has staged them before it returns; `vis` may be page-locked and is

@@ -489,8 +489,8 @@ def _check_per_time_supported(solver, basis0, ninv_dense):
     mask -- as a low-rank correction of one shared factorisation (csrc/hp_ptlow.cu)."""
     if solver != "exact":
         raise NotImplementedError("per-time flags: only solver='exact' (the reference has no per-time CG to reproduce)")
-    if basis0 is not None:
-        raise NotImplementedError("per-time flags need a delay-diagonal S_initial")
+    # (a non-delay-diagonal S_initial is taken by the low-rank form only: the engine refuses it when Nfreqs + Nmodes > 448 or
+    #  when a time has more than 64 channels flagged beyond the all-times mask)
     if ninv_dense is not None:
         raise NotImplementedError("per-time flags need a diagonal Ninv")
 

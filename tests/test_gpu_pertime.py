@@ -141,8 +141,25 @@ def test_per_time_unsupported_combinations_raise():
     dense = Ninv + 0.01 * np.ones_like(Ninv)
     with pytest.raises(NotImplementedError):
         pspec.gibbs_sample_with_fg(vis, flags, S0, F, dense, prior, Niter=1, verbose=False)
-    with pytest.raises(NotImplementedError):
-        pspec.gibbs_sample_with_fg(vis, flags, S0 + 0.01 * np.diag(np.arange(32.0)), F, Ninv, prior, Niter=1, verbose=False)
+
+
+@pytest.mark.parametrize("nt,nf,nm,frac,seed", [(7, 32, 4, 0.1, 81), (9, 96, 8, 0.15, 82), (5, 128, 0, 0.2, 83)])
+def test_per_time_flags_with_general_S_initial(nt, nf, nm, frac, seed, monkeypatch):
+    """A non-delay-diagonal S_initial (first iteration in its eigenbasis) together with per-time flags: taken by the low-rank
+    form (any first basis; hp_ptlow.cu), refused by the direct form (k_pt_cholsolve relies on the circulant signal block)."""
+    from hydra_pspec_b200 import pspec, _lib
+    monkeypatch.delenv("HP_PT_DIRECT", raising=False)
+    vis, flags, S0, F, Ninv, prior = make_case(nt, nf, nm, frac, seed)
+    rng = np.random.default_rng(seed)
+    G = crandn(rng, nf, nf)
+    Sg = S0 + 0.3 * np.trace(S0).real / nf * (G @ G.conj().T) / nf          # Hermitian positive definite, not circulant
+    ref = ho.gibbs_sample_with_fg(vis, flags, Sg, F, Ninv, prior, Niter=3, seed=5, solver="direct")
+    out = pspec.gibbs_sample_with_fg(vis, flags, Sg, F, Ninv, prior, Niter=3, seed=5, verbose=False)
+    for o, r, k in zip(out[:6], ref, KEYS):
+        assert rel(o, r) < (1e-8 if k == "chisq" else 5e-10), k
+    monkeypatch.setenv("HP_PT_DIRECT", "1")
+    with pytest.raises(_lib.HydraLibError):
+        pspec.gibbs_sample_with_fg(vis, flags, Sg, F, Ninv, prior, Niter=1, seed=5, verbose=False)
 
 
 @pytest.mark.parametrize("nt,nf,nm,seed", [(2, 8, 1, 1), (3, 12, 2, 2), (5, 16, 0, 3)])
