@@ -642,20 +642,20 @@ __global__ void __launch_bounds__(kCT, 2) k_chol_w(CholArgs a, TrinvExtra ex, do
         load_block_async_ct(s.B[0], Wp + blk_index(jp, jp) * kLBlkDoubles);
         cp_async_commit();
         for (int j = jp; j < k; ++j) {
+            // one barrier per block step: it publishes stage st AND says that every warp is done with stage st ^ 1 (read by
+            // the previous step), which the loads issued right after it refill while this step multiplies
             const int st = (j - jp) & 1;
+            cp_async_wait<0>();
+            __syncthreads();
             if (j + 1 < k) {
                 load_block_async_ct(s.A[st ^ 1], Lp + blk_index(k, j + 1) * kLBlkDoubles);
                 load_block_async_ct(s.B[st ^ 1], Wp + blk_index(j + 1, jp) * kLBlkDoubles);
                 cp_async_commit();
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
             }
-            __syncthreads();
             warp_zgemm3m<1, 1, false, false, false, false>(P3m, s.A[st] + 8 * ti * kLdBlk, s.A[st] + kLPlane + 8 * ti * kLdBlk, kLdBlk,
                                                            s.B[st] + 8 * tj, s.B[st] + kLPlane + 8 * tj, kLdBlk, 32);
-            __syncthreads();
         }
+        __syncthreads();   // every warp is done with the operand stages: s.A[0] takes the accumulated sum
         warp_zgemm3m_finish<1, 1, false, false>(P3m, cr, ci);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -720,23 +720,20 @@ __global__ void __launch_bounds__(kCT, 2) k_chol_w(CholArgs a, TrinvExtra ex, do
         cp_async_commit();
         for (int j = 0; j < kc; ++j) {
             const int st = j & 1;
+            cp_async_wait<0>();
+            __syncthreads();   // stage st has landed; every warp is done with stage st ^ 1 (one barrier per block step)
             if (j + 1 < kc) {
                 load_block_async_ct(s.A[st ^ 1], Lp + blk_index(i, j + 1) * kLBlkDoubles);
                 if (!diag) load_block_async_ct(s.B[st ^ 1], Lp + blk_index(kc, j + 1) * kLBlkDoubles);
                 cp_async_commit();
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
             }
-            __syncthreads();
             const double* ar = s.A[st];
             const double* br = diag ? s.A[st] : s.B[st];
             warp_zgemm3m<1, 1, false, false, true, true>(P3m, ar + 8 * ti * kLdBlk, ar + kLPlane + 8 * ti * kLdBlk, kLdBlk,
                                                          br + 8 * tj * kLdBlk, br + kLPlane + 8 * tj * kLdBlk, kLdBlk, 32);
-            __syncthreads();
         }
         cp_async_wait<0>();
-        __syncthreads();
+        __syncthreads();   // V_kk landed (kc = 0: nothing else waited for it); every warp is done with the operand stages
         warp_zgemm3m_finish<1, 1, false, true>(P3m, cr, ci);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
