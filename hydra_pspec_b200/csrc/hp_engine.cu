@@ -262,6 +262,8 @@ struct hp_engine {
     uint16_t* ptFidx = nullptr;   // [C][T][kPtLowMaxRank]
     int* ptFcnt = nullptr;   // [C][T]
     std::vector<int> pt_kmax;     // per chain: largest extra-flag count
+    std::vector<uint8_t> hpt_built;   // per chain: the operands of k_pt_cholsolve (Hpt) are current
+    std::vector<uint8_t> pt_loaded;   // per chain: loaded with per-time flags
     int gd_slots = 1;
     std::vector<uint8_t> pending;         // chains whose G / Rfix products are still to be built (flush_pending)
     bool big_solve = false;               // N too large for k_solve's resident tile: dense k_zgemm products with W
@@ -560,6 +562,8 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     }
     e->flagged.assign(C, 0);
     e->pt_kmax.assign(C, 0);
+    e->hpt_built.assign(C, 0);
+    e->pt_loaded.assign(C, 0);
     e->pending.assign(C, 0);
     e->have_omega.assign(C, 0);
     {
@@ -586,6 +590,26 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
         return fail(HP_ERR_CUDA, "engine initialisation kernels failed");
     }
     *out = e;
+    return HP_OK;
+}
+
+// Per-time flags, one factorisation per time (hp_pertime.cu): H_t = [Q|F]^H (w_t N^-1) [q_0 | F] for every time of chain c --
+// column 0 is the generator chat_t of the circulant signal block, the rest are the foreground columns of G_t.  Built from what
+// load_chain left on the device (Bmat, wT, ninvd), so it can be deferred until the direct form is actually needed.
+static int build_hpt(hp_engine* e, int c) {
+    const int n = e->n, m = e->m, N = e->N, Np = e->Np, T = e->T;
+    const double* Bm = e->bF.Bmat + 2 * (size_t)c * n * Np;
+    k_rowscale<<<nblocks((long long)T * n), 256, 0, e->st>>>(e->niT, e->wT + (size_t)c * e->Tp * n, e->ninvd + (size_t)c * n, T, n);
+    k_select_cols<<<nblocks((long long)n * (1 + m)), 256, 0, e->st>>>(e->Bsel, Bm, n, m, Np);
+    hp::ZgemmArgs h{};
+    h.A = Bm; h.sAi = 1; h.sAk = Np; h.bsA = 0; h.conjA = 1;
+    h.B = e->Bsel; h.sBk = 1 + m; h.sBj = 1; h.bsB = 0;
+    h.C = e->Hpt + 2 * (size_t)c * e->Tp * (1 + m) * Np; h.sCi = 1; h.sCj = Np; h.bsC = (long long)(1 + m) * Np;
+    h.dk = e->niT; h.bsD = n;
+    h.M = N; h.N = 1 + m; h.K = n; h.accumulate = 0; h.alpha = 1.0; h.batch = T;
+    hp::launch_zgemm(h, e->st);
+    CU_TRY(cudaGetLastError());
+    e->hpt_built[c] = 1;
     return HP_OK;
 }
 
@@ -636,19 +660,10 @@ static int build_basis_products(hp_engine* e, Basis& b, int c) {
     if (b.Rt && e->cfg.rng_mode == HP_RNG_PHILOX)
         hp::launch_rhs_tile(b.Rt + 2 * (size_t)c * e->Tp * Np, b.Rfix + 2 * (size_t)c * e->Tp * Np, nullptr, nullptr, e->nblk, e->n, e->N,
                             e->ptFidx ? e->Tp : e->T, e->Tp, e->ntiles, 1, e->st);
+    // the operands of k_pt_cholsolve are built only when the engine runs (or falls back to) one factorisation per time
     if (e->cfg.time_flags && &b == &e->bF) {
-        // H_t = [Q|F]^H (w_t N^-1) [q_0 | F]  for every time: column 0 is the generator chat_t of the circulant
-        // signal block, the rest are the foreground columns of G_t (hp_pertime.cu)
-        const int m = e->m;
-        k_rowscale<<<nblocks((long long)T * n), 256, 0, e->st>>>(e->niT, e->wT + (size_t)c * e->Tp * n, e->ninvd + (size_t)c * n, T, n);
-        k_select_cols<<<nblocks((long long)n * (1 + m)), 256, 0, e->st>>>(e->Bsel, Bm, n, m, Np);
-        hp::ZgemmArgs h{};
-        h.A = Bm; h.sAi = 1; h.sAk = Np; h.bsA = 0; h.conjA = 1;
-        h.B = e->Bsel; h.sBk = 1 + m; h.sBj = 1; h.bsB = 0;
-        h.C = e->Hpt + 2 * (size_t)c * e->Tp * (1 + m) * Np; h.sCi = 1; h.sCj = Np; h.bsC = (long long)(1 + m) * Np;
-        h.dk = e->niT; h.bsD = n;
-        h.M = N; h.N = 1 + m; h.K = n; h.accumulate = 0; h.alpha = 1.0; h.batch = T;
-        hp::launch_zgemm(h, e->st);
+        e->hpt_built[c] = 0;
+        if (!e->pt_low) { const int rc = build_hpt(e, c); if (rc != HP_OK) return rc; }
     }
     CU_TRY(cudaGetLastError());
     return HP_OK;
@@ -688,6 +703,9 @@ static int build_basis_products_batch(hp_engine* e, Basis& b, int c0, int nc) {
 
 static int flush_pending(hp_engine* e) {
     const int C = e->C;
+    if (e->cfg.time_flags && !e->pt_low)   // fell back to one factorisation per time after some chains were loaded
+        for (int c = 0; c < C; ++c)
+            if (e->pt_loaded[c] && !e->hpt_built[c]) { const int rc = build_hpt(e, c); if (rc != HP_OK) return rc; }
     for (int c = 0; c < C;) {
         if (!e->pending[c]) { ++c; continue; }
         int c1 = c;
@@ -724,6 +742,7 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
         for (int t = 0; t < T; ++t)
             for (int x = 0; x < n; ++x) if (flags[(size_t)t * n + x]) wv[x] = 1.0;
         anyf = true;  // the masked-signal term of ln_post is always evaluated with the per-time mask
+        e->pt_loaded[c] = 1;
     } else {
         for (int x = 0; x < n; ++x) { wv[x] = flags[x] ? 1.0 : 0.0; anyf |= !flags[x]; }
     }

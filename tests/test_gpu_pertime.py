@@ -243,3 +243,18 @@ def test_per_time_forms_agree_at_config2_shape():
     for a, b in zip(low, direct):
         for x, y, k in zip(a[:6], b[:6], KEYS):
             assert rel(x, y) < (1e-8 if k == "chisq" else TOL), k
+
+
+def test_per_time_fallback_after_low_rank_chains_were_loaded():
+    """Two chains in one engine: the first stays within the rank limit (its direct-form operands are not built at load time),
+    the second has times with more than 64 extra flags, which switches the whole engine to one factorisation per time: the
+    operands of the first chain are then built lazily.  Both against the oracle."""
+    from hydra_pspec_b200 import pspec
+    a = make_case(5, 256, 8, 0.05, 91)
+    b = make_case(5, 256, 8, 0.45, 92)
+    bls = [dict(vis=c[0], flags=c[1], S_initial=c[2], fgmodes=c[3], Ninv=c[4], ps_prior=c[5]) for c in (a, b)]
+    outs = pspec.gibbs_sample_batch(bls, Niter=2, seed=13, rng="numpy", solver="exact")
+    for c, out in zip((a, b), outs):
+        ref = ho.gibbs_sample_with_fg(c[0], c[1], c[2], c[3], c[4], c[5], Niter=2, seed=13, solver="direct")
+        for o, r, k in zip(out[:6], ref, KEYS):
+            assert rel(o, r) < (1e-8 if k == "chisq" else TOL), k
