@@ -632,7 +632,9 @@ def run_b200(args):
             done = 0
             while done < Ke:
                 n_ = min(chunk, Ke - done)
-                e.run_to_host(n_, stage[keep], first_iter=done, iter_major=True)   # compute overlapped with the device-to-host copies
+                # compute overlapped with the device-to-host copies; read-ahead: the next chunk's first iterations are computed
+                # under this chunk's last copies (hp_host_sink.read_ahead)
+                e.run_to_host(n_, stage[keep], first_iter=done, iter_major=True, read_ahead=(2 if done + n_ < Ke else 0))
                 done += n_
             e.close()
 

@@ -28,7 +28,7 @@ class HPConfig(C.Structure):
 class HPHostSink(C.Structure):
     _fields_ = [("signal_ps", C.c_void_p), ("ln_post", C.c_void_p), ("signal_cr", C.c_void_p),
                 ("fg_amps", C.c_void_p), ("chisq", C.c_void_p), ("iters", C.c_int), ("first_iter", C.c_int),
-                ("iter_major", C.c_int)]
+                ("iter_major", C.c_int), ("read_ahead", C.c_int)]
 
 
 class HydraLibError(RuntimeError):

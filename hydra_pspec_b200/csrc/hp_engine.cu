@@ -299,6 +299,8 @@ struct hp_engine {
     std::vector<cudaEvent_t> sub_done;    // run_to_host: sub-batch i has finished the iteration being copied
     int iter = 0;     // Gibbs iterations since the chains were loaded (RNG counter, basis choice)
     int out_pos = 0;  // cursor in the per-iteration output buffers
+    int ahead = 0;    // iterations computed beyond out_pos by hp_engine_run_to_host (sink.read_ahead), not yet delivered
+    std::vector<cudaEvent_t> it_done;   // run_to_host: [ring slot][sub-batch] the iteration in that slot has been computed
     uint32_t draw_counter = 0;  // Philox counter of the GCR fluctuation draws (advances per GCR step)
     const double* last_sf = nullptr;  // where the last GCR solve's frequency-space signal lives
     long long last_sf_bs = 0;         // its batch stride (complex elements)
@@ -393,6 +395,9 @@ void want_basis(hp_engine* e, ArenaPlan& ap, Basis& b) {
 }
 }  // namespace
 
+static const char* kAheadMsg = "read-ahead iterations are pending (hp_host_sink.read_ahead): deliver them with hp_engine_run_to_host or "
+                               "drop them with hp_engine_rewind first";
+
 extern "C" {
 
 const char* hp_last_error(void) { return g_err.c_str(); }
@@ -425,6 +430,7 @@ int hp_engine_destroy(hp_engine* e) {
     if (e->fork_ev) cudaEventDestroy(e->fork_ev);
     for (auto x : e->join_ev) cudaEventDestroy(x);
     for (auto x : e->copy_done) cudaEventDestroy(x);
+    for (auto x : e->it_done) cudaEventDestroy(x);
     for (auto x : e->sub_done) cudaEventDestroy(x);
     if (e->own_stream) cudaStreamDestroy(e->st);
     delete e;
@@ -727,6 +733,7 @@ static int load_chain_impl(hp_engine* e, int c, const double* vis, const uint8_t
     if ((e->cfg.dense_noise != 0) != (ninv_dense != nullptr))
         return fail(HP_ERR_ARG, "hp_engine_load_chain: dense noise needs cfg.dense_noise and hp_engine_load_chain_dense");
     if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "hp_engine_load_chain: chain index out of range");
+    if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
     if (e->cfg.general_basis0 && !basis0) return fail(HP_ERR_ARG, "hp_engine_load_chain: general_basis0 set but basis0 is NULL");
     CU_TRY(cudaSetDevice(e->cfg.device));
     const int n = e->n, m = e->m, N = e->N, Np = e->Np, T = e->T, Tp = e->Tp;
@@ -853,6 +860,7 @@ int hp_engine_set_draws(hp_engine* e, int c, const double* omega_a, const double
                         int n_draw_iters) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
     if (e->cfg.rng_mode != HP_RNG_INJECTED) return fail(HP_ERR_ARG, "hp_engine_set_draws: engine is not in injected-draw mode");
+    if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
     if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "chain index out of range");
     if ((omega_a == nullptr) != (omega_b == nullptr)) return fail(HP_ERR_ARG, "omega_a and omega_b must both be given or both NULL");
     if (n_draw_iters > e->cfg.max_iters) return fail(HP_ERR_ARG, "more draw iterations than max_iters");
@@ -1261,6 +1269,7 @@ static void join_subs(hp_engine* e, const std::vector<Sub>& subs) {
 
 int hp_engine_gcr(hp_engine* e) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
     CU_TRY(cudaSetDevice(e->cfg.device));
     { int rcf = flush_pending(e); if (rcf != HP_OK) return rcf; }
     Basis& b = (e->cfg.general_basis0 && e->iter == 0) ? e->b0 : e->bF;
@@ -1335,6 +1344,7 @@ static void enqueue_iterations(hp_engine* e, int niter, F&& after_iter) {
 
 int hp_engine_run(hp_engine* e, int niter) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
     if (niter < 0 || e->out_pos + niter > e->cfg.max_iters)
         return fail(HP_ERR_ARG, "hp_engine_run: would exceed max_iters (use hp_engine_rewind)");
     CU_TRY(cudaSetDevice(e->cfg.device));
@@ -1359,16 +1369,19 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
     const bool big = sink->signal_cr || (sink->fg_amps && m) || sink->chisq;
     const bool philox = e->cfg.rng_mode == HP_RNG_PHILOX;
     auto subs = make_subs(e);
+    const size_t nsub = subs.size();
+    if (e->ahead > 0 && (!big || e->it_done.size() < R * nsub))
+        return fail(HP_ERR_ARG, "hp_engine_run_to_host: read-ahead iterations are pending; deliver them with the same kind of sink");
     if (big) {
         while (e->copy_done.size() < R) {
             cudaEvent_t ev;
             CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             e->copy_done.push_back(ev);
         }
-        while (e->sub_done.size() < subs.size()) {
+        while (e->it_done.size() < R * nsub) {
             cudaEvent_t ev;
             CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            e->sub_done.push_back(ev);
+            e->it_done.push_back(ev);
         }
     }
     // Sub-batches never join between iterations: each records an event after its part of an iteration, the copy stream
@@ -1376,21 +1389,26 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
     // sub-batch only waits (for the copies out of the slot it is about to overwrite) when it is R iterations ahead.
     fork_subs(e, subs);
     cudaError_t cerr = cudaSuccess;
-    for (int k = 0; k < niter && cerr == cudaSuccess; ++k) {
-        const size_t it = (size_t)e->out_pos, slot = it % R, hs = it - (size_t)sink->first_iter;
+    // compute iteration `it` (the next one of the chain) into its ring slot; records it_done[slot][*]
+    auto compute_next = [&](size_t it) {
+        const size_t slot = it % R;
         const bool general = e->cfg.general_basis0 && e->iter == 0;
         const uint32_t draw_iter = (philox && !e->cfg.refresh_omega) ? 0u : e->draw_counter++;
-        for (auto& sb : subs) {
-            if (big && it >= R + (size_t)first) cudaStreamWaitEvent(sb.st, e->copy_done[slot], 0);
-            enqueue_iteration_sub(e, sb, (int)it, (uint32_t)e->iter, draw_iter, general);
+        for (size_t i = 0; i < nsub; ++i) {
+            // the slot was last used by iteration it - R: wait for its copies unless they completed in an earlier call
+            if (big && it >= R + (size_t)first) cudaStreamWaitEvent(subs[i].st, e->copy_done[slot], 0);
+            enqueue_iteration_sub(e, subs[i], (int)it, (uint32_t)e->iter, draw_iter, general);
+            if (big) cudaEventRecord(e->it_done[slot * nsub + i], subs[i].st);
         }
         e->iter++;
+    };
+    for (int k = 0; k < niter && cerr == cudaSuccess; ++k) {
+        const size_t it = (size_t)e->out_pos, slot = it % R, hs = it - (size_t)sink->first_iter;
+        if (e->ahead > 0) --e->ahead;          // computed at the end of the previous call (read-ahead): only the copies are left
+        else compute_next(it);
         e->out_pos++;
         if (!big) continue;
-        for (size_t i = 0; i < subs.size(); ++i) {
-            cudaEventRecord(e->sub_done[i], subs[i].st);
-            cudaStreamWaitEvent(e->copy_st, e->sub_done[i], 0);
-        }
+        for (size_t i = 0; i < nsub; ++i) cudaStreamWaitEvent(e->copy_st, e->it_done[slot * nsub + i], 0);
         // The ring is [slot][chain][...]: an iteration's array of all chains is one contiguous block.  iter_major sinks
         // ([iters][nchains][...]) take it with one plain copy per array; chain-major sinks ([nchains][iters][...]) with one
         // strided copy per array (rows = chains).
@@ -1416,6 +1434,16 @@ int hp_engine_run_to_host(hp_engine* e, int niter, const hp_host_sink* sink) {
                                      e->copy_st);
         }
         cudaEventRecord(e->copy_done[slot], e->copy_st);
+    }
+    // Read-ahead: a call starts with one compute step during which the copy engine has nothing to do (a chunked chain pays it
+    // once per chunk: 8 of 57 ms per two-iteration chunk at the headline shape).  With sink.read_ahead the next iterations of
+    // the chain are computed into free ring slots now, under this call's last copies; the next call only copies them.
+    if (big && cerr == cudaSuccess && sink->read_ahead > 0) {
+        int want = sink->read_ahead < (int)R - 1 ? sink->read_ahead : (int)R - 1;
+        while (e->ahead < want && e->out_pos + e->ahead < e->cfg.max_iters) {
+            compute_next((size_t)(e->out_pos + e->ahead));
+            ++e->ahead;
+        }
     }
     join_subs(e, subs);
     if (cerr != cudaSuccess) return fail(HP_ERR_CUDA, std::string("hp_engine_run_to_host: ") + cudaGetErrorString(cerr));
@@ -1450,6 +1478,7 @@ int hp_engine_set_chain_ids(hp_engine* e, const int* ids) {
 
 int hp_engine_set_substreams(hp_engine* e, int n) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
+    if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
     e->active_subs = n < 1 ? 1 : n;
     return HP_OK;
 }
@@ -1471,6 +1500,7 @@ int hp_engine_iterations_done(const hp_engine* e) { return e ? e->iter : -1; }
 int hp_engine_rewind(hp_engine* e) {
     if (!e) return fail(HP_ERR_ARG, "null engine");
     e->out_pos = 0;
+    e->ahead = 0;     // read-ahead iterations stay part of the chain's history (the spectrum state is kept), undelivered
     return HP_OK;
 }
 long long hp_engine_launch_count(const hp_engine* e) { return e ? e->launches : -1; }
@@ -1504,7 +1534,7 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
             const size_t per = buffer == HP_BUF_CR ? 2 * T * n : (buffer == HP_BUF_FG ? 2 * T * m : T * n);   // doubles per iteration
             bytes = (size_t)niter * per * 8;
             if (dst_bytes < bytes) return fail(HP_ERR_ARG, "destination too small");
-            if (niter > 0 && (size_t)iter0 + R < (size_t)e->out_pos)
+            if (niter > 0 && (size_t)iter0 + R < (size_t)(e->out_pos + e->ahead))
                 return fail(HP_ERR_ARG, "iteration no longer in the device ring (cfg.ring_iters): stream it with hp_engine_run_to_host");
             for (int k = 0; k < niter; ++k) {
                 const size_t slot = (size_t)(iter0 + k) % R;
@@ -1513,6 +1543,7 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
             return HP_OK;
         }
         case HP_BUF_LAST_CR:
+            if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
             if (!e->last_sf) return fail(HP_ERR_ARG, "no GCR solve has run yet");
             src = e->last_sf + 2 * (size_t)c * e->last_sf_bs; bytes = T * n * 16; break;
         case HP_BUF_PS_CUR: src = e->ps + (size_t)c * n; bytes = n * 8; break;
@@ -1533,6 +1564,7 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
 int hp_engine_read_signal_S(hp_engine* e, int c, double* dst) {
     if (!e || !dst) return fail(HP_ERR_ARG, "null argument");
     if (c < 0 || c >= e->C) return fail(HP_ERR_ARG, "chain index out of range");
+    if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);   // the spectrum state is ahead of the delivered iterations
     CU_TRY(cudaSetDevice(e->cfg.device));
     const int n = e->n;
     // S = Fop^H diag(ps / n^2) Fop  (pspec.py:464, 313-322)

@@ -300,11 +300,13 @@ class GibbsEngine:
             out["chisq"] = mk(lead + (T, n), np.float64)
         return out
 
-    def run_to_host(self, niter, bufs, first_iter=0, iter_major=False):
+    def run_to_host(self, niter, bufs, first_iter=0, iter_major=False, read_ahead=0):
         """Run ``niter`` iterations and stream every iteration's arrays into ``bufs`` (from
         :meth:`host_buffers`) while the next iteration computes; returns when all data has landed.
         Iteration ``i`` of the chain lands in slot ``i - first_iter`` of the host arrays: a bounded staging area is
-        re-used chunk after chunk by passing the index of the chunk's first iteration."""
+        re-used chunk after chunk by passing the index of the chunk's first iteration.  ``read_ahead`` > 0: the next
+        iterations of the chain (at most ring_iters - 1) are computed into free device ring slots before the call
+        returns, so that the next chunk starts copying at once (``hp_host_sink.read_ahead``; pass 0 in the last call)."""
         sink = _lib.HPHostSink()
         for k in ("signal_ps", "ln_post", "signal_cr", "fg_amps", "chisq"):
             a = bufs.get(k)
@@ -315,6 +317,7 @@ class GibbsEngine:
         sink.iters = int(bufs["signal_ps"].shape[1])
         sink.first_iter = int(first_iter)
         sink.iter_major = int(bool(iter_major))
+        sink.read_ahead = int(read_ahead)
         _lib.check(_lib.lib().hp_engine_run_to_host(self._h, int(niter), _lib.C.byref(sink)))
 
     def gcr(self):
@@ -443,7 +446,11 @@ def _staged_run(eng, Niter, dest, write_Niter=None, after_chunk=None):
         c = min(chunk, Niter - done)
         if write_Niter:   # never run past a write boundary (pspec.py:625: files every write_Niter iterations)
             c = min(c, write_Niter - done % write_Niter)
-        eng.run_to_host(c, stage, first_iter=done, iter_major=True)
+        # read-ahead: the device computes the next iterations while this chunk's last copies land and while the host moves the
+        # chunk out of the staging area; not across a write boundary (the callback reads the chain's current signal_S)
+        at_boundary = after_chunk is not None and (done + c == Niter or (write_Niter and (done + c) % write_Niter == 0))
+        ra = 0 if (done + c >= Niter or at_boundary) else _RING_ITERS - 1
+        eng.run_to_host(c, stage, first_iter=done, iter_major=True, read_ahead=ra)
         for k, a in dest.items():
             if a is not None:
                 big = k in ("signal_cr", "fg_amps", "chisq")

@@ -139,6 +139,12 @@ typedef struct hp_host_sink {
                             iteration); 1: [iters][nchains][...] -- an iteration's array of all chains is then one contiguous block
                             on both sides and leaves with one plain copy (full PCIe rate).  signal_ps / ln_post are always
                             [nchains][iters][...] */
+    int read_ahead;      /* > 0: before returning, compute up to this many further iterations of the chain (at most ring_iters - 1)
+                            into free device ring slots, under the call's last device-to-host copies; the next
+                            hp_engine_run_to_host then starts copying at once instead of waiting for its first compute step.
+                            The samples are unchanged (same draws, same order).  While read-ahead iterations are pending the
+                            chain state is ahead of the delivered iterations: hp_engine_run / _gcr / _load_chain / _set_draws /
+                            _read_signal_S refuse to run; pass read_ahead = 0 in the last call of a chain (or hp_engine_rewind) */
 } hp_host_sink;
 /* hp_engine_run + copy-out: every iteration's arrays are streamed to the host on a second stream
  * while the next iteration computes.  Returns when everything has landed. */

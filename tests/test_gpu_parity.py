@@ -386,3 +386,48 @@ def test_verbose_prints_the_reference_table(capsys):
     for r, lp, cs in zip(rows, out[5], out[4]):
         assert abs(float(r[-1]) - lp) <= 0.05 + 1e-6 * abs(lp)
         assert abs(float(r[-2]) - cs[:, flags].mean()) <= 1e-3 * max(1.0, cs[:, flags].mean())
+
+
+def test_read_ahead_gives_identical_samples_and_guards_the_state():
+    """hp_host_sink.read_ahead: the next iterations are computed under a chunk's last copies.  Same samples bit for bit
+    (Philox draws, 4 chains on 2 sub-streams, 9 iterations through a 3-slot ring in chunks of 2); while read-ahead iterations
+    are pending the calls that would see the advanced chain state are refused."""
+    from hydra_pspec_b200 import pspec, _lib
+    rng = np.random.default_rng(77)
+    nt, nf, nm, nch, niter = 20, 64, 4, 4, 9
+    F = np.linalg.qr(crandn(rng, nf, nm))[0]
+    vis = crandn(rng, nch, nt, nf) + (3 * crandn(rng, nch, nt, nm)) @ F.T
+    flags = np.ones(nf, dtype=bool)
+    flags[[3, 40]] = False
+
+    def run(read_ahead):
+        eng = pspec.GibbsEngine(nch, nt, nf, nm, max_iters=niter, rng="philox", keep=("cr", "fg", "chisq"), ring_iters=3, seed=5,
+                                substreams=2)
+        for c in range(nch):
+            eng.load_chain(c, vis[c] * flags, flags, F, np.ones(nf), np.full(nf, 1.0 / nf))
+        stage = eng.host_buffers(2, iter_major=True)
+        out = {k: [] for k in ("signal_cr", "fg_amps", "chisq", "signal_ps", "ln_post")}
+        done = 0
+        while done < niter:
+            c = min(2, niter - done)
+            ra = read_ahead if done + c < niter else 0
+            eng.run_to_host(c, stage, first_iter=done, iter_major=True, read_ahead=ra)
+            if ra:
+                with pytest.raises(_lib.HydraLibError):
+                    eng.signal_S(0)
+                with pytest.raises(_lib.HydraLibError):
+                    eng.run(1)
+            for k in out:
+                big = k in ("signal_cr", "fg_amps", "chisq")
+                out[k].append(np.array(stage[k][:c] if big else stage[k][:, :c]))
+            done += c
+        S = eng.signal_S(0)
+        eng.close()
+        return {k: np.concatenate(v, axis=0 if k in ("signal_cr", "fg_amps", "chisq") else 1) for k, v in out.items()}, S
+
+    a, Sa = run(0)
+    for ra in (1, 2, 5):
+        b, Sb = run(ra)
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        np.testing.assert_array_equal(Sa, Sb)
