@@ -517,7 +517,7 @@ def run_b200(args):
         note = ("8 N^2 (Ntimes + Nfreq) flops per baseline-iteration: two triangular products with W = L^-1 for the Ntimes right-hand "
                 "sides and the Nfreq columns of A (low-rank form of the per-time systems)")
     else:
-        kernel = "k_solve3" if N <= 448 else ("k_solve2 / k_solve" if N <= 576 else "k_zgemm (dense-product solve)")
+        kernel = "k_solve3" if N <= 448 else ("k_solve2 / k_solve" if N <= 576 else "k_zgemm2 (dense-product solve)")
         flops_per_launch = 8.0 * N * N * nt * B
         note = "8 N^2 Ntimes flops per baseline-iteration (two triangular products with W = L^-1)"
     achieved = flops_per_launch / (solve_ms / KP * 1e-3) * 1e-12 if solve_ms > 0 else None
