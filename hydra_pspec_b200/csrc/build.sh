@@ -10,6 +10,6 @@ for f in hp_kernels hp_zgemm hp_solve hp_solve2 hp_solve3 hp_fft hp_fft2 hp_pert
   fi
 done
 wait
-$NVCC -shared -o libhydra_pspec_b200.so hp_kernels.o hp_zgemm.o hp_solve.o hp_solve2.o hp_solve3.o hp_fft.o hp_fft2.o hp_pertime.o hp_ptlow.o hp_engine.o hp_testhooks.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libhydra_pspec_b200.so hp_kernels.o hp_zgemm.o hp_solve.o hp_solve2.o hp_solve3.o hp_fft.o hp_fft2.o hp_pertime.o hp_ptlow.o hp_engine.o hp_testhooks.o -lcudart
 g++ -O2 -shared -fPIC -o libhp_math_host.so hp_math_host.cpp
 echo "built $(pwd)/libhydra_pspec_b200.so"

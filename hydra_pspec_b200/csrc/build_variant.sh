@@ -11,6 +11,6 @@ for f in hp_kernels hp_zgemm hp_solve hp_solve2 hp_solve3 hp_fft hp_fft2 hp_pert
   $NVCC $FLAGS -c $f.cu -o build_$tag/$f.o &
 done
 wait
-$NVCC -shared -o libhydra_pspec_b200_$tag.so build_$tag/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libhydra_pspec_b200_$tag.so build_$tag/*.o -lcudart
 rm -rf build_$tag
 echo "built libhydra_pspec_b200_$tag.so"
