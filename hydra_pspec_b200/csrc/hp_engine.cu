@@ -290,7 +290,7 @@ struct hp_engine {
     bool fft2_ok = false;
     bool fft_ok = false;
     int ntilesE = 0, ktp = 8;
-    double *tw = nullptr, *Empart = nullptr, *Eupart = nullptr;
+    double *tw = nullptr, *tw2 = nullptr, *Empart = nullptr, *Eupart = nullptr;
     std::vector<uint8_t> flagged;  // per chain: any channel flagged
     std::vector<uint8_t> have_omega;
     bool any_flagged = false;
@@ -557,6 +557,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     ap.want(&e->stage, 2 * (T * n > n * n ? T * n : n * n));
     ap.want(&e->vecn, 4 * n);
     ap.want(&e->tw, 2 * n);
+    if (e->fft2_ok) ap.want(&e->tw2, 4 * n);
     ap.want(&e->Empart, C * e->ntilesE * n); ap.want(&e->Eupart, C * e->ntilesE * n);
     {
         cudaError_t ce = ap.commit(&e->arena, &e->arena_bytes, cfg->device, e->st);
@@ -591,6 +592,7 @@ int hp_engine_create(const hp_config* cfg, hp_engine** out) {
     hp::launch_fourier_operator(e->Fop, e->n, 1.0, e->st);
     hp::launch_fourier_operator(e->U, e->n, 1.0 / std::sqrt((double)e->n), e->st);
     hp::launch_twiddles(e->tw, e->n, e->st);
+    if (e->tw2 && !hp::launch_fft2_tables(e->tw2, e->tw, e->n, e->st)) e->tw2 = nullptr;
     if (cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         hp_engine_destroy(e);
         return fail(HP_ERR_CUDA, "engine initialisation kernels failed");
@@ -1189,7 +1191,7 @@ static void enqueue_gcr(hp_engine* e, Basis& b, const IterOut& o, const Sub& sb,
     if (e->fft_ok) {
         e->prof_begin(CLS_POST, sb.st);
         hp::PostFftArgs pa{};
-        pa.plan = e->plan; pa.tw = e->tw; pa.X = OFFS(e->X, 2 * Tp * Np); pa.lam = OFFS(e->lam, Np); pa.Sf = sf; pa.sf_bs = o.sf_bs;
+        pa.plan = e->plan; pa.tw = e->tw; pa.tw2 = e->tw2; pa.X = OFFS(e->X, 2 * Tp * Np); pa.lam = OFFS(e->lam, Np); pa.Sf = sf; pa.sf_bs = o.sf_bs;
         pa.Ft = OFFS(e->Ft, 2 * (m ? m : 1) * n); pa.wd = OFFS(e->wd, 2 * Tp * n); pa.w = OFFS(e->w, n); pa.ninvd = OFFS(e->ninvd, n);
         pa.w_bs = e->n; pa.w_ts = 0;
         if (pt) { pa.w = OFFS(e->wT, Tp * n); pa.w_bs = (long long)e->Tp * e->n; pa.w_ts = e->n; }

@@ -245,10 +245,18 @@ __global__ void __launch_bounds__(32 * kTP2, (E >= 16 ? 1 : HP_FFT2_CTAS)) k_pos
             v[e] = make_double2(sg * y.x, -sg * y.y);
         }
     }
-    build_twiddle_tables<E, P0, P1, P2, P3>(tw, twg, tid, kThreads);
-    if (a.Empart) {
-        if constexpr (P3 > 1) build_twiddle_tables<E, P3, P2, P1, P0>(tw + n, twg, tid, kThreads);
-        else build_twiddle_tables<E, P2, P1, P0, 1>(tw + n, twg, tid, kThreads);
+    if (a.tw2) {
+        // the tables were built once per engine: a straight, coalesced copy (the per-CTA build is ~760 scattered 16-byte gathers
+        // with index arithmetic in front of every CTA's first pass)
+        const double2* t2 = reinterpret_cast<const double2*>(a.tw2);
+        const int cnt = a.Empart ? 2 * n : n;
+        for (int e = tid; e < cnt; e += kThreads) tw[e] = t2[e];
+    } else {
+        build_twiddle_tables<E, P0, P1, P2, P3>(tw, twg, tid, kThreads);
+        if (a.Empart) {
+            if constexpr (P3 > 1) build_twiddle_tables<E, P3, P2, P1, P0>(tw + n, twg, tid, kThreads);
+            else build_twiddle_tables<E, P2, P1, P0, 1>(tw + n, twg, tid, kThreads);
+        }
     }
     for (int e = tid; e < kTP2 * ldf; e += kThreads) {
         const int tt = e / ldf, j = e - tt * ldf;
@@ -385,6 +393,30 @@ __global__ void __launch_bounds__(32 * kTP2, (E >= 16 ? 1 : HP_FFT2_CTAS)) k_pos
             Ep[k] = acc / (double)n;
         }
     }
+}
+
+namespace {
+template <int E, int P0, int P1, int P2, int P3>
+__global__ void __launch_bounds__(256) k_fft2_tables(double2* tw2, const double2* twg) {
+    constexpr int n = 32 * E;
+    for (int e = threadIdx.x; e < 2 * n; e += 256) tw2[e] = make_double2(0.0, 0.0);
+    __syncthreads();
+    build_twiddle_tables<E, P0, P1, P2, P3>(tw2, twg, threadIdx.x, 256);
+    if constexpr (P3 > 1) build_twiddle_tables<E, P3, P2, P1, P0>(tw2 + n, twg, threadIdx.x, 256);
+    else build_twiddle_tables<E, P2, P1, P0, 1>(tw2 + n, twg, threadIdx.x, 256);
+}
+}  // namespace
+
+bool launch_fft2_tables(double* tw2, const double* tw, int n, cudaStream_t st) {
+    double2* o = reinterpret_cast<double2*>(tw2);
+    const double2* t = reinterpret_cast<const double2*>(tw);
+    if (n == 128) k_fft2_tables<4, 4, 4, 4, 2><<<1, 256, 0, st>>>(o, t);
+    else if (n == 256) k_fft2_tables<8, 8, 8, 4, 1><<<1, 256, 0, st>>>(o, t);
+    else if (n == 384) k_fft2_tables<12, 6, 4, 4, 4><<<1, 256, 0, st>>>(o, t);
+    else if (n == 512) k_fft2_tables<16, 8, 8, 4, 2><<<1, 256, 0, st>>>(o, t);
+    else if (n == 1024) k_fft2_tables<32, 8, 8, 4, 4><<<1, 256, 0, st>>>(o, t);
+    else return false;
+    return true;
 }
 
 // true: the launch was taken by k_post_fft2

@@ -249,6 +249,8 @@ size_t postfft_smem_bytes(int n, int m, int ktp);
 struct PostFftArgs {
     FftPlan plan;
     const double* tw;
+    const double* tw2;     // k_post_fft2: per-pass twiddle tables of the forward plan ([0, n)) and of the reverse plan ([n, 2 n)),
+                           //   built once per engine (launch_fft2_tables); null: every CTA derives them from tw
     const double* X;       // [nsys][Tp][Np]
     const double* lam;     // [nsys][Np]
     double* Sf;            // [nsys][..][n] frequency-space signal: written (do_inverse) or read
@@ -269,6 +271,7 @@ void launch_post_fft(const PostFftArgs& a, cudaStream_t st);
 bool make_fft2_plan(int n, FftPlan* fwd, FftPlan* rev);   // false: Nfreqs not covered (k_post_fft takes it)
 size_t postfft2_smem_bytes(int n, int m);
 bool launch_post_fft2(const PostFftArgs& a, const FftPlan& fwd, const FftPlan& rev, cudaStream_t st);
+bool launch_fft2_tables(double* tw2, const double* tw, int n, cudaStream_t st);   // tw2: 4 n doubles; false: Nfreqs not covered
 
 
 // small elementwise helpers used by the set-up
