@@ -63,6 +63,7 @@ _SIGNATURES = {
     "hp_kernel_class_name": (C.c_char_p, [C.c_int]),
     "hp_sample_S": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hp_fourier_operator": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "hp_eigh_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hp_test_zgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_void_p]),
     "hp_test_chol_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

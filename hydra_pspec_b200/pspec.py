@@ -132,29 +132,64 @@ def _unitary_dft(n):
     return _UNITARY_CACHE[n]
 
 
-def _analyse_signal_cov(S):
-    """Eigen-structure of the signal covariance handed to the device.
-
-    Returns (basis0 or None, lam0sq).  A delay-diagonal S (every covariance the chain itself
-    produces, the reference's test data, and the identity default) needs no decomposition:
-    its eigenvectors are the columns of U^H.  Anything else is decomposed once on the host
-    (numpy eigh); the first iteration then runs in that basis.
-    """
+def _delay_diagonal(S):
+    """Eigenvalues of a delay-diagonal S = U^H diag(d) U (U = fourier_operator / sqrt(n)), or None.  Such an S is circulant,
+    S[x, x'] = c[(x - x') mod n]; checked in O(n^2), d from one FFT of its first column (no matrix product)."""
     S = np.asarray(S)
     n = S.shape[0]
-    U = _unitary_dft(n)
-    D = U @ S @ U.conj().T
-    d = np.real(np.diagonal(D)).copy()
-    off = D - np.diag(np.diagonal(D))
-    scale = max(np.max(np.abs(d)), 1e-300)
-    # eigenvalues are clipped at zero: a rank-deficient or barely positive semi-definite S (e.g. a sample covariance
-    # passed as --sigcov0) has eigenvalues ~ -1e-17, whose square root would turn the whole chain into NaN
-    # (the reference's sqrtm tolerates them, pspec.py:355)
-    if np.max(np.abs(off)) <= 1e-13 * scale and np.max(np.abs(np.imag(np.diagonal(D)))) <= 1e-13 * scale:
-        return None, np.clip(d, 0.0, None)
-    Sh = 0.5 * (S + S.conj().T)
-    w, V = np.linalg.eigh(Sh)
-    return np.ascontiguousarray(V, dtype=np.complex128), np.ascontiguousarray(np.clip(w, 0.0, None), dtype=np.float64)
+    c = S[:, 0]
+    idx = (np.arange(n)[:, None] - np.arange(n)[None, :]) % n
+    scale = max(np.max(np.abs(np.diagonal(S))), 1e-300)
+    if np.max(np.abs(S - c[idx])) > 1e-13 * scale:
+        return None
+    d = np.roll(np.fft.fft(c), n // 2)          # d[k] = sum_j c[j] exp(-2 pi i (k - n/2) j / n)
+    if np.max(np.abs(d.imag)) > 1e-13 * max(np.max(np.abs(d.real)), 1e-300) * n:
+        return None
+    return np.ascontiguousarray(d.real, dtype=np.float64)
+
+
+def device_eigh(mats, device=0):
+    """Batched Hermitian eigendecomposition on the GPU (csrc/hp_eigh.cu: one-sided Jacobi, one CTA per matrix).
+    ``mats``: (batch, n, n); returns ``(w, V)`` like ``numpy.linalg.eigh`` (eigenvalues unordered)."""
+    mats = np.ascontiguousarray(mats, dtype=np.complex128)
+    batch, n, _ = mats.shape
+    V = np.empty_like(mats)
+    w = np.empty((batch, n), dtype=np.float64)
+    _lib.check(_lib.lib().hp_eigh_batch(int(device), n, batch, _lib.ptr(mats), _lib.ptr(V), _lib.ptr(w), None))
+    return w, V
+
+
+def _analyse_signal_covs(covs, device=0, eigh=None):
+    """Eigen-structure of the signal covariances handed to the device, for a list of baselines.
+
+    Returns a list of (basis0 or None, lam0sq).  A delay-diagonal S (every covariance the chain itself produces, the
+    reference's test data, and the identity default) needs no decomposition: its eigenvectors are the columns of U^H.
+    Everything else is decomposed once, all such matrices of the list in one batched device call (``device_eigh``; the first
+    iteration then runs in that basis).  ``eigh``: replacement for the decomposition (host-logic tests without a GPU).
+    """
+    out = [None] * len(covs)
+    todo = []
+    for i, S in enumerate(covs):
+        S = np.asarray(S)
+        d = _delay_diagonal(S)
+        if d is not None:
+            # eigenvalues are clipped at zero: a rank-deficient or barely positive semi-definite S (e.g. a sample covariance
+            # passed as --sigcov0) has eigenvalues ~ -1e-17, whose square root would turn the whole chain into NaN
+            # (the reference's sqrtm tolerates them, pspec.py:355)
+            out[i] = (None, np.clip(d, 0.0, None))
+        else:
+            todo.append(i)
+    if todo:
+        Sh = np.stack([0.5 * (np.asarray(covs[i]) + np.asarray(covs[i]).conj().T) for i in todo])
+        w, V = (eigh or (lambda m: device_eigh(m, device)))(Sh)
+        for j, i in enumerate(todo):
+            out[i] = (np.ascontiguousarray(V[j], dtype=np.complex128), np.ascontiguousarray(np.clip(w[j], 0.0, None), dtype=np.float64))
+    return out
+
+
+def _analyse_signal_cov(S, device=0, eigh=None):
+    """One covariance: (basis0 or None, lam0sq); see :func:`_analyse_signal_covs`."""
+    return _analyse_signal_covs([S], device=device, eigh=eigh)[0]
 
 
 def _noise_model(Ninv, flags, nfreqs, need_sqrt):
@@ -510,7 +545,7 @@ def _single_chain_engine(vis, flags, S, fgmodes, Ninv, ps_prior, max_iters, rng,
     nmodes = np.asarray(fgmodes).shape[1]
     per_time = np.asarray(flags).ndim == 2
     ninv_diag, ninv_dense, nih_dense = _noise_model(Ninv, flags, nfreqs, need_sqrt=(rng == "numpy" and not map_estimate))
-    basis0, lam0sq = _analyse_signal_cov(S)
+    basis0, lam0sq = _analyse_signal_cov(S, device=device)
     if solver is None:
         solver = "reference-cg" if (rng == "numpy" and not per_time) else "exact"
     if solver not in ("reference-cg", "exact"):
@@ -711,11 +746,12 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
         assert flags.shape in ((nfreqs,), (ntimes, nfreqs)), "`flags` array must have shape (Nfreqs,) [or (Ntimes, Nfreqs)]"
         F = np.asarray(b["fgmodes"])
         assert F.shape == (nfreqs, nmodes), "fgmodes must have shape (Nfreqs, Nmodes)"
-        S0 = b.get("S_initial")
-        basis0, lam0sq = _analyse_signal_cov(np.eye(nfreqs) if S0 is None else S0)
         nd, nD, nH = _noise_model(b["Ninv"], flags, nfreqs, need_sqrt=(rng == "numpy" and not map_estimate))
-        prep.append(dict(vis=vis * flags, flags=flags, F=F, basis0=basis0, lam0sq=lam0sq, nd=nd, nD=nD, nH=nH,
-                         prior=_check_prior(b.get("ps_prior"), nfreqs)))
+        prep.append(dict(vis=vis * flags, flags=flags, F=F, nd=nd, nD=nD, nH=nH, prior=_check_prior(b.get("ps_prior"), nfreqs)))
+    # one batched device eigendecomposition for all baselines with a non-delay-diagonal S_initial
+    covs = [np.eye(nfreqs) if b.get("S_initial") is None else b["S_initial"] for b in baselines]
+    for pr_, (basis0, lam0sq) in zip(prep, _analyse_signal_covs(covs, device=device)):
+        pr_["basis0"], pr_["lam0sq"] = basis0, lam0sq
     general = any(p["basis0"] is not None for p in prep)
     dense = any(p["nD"] is not None for p in prep)
     per_time = any(p["flags"].ndim == 2 for p in prep)

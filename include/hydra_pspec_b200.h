@@ -192,6 +192,11 @@ int hp_sample_S(int device, int ntimes, int nfreqs, const double* s, const doubl
 
 /* utils.fourier_operator (utils.py:14-40), computed on the device; out [n][n] complex128. */
 int hp_fourier_operator(int device, int n, double* out);
+/* Batched Hermitian eigendecomposition on the device (one-sided Jacobi, csrc/hp_eigh.cu): S [batch][n][n] complex128
+ * Hermitian, V [batch][n][n] (eigenvectors as columns, numpy.linalg.eigh convention, unordered), w [batch][n] eigenvalues,
+ * sweeps [batch] or NULL.  Used for a non-delay-diagonal S_initial, whose eigenbasis the first Gibbs iteration runs in; stands
+ * in for the matrix square root the reference takes of the signal covariance (scipy sqrtm in build_matrices, pspec.py:355). */
+int hp_eigh_batch(int device, int n, int batch, const double* S, double* V, double* w, int* sweeps);
 
 /* ---- test hooks (tests/ only): single kernels with host buffers ------------------------------- */
 int hp_test_zgemm(int M, int N, int K, const double* A, int transA, int conjA, const double* B, int transB, int conjB,

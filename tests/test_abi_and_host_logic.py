@@ -94,8 +94,16 @@ def test_signal_cov_analysis():
     b0, lam = pspec._analyse_signal_cov(np.eye(n))
     assert b0 is None and np.allclose(lam, 1.0)
     X = np.random.default_rng(2).standard_normal((n, n))
-    b0, lam = pspec._analyse_signal_cov(X @ X.T + np.eye(n))
+    # a general covariance goes to the batched device eigensolver (tests/test_gpu_kernels.py); here only the host logic,
+    # with numpy standing in for it
+    host_eigh = lambda m: np.linalg.eigh(m)
+    b0, lam = pspec._analyse_signal_cov(X @ X.T + np.eye(n), eigh=host_eigh)
     assert b0 is not None and np.allclose((b0 * lam) @ b0.conj().T, X @ X.T + np.eye(n))
+    # almost delay-diagonal is not delay-diagonal
+    S2 = S.copy()
+    S2[1, 5] += 1e-9 * np.abs(S).max()
+    S2[5, 1] += 1e-9 * np.abs(S).max()
+    assert pspec._analyse_signal_cov(S2, eigh=host_eigh)[0] is not None
 
 
 def test_host_helpers_match_reference(golden_dir):

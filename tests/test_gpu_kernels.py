@@ -185,3 +185,25 @@ def test_solve2(n, m, T, nsys, grid, use_wa, cg, variant):
     assert rel(X, Xw) < 1e-11
     if not cg:  # (with cg_compat the engine recomputes the sums after the scaling)
         assert rel(psum, np.sum(np.abs(Xw[:, :, :n]) ** 2, axis=1)) < 1e-11
+
+
+@pytest.mark.parametrize("n,batch", [(5, 2), (33, 3), (120, 2), (384, 3)])
+def test_device_eigh_batch(n, batch):
+    """hp_eigh_batch (one-sided Jacobi, csrc/hp_eigh.cu) against numpy.linalg.eigh: eigenvalues, unitarity, reconstruction;
+    a rank-deficient and a slightly indefinite matrix in the batch (signed Rayleigh quotients)."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(10 * n + batch)
+    mats = []
+    for b in range(batch):
+        X = crandn(rng, n, n if b != 1 else max(1, n // 2))          # b == 1: rank n / 2
+        S = X @ X.conj().T * 10.0 ** rng.uniform(-3, 3)
+        if b == 0:
+            S = S - 1e-9 * np.trace(S).real / n * np.eye(n) * (n > 5)   # eigenvalues down to slightly negative values
+        mats.append(0.5 * (S + S.conj().T))
+    mats = np.stack(mats)
+    w, V = pspec.device_eigh(mats)
+    for b in range(batch):
+        scale = np.abs(np.linalg.eigvalsh(mats[b])).max()
+        assert np.max(np.abs(V[b].conj().T @ V[b] - np.eye(n))) < 1e-12
+        assert np.max(np.abs((V[b] * w[b]) @ V[b].conj().T - mats[b])) < 1e-11 * scale
+        assert np.max(np.abs(np.sort(w[b]) - np.linalg.eigvalsh(mats[b]))) < 1e-11 * scale
