@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) k_eigh_init(const double2* __restrict__ S
 }
 
 // One round of the tournament: the ne / 2 disjoint column pairs of round `round`, a warp per pair, for every matrix of the
-// batch (blockIdx.y).  rotated[matrix] is set when a pair was not yet orthogonal.
+// batch (blockIdx.y).  rotated[matrix] is set when a pair was not yet orthogonal.  kNJ > 0: n <= 32 kNJ, the two columns of G
+// stay in registers between the inner products and the rotation (one read instead of two, all loads issued up front).
+template <int kNJ>
 __global__ void __launch_bounds__(32 * kEighWarps) k_eigh_round(double2* G_all, double2* V_all, int n, int ne, int round, double tol,
                                                                  int* rotated) {
     const int lane = threadIdx.x & 31, i = blockIdx.x * kEighWarps + (threadIdx.x >> 5);
@@ -50,13 +52,32 @@ __global__ void __launch_bounds__(32 * kEighWarps) k_eigh_round(double2* G_all, 
     double2* V = V_all + blockIdx.y * nn;
     double2* x = G + (size_t)p * n;
     double2* y = G + (size_t)q * n;
+    constexpr int kR = kNJ > 0 ? kNJ : 1;
+    double2 xa[kR], ya[kR];
     double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
-    for (int r = lane; r < n; r += 32) {
-        const double2 a = x[r], b = y[r];
-        al += a.x * a.x + a.y * a.y;
-        be += b.x * b.x + b.y * b.y;
-        gr += a.x * b.x + a.y * b.y;                  // conj(a) b
-        gi += a.x * b.y - a.y * b.x;
+    if (kNJ > 0) {
+#pragma unroll
+        for (int u = 0; u < kR; ++u) {
+            const int r = lane + 32 * u;
+            xa[u] = r < n ? x[r] : make_double2(0.0, 0.0);
+            ya[u] = r < n ? y[r] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < kR; ++u) {
+            const double2 a = xa[u], b = ya[u];
+            al += a.x * a.x + a.y * a.y;
+            be += b.x * b.x + b.y * b.y;
+            gr += a.x * b.x + a.y * b.y;              // conj(a) b
+            gi += a.x * b.y - a.y * b.x;
+        }
+    } else {
+        for (int r = lane; r < n; r += 32) {
+            const double2 a = x[r], b = y[r];
+            al += a.x * a.x + a.y * a.y;
+            be += b.x * b.x + b.y * b.y;
+            gr += a.x * b.x + a.y * b.y;
+            gi += a.x * b.y - a.y * b.x;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -71,22 +92,24 @@ __global__ void __launch_bounds__(32 * kEighWarps) k_eigh_round(double2* G_all, 
     const double zeta = (be - al) / (2.0 * ga);
     const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+    auto rot = [&](double2 a, double2 b0, double2& xo, double2& yo) {
+        const double2 b = make_double2(b0.x * er - b0.y * ei, b0.x * ei + b0.y * er);
+        xo = make_double2(c * a.x - s * b.x, c * a.y - s * b.y);
+        yo = make_double2(s * a.x + c * b.x, s * a.y + c * b.y);
+    };
     double2* vx = V + (size_t)p * n;
     double2* vy = V + (size_t)q * n;
-    for (int r = lane; r < n; r += 32) {
-        {
-            const double2 a = x[r], b0 = y[r];
-            const double2 b = make_double2(b0.x * er - b0.y * ei, b0.x * ei + b0.y * er);
-            x[r] = make_double2(c * a.x - s * b.x, c * a.y - s * b.y);
-            y[r] = make_double2(s * a.x + c * b.x, s * a.y + c * b.y);
+    if (kNJ > 0) {
+#pragma unroll
+        for (int u = 0; u < kR; ++u) {
+            const int r = lane + 32 * u;
+            if (r < n) { double2 xo, yo; rot(xa[u], ya[u], xo, yo); x[r] = xo; y[r] = yo; }
         }
-        {
-            const double2 a = vx[r], b0 = vy[r];
-            const double2 b = make_double2(b0.x * er - b0.y * ei, b0.x * ei + b0.y * er);
-            vx[r] = make_double2(c * a.x - s * b.x, c * a.y - s * b.y);
-            vy[r] = make_double2(s * a.x + c * b.x, s * a.y + c * b.y);
-        }
+    } else {
+        for (int r = lane; r < n; r += 32) { double2 xo, yo; rot(x[r], y[r], xo, yo); x[r] = xo; y[r] = yo; }
     }
+#pragma unroll 4
+    for (int r = lane; r < n; r += 32) { double2 xo, yo; rot(vx[r], vy[r], xo, yo); vx[r] = xo; vy[r] = yo; }
     if (lane == 0) rotated[blockIdx.y] = 1;
 }
 
@@ -144,7 +167,9 @@ extern "C" int hp_eigh_batch(int device, int n, int batch, const double* S, doub
         for (; sweeps_used < max_sweeps && e == cudaSuccess;) {
             cudaMemsetAsync(dsw, 0, sizeof(int) * batch, 0);
             for (int round = 0; round < ne - 1; ++round)
-                hp::k_eigh_round<<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+                if (n <= 256) hp::k_eigh_round<8><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+                else if (n <= 512) hp::k_eigh_round<16><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+                else hp::k_eigh_round<0><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
             ++sweeps_used;
             e = cudaMemcpy(flag.data(), dsw, sizeof(int) * batch, cudaMemcpyDeviceToHost);
             bool any = false;
