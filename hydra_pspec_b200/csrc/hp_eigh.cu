@@ -13,6 +13,7 @@
 // work arrays), so every access is coalesced; V stays unitary to round-off by construction.
 #include "hp_kernels.cuh"
 #include "../../include/hydra_pspec_b200.h"
+#include <cstdlib>
 #include <vector>
 
 namespace hp {
@@ -113,6 +114,92 @@ __global__ void __launch_bounds__(32 * kEighWarps) k_eigh_round(double2* G_all, 
     if (lane == 0) rotated[blockIdx.y] = 1;
 }
 
+// Blocked round: a CTA takes a PAIR OF COLUMN BLOCKS (2 bw columns of G and of V) into shared memory, runs a full inner
+// tournament over those columns there (a warp per pair, one CTA barrier per inner round) and writes them back.  A sweep over
+// the blocks is nb - 1 launches instead of n - 1, and every column crosses L2 once per launch instead of once per pair: ~10x
+// less L2 traffic at n = 384, bw = 8 (the unblocked rounds are L2-bandwidth bound for a batch of matrices).
+__global__ void __launch_bounds__(256) k_eigh_block_round(double2* G_all, double2* V_all, int n, int nb, int nbe, int bw, int round,
+                                                          double tol, int* rotated) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* gs = reinterpret_cast<double2*>(smem_raw);     // [2 bw][n]
+    double2* vs = gs + (size_t)2 * bw * n;                  // [2 bw][n]
+    const int i = blockIdx.x;
+    int P, Q;
+    if (i == 0) { P = nbe - 1; Q = round; }
+    else { P = (round + i) % (nbe - 1); Q = (round - i + (nbe - 1)) % (nbe - 1); }
+    if (P >= nb || Q >= nb) return;                         // the dummy block of an odd number of blocks
+    if (P > Q) { const int t = P; P = Q; Q = t; }
+    const int cP = min(bw, n - P * bw), cQ = min(bw, n - Q * bw), m = cP + cQ;
+    const size_t nn = (size_t)n * n;
+    double2* G = G_all + blockIdx.y * nn;
+    double2* V = V_all + blockIdx.y * nn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    auto gcol = [&](int j) { return j < cP ? P * bw + j : Q * bw + (j - cP); };   // local column -> column of the matrix
+    for (int j = 0; j < m; ++j) {
+        const size_t src = (size_t)gcol(j) * n;
+        for (int r = tid; r < n; r += nthr) { gs[(size_t)j * n + r] = G[src + r]; vs[(size_t)j * n + r] = V[src + r]; }
+    }
+    __syncthreads();
+    const int me = m + (m & 1);
+    bool any = false;
+    for (int ir = 0; ir < me - 1; ++ir) {
+        if (warp < me / 2) {
+            int a, b;
+            if (warp == 0) { a = me - 1; b = ir; }
+            else { a = (ir + warp) % (me - 1); b = (ir - warp + (me - 1)) % (me - 1); }
+            if (a < m && b < m) {
+                if (a > b) { const int t = a; a = b; b = t; }
+                double2* x = gs + (size_t)a * n;
+                double2* y = gs + (size_t)b * n;
+                double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+                for (int r = lane; r < n; r += 32) {
+                    const double2 u = x[r], v = y[r];
+                    al += u.x * u.x + u.y * u.y;
+                    be += v.x * v.x + v.y * v.y;
+                    gr += u.x * v.x + u.y * v.y;
+                    gi += u.x * v.y - u.y * v.x;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(0xffffffffu, al, o); be += __shfl_xor_sync(0xffffffffu, be, o);
+                    gr += __shfl_xor_sync(0xffffffffu, gr, o); gi += __shfl_xor_sync(0xffffffffu, gi, o);
+                }
+                const double g2 = gr * gr + gi * gi;
+                if (g2 > tol * tol * al * be && g2 != 0.0) {
+                    const double ga = sqrt(g2);
+                    const double er = gr / ga, ei = -gi / ga;
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    double2* vx = vs + (size_t)a * n;
+                    double2* vy = vs + (size_t)b * n;
+                    for (int r = lane; r < n; r += 32) {
+                        {
+                            const double2 u = x[r], w0 = y[r];
+                            const double2 w = make_double2(w0.x * er - w0.y * ei, w0.x * ei + w0.y * er);
+                            x[r] = make_double2(c * u.x - s * w.x, c * u.y - s * w.y);
+                            y[r] = make_double2(s * u.x + c * w.x, s * u.y + c * w.y);
+                        }
+                        {
+                            const double2 u = vx[r], w0 = vy[r];
+                            const double2 w = make_double2(w0.x * er - w0.y * ei, w0.x * ei + w0.y * er);
+                            vx[r] = make_double2(c * u.x - s * w.x, c * u.y - s * w.y);
+                            vy[r] = make_double2(s * u.x + c * w.x, s * u.y + c * w.y);
+                        }
+                    }
+                    any = true;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = 0; j < m; ++j) {
+        const size_t dst = (size_t)gcol(j) * n;
+        for (int r = tid; r < n; r += nthr) { G[dst + r] = gs[(size_t)j * n + r]; V[dst + r] = vs[(size_t)j * n + r]; }
+    }
+    if (any && lane == 0) rotated[blockIdx.y] = 1;
+}
+
 // lambda_j = Re(v_j^H g_j) (g_j = S v_j); eigenvectors as the columns of a row-major matrix (numpy.linalg.eigh convention)
 __global__ void __launch_bounds__(256) k_eigh_finish(const double2* __restrict__ G_all, const double2* __restrict__ V_all, double* w_all,
                                                      double2* Vout_all, int n) {
@@ -162,14 +249,30 @@ extern "C" int hp_eigh_batch(int device, int n, int batch, const double* S, doub
         const int ne = n + (n & 1), max_sweeps = 30;
         const double tol = 1e-13;
         const dim3 grid((ne / 2 + hp::kEighWarps - 1) / hp::kEighWarps, batch);
+        // blocked rounds when two blocks of >= 2 columns (G and V) fit the shared memory of a CTA
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        int bw = (int)((size_t)(max_smem > 8192 ? max_smem - 8192 : 0) / ((size_t)4 * n * 16));
+        if (bw > 8) bw = 8;
+        const char* ub = getenv("HP_EIGH_UNBLOCKED");   // A/B runs
+        if (ub && ub[0] == '1') bw = 0;
+        const int nb = bw >= 2 ? (n + bw - 1) / bw : 0, nbe = nb + (nb & 1);
+        const size_t bsmem = (size_t)4 * bw * n * 16;
+        if (bw >= 2) cudaFuncSetAttribute(hp::k_eigh_block_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
         hp::k_eigh_init<<<dim3(64, batch), 256>>>(dS, dG, dV, n);
         std::vector<int> flag(batch);
         for (; sweeps_used < max_sweeps && e == cudaSuccess;) {
             cudaMemsetAsync(dsw, 0, sizeof(int) * batch, 0);
-            for (int round = 0; round < ne - 1; ++round)
-                if (n <= 256) hp::k_eigh_round<8><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
-                else if (n <= 512) hp::k_eigh_round<16><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
-                else hp::k_eigh_round<0><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+            if (bw >= 2 && nb >= 2) {
+                for (int round = 0; round < nbe - 1; ++round)
+                    hp::k_eigh_block_round<<<dim3(nbe / 2, batch), 32 * bw, bsmem>>>(dG, dV, n, nb, nbe, bw, round, tol, dsw);
+            } else {
+                for (int round = 0; round < ne - 1; ++round) {
+                    if (n <= 256) hp::k_eigh_round<8><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+                    else if (n <= 512) hp::k_eigh_round<16><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+                    else hp::k_eigh_round<0><<<grid, 32 * hp::kEighWarps>>>(dG, dV, n, ne, round, tol, dsw);
+                }
+            }
             ++sweeps_used;
             e = cudaMemcpy(flag.data(), dsw, sizeof(int) * batch, cudaMemcpyDeviceToHost);
             bool any = false;

@@ -251,11 +251,19 @@ void launch_pt_lowrank(const PtLowArgs& a_in, cudaStream_t st) {
         attr_smem = smem;
     }
     const int nj = (a.N + 31) / 32;   // rows of the system per lane
-    int per_sm = 0;
-    if (nj <= 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_lowrank<5>, 32 * warps, smem);
-    else if (nj <= 9) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_lowrank<9>, 32 * warps, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt_lowrank<kPLMaxJ>, 32 * warps, smem);
-    if (per_sm < 1) per_sm = 1;
+    // resident CTAs per SM for this (instantiation, CTA size, shared memory): queried once per device and configuration
+    struct OccKey { size_t smem; int warps, cls, per_sm; };
+    static OccKey occ_dev[kMaxDev] = {};
+    OccKey& occ = occ_dev[current_device_slot()];
+    const int cls = nj <= 5 ? 5 : (nj <= 9 ? 9 : kPLMaxJ);
+    if (occ.per_sm < 1 || occ.smem != smem || occ.warps != warps || occ.cls != cls) {
+        int per = 0;
+        if (cls == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_pt_lowrank<5>, 32 * warps, smem);
+        else if (cls == 9) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_pt_lowrank<9>, 32 * warps, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_pt_lowrank<kPLMaxJ>, 32 * warps, smem);
+        occ = OccKey{smem, warps, cls, per < 1 ? 1 : per};
+    }
+    const int per_sm = occ.per_sm;
     long long grid = (nitems + warps - 1) / warps;
     const long long cap = (long long)num_sm * per_sm;   // persistent: every resident warp strides over the systems
     if (grid > cap) grid = cap;
