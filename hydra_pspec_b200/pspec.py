@@ -465,6 +465,42 @@ def _big_bytes_per_iter(nchains, ntimes, nfreqs, nmodes, keep):
     return nchains * (per + nfreqs * 8 + 8)
 
 
+# threads of the staging -> destination copy: HP_COPY_THREADS, else the host cores shared by the ranks of this node (at most 16)
+_COPY_THREADS = max(1, int(os.environ.get("HP_COPY_THREADS", "0")) or
+                    min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+_copy_pool = None
+
+
+def _scatter_chunk(dest, stage, done, c):
+    """Move iterations [done, done + c) of a chunk from the iteration-major staging arrays ``stage[k][iter][chain]...`` into
+    the chain-major destination arrays ``dest[k][chain][iter]...``.  One numpy copy of a headline-size chunk (1.3 GB per
+    iteration) runs at a few GB/s on one core -- ten times longer than the GPU needs for the iteration -- so the chains are
+    split over a small thread pool (numpy releases the GIL while it copies)."""
+    global _copy_pool
+    jobs = []
+    for k, a in dest.items():
+        if a is None:
+            continue
+        big = k in ("signal_cr", "fg_amps", "chisq")
+        nch = a.shape[0]
+        if not big or _COPY_THREADS == 1 or a[:, done:done + c].nbytes < (32 << 20):
+            a[:, done:done + c] = np.swapaxes(stage[k][:c], 0, 1) if big else stage[k][:, :c]
+            continue
+        step = -(-nch // _COPY_THREADS)
+        for c0 in range(0, nch, step):
+            jobs.append((a, stage[k], c0, min(nch, c0 + step)))
+    if jobs:
+        if _copy_pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _copy_pool = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="hp-copy")
+
+        def work(job):
+            a, st, c0, c1 = job
+            a[c0:c1, done:done + c] = np.swapaxes(st[:c, c0:c1], 0, 1)
+
+        list(_copy_pool.map(work, jobs))
+
+
 def _staged_run(eng, Niter, dest, write_Niter=None, after_chunk=None):
     """Run ``Niter`` iterations of ``eng`` through a bounded page-locked staging area.
 
@@ -486,10 +522,7 @@ def _staged_run(eng, Niter, dest, write_Niter=None, after_chunk=None):
         at_boundary = after_chunk is not None and (done + c == Niter or (write_Niter and (done + c) % write_Niter == 0))
         ra = 0 if (done + c >= Niter or at_boundary) else _RING_ITERS - 1
         eng.run_to_host(c, stage, first_iter=done, iter_major=True, read_ahead=ra)
-        for k, a in dest.items():
-            if a is not None:
-                big = k in ("signal_cr", "fg_amps", "chisq")
-                a[:, done:done + c] = np.swapaxes(stage[k][:c], 0, 1) if big else stage[k][:, :c]
+        _scatter_chunk(dest, stage, done, c)
         done += c
         if after_chunk is not None and (done == Niter or (write_Niter and done % write_Niter == 0)):
             after_chunk(done)

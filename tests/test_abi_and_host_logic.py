@@ -192,3 +192,21 @@ def test_solve3_schedule_covers_every_strip_once(nblk):
         if nblk == 13:
             assert sched.max() <= 1.03 * sched.mean(), sched
             assert loads.max() <= 1.25 * loads.mean(), loads
+
+
+def test_scatter_chunk_threads_match_a_plain_copy(monkeypatch):
+    """pspec._scatter_chunk: iteration-major staging -> chain-major destinations, split over the copy threads."""
+    from hydra_pspec_b200 import pspec
+    rng = np.random.default_rng(0)
+    nch, niter, nt, nf, nm, c, done = 37, 5, 64, 512, 3, 2, 3        # signal_cr chunk: 37 x 2 x 64 x 512 x 16 B = 38.8 MB (threaded)
+    stage = {"signal_cr": rng.standard_normal((c, nch, nt, nf)) + 1j * rng.standard_normal((c, nch, nt, nf)),
+             "fg_amps": rng.standard_normal((c, nch, nt, nm)) + 0j, "chisq": rng.standard_normal((c, nch, nt, nf)),
+             "signal_ps": rng.standard_normal((nch, c, nf)), "ln_post": rng.standard_normal((nch, c))}
+    dest = {"signal_cr": np.zeros((nch, niter, nt, nf), dtype=complex), "fg_amps": np.zeros((nch, niter, nt, nm), dtype=complex),
+            "chisq": np.zeros((nch, niter, nt, nf)), "signal_ps": np.zeros((nch, niter, nf)), "ln_post": None}
+    monkeypatch.setattr(pspec, "_COPY_THREADS", 4)
+    pspec._scatter_chunk(dest, stage, done, c)
+    for k in ("signal_cr", "fg_amps", "chisq"):
+        assert np.array_equal(dest[k][:, done:done + c], np.swapaxes(stage[k], 0, 1))
+        assert not dest[k][:, :done].any()
+    assert np.array_equal(dest["signal_ps"][:, done:done + c], stage["signal_ps"])
