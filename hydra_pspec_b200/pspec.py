@@ -483,7 +483,7 @@ def _scatter_chunk(dest, stage, done, c):
             continue
         big = k in ("signal_cr", "fg_amps", "chisq")
         nch = a.shape[0]
-        if not big or _COPY_THREADS == 1 or a[:, done:done + c].nbytes < (32 << 20):
+        if not big or _COPY_THREADS == 1 or stage[k][:c].nbytes < (32 << 20):
             a[:, done:done + c] = np.swapaxes(stage[k][:c], 0, 1) if big else stage[k][:, :c]
             continue
         step = -(-nch // _COPY_THREADS)
@@ -881,10 +881,12 @@ def gibbs_sample_batch(baselines, Niter=100, seed=None, rng="philox", solver=Non
                 def __init__(self, key):
                     self.key = key
 
+                    self.shape = (len(cs),)      # chains of this group (what _scatter_chunk splits over its threads)
+
                 def __setitem__(self, idx, val):
-                    _, its = idx
-                    for lc, c in enumerate(cs):
-                        results[c][self.key][its] = val[lc]
+                    chs, its = idx               # (slice of the group's chains, slice of iterations)
+                    for j, lc in enumerate(range(*chs.indices(len(cs)))):
+                        results[cs[lc]][self.key][its] = val[j]
 
             dest = {k: (_Dest(k) if (k in ("signal_ps", "ln_post") or results[cs[0]][k] is not None) else None)
                     for k in ("signal_ps", "ln_post", "signal_cr", "fg_amps", "chisq")}
