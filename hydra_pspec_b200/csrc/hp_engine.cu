@@ -1548,8 +1548,11 @@ int hp_engine_read(hp_engine* e, int c, int buffer, int iter0, int niter, void* 
             if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
             if (!e->last_sf) return fail(HP_ERR_ARG, "no GCR solve has run yet");
             src = e->last_sf + 2 * (size_t)c * e->last_sf_bs; bytes = T * n * 16; break;
-        case HP_BUF_PS_CUR: src = e->ps + (size_t)c * n; bytes = n * 8; break;
+        case HP_BUF_PS_CUR:
+            if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
+            src = e->ps + (size_t)c * n; bytes = n * 8; break;
         case HP_BUF_LAST_FG: {
+            if (e->ahead > 0) return fail(HP_ERR_ARG, kAheadMsg);
             bytes = T * m * 16;
             if (dst_bytes < bytes) return fail(HP_ERR_ARG, "destination too small");
             if (m == 0) return HP_OK;
